@@ -1,0 +1,1197 @@
+// fw_api.cu -- host side of libfirework_b200.so: the C ABI of include/firework_b200.h.
+//
+// What lives here is the part of the reference's two systems that is inherently sequential
+// host logic -- which emitters are enabled, emission pacing (reference src/core.rs:396-428,
+// 553-575), OneShot/OnDemand bookkeeping, the finished condition (:674-688) -- plus the
+// management of device memory. Everything per-particle runs in fw_kernels.cu.
+//
+// There is no CPU fallback: every entry point needs a live CUDA context.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "fw_internal.h"
+
+using namespace fw;
+
+namespace {
+
+thread_local std::string g_global_error;
+
+constexpr uint32_t kRing = 4; // frames in flight (pinned parameter blocks + state readbacks)
+
+struct Emitter {
+    fw_emission_settings es;
+    float last_emission = 0.f;
+    float time_passed_in_cycle = 0.f;
+    bool enabled = true;
+    bool emits_on_other_particles = false;
+    uint64_t serial = 0;   // particles spawned since reset (RNG protocol)
+    uint32_t dev_idx = 0;  // index into the device emitter array
+};
+
+struct Block { // one device allocation holding the four arrays of a stream
+    void *base = nullptr;
+    uint32_t capacity = 0;
+};
+
+struct Stream {
+    uint32_t slot = 0;
+    uint32_t type = 0;
+    Block block;
+    uint32_t variant = kFifo;
+    uint64_t n_hi = 0;        // host-side upper bound of the live count
+    uint64_t born_frame = 0;  // readbacks of older frames do not describe this stream
+    fw_particle_settings ps;
+};
+
+struct Spawner {
+    uint32_t key = 0;
+    std::vector<Stream> streams; // one per particle type
+    std::vector<Emitter> emitters;
+    SpawnerInput input;
+    uint64_t manual_queued_count = 0;
+    bool initialized = false;
+    bool finished_notified = false;
+};
+
+struct FrameSlot {
+    uint8_t *host = nullptr; // pinned
+    uint8_t *dev = nullptr;
+    size_t bytes = 0;
+    StreamState *states_host = nullptr; // pinned readback of all stream states after the frame
+    uint32_t states_slots = 0;
+    PlanOut *plan_host = nullptr; // pinned readback of the plan kernel's output
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+    uint64_t frame = 0;
+    std::vector<uint32_t> spawn_per_slot; // host copy, for the n_hi bound
+    // profiling
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool profiled = false;
+    uint64_t particles_spawned = 0;
+    uint32_t launches = 0;
+};
+
+} // namespace
+
+struct fw_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    uint64_t seed = 0;
+    uint32_t flags = 0;
+    std::string error;
+
+    std::vector<std::unique_ptr<Spawner>> spawners; // creation order
+    std::unordered_map<uint32_t, Spawner *> by_key;
+
+    // device tables
+    uint32_t slots_cap = 0, n_slots = 0; // n_slots = high-water mark of used slots
+    std::vector<uint32_t> free_slots;
+    std::vector<Stream *> slot_owner;
+    StreamDesc *d_descs = nullptr;
+    StreamState *d_states = nullptr;
+    DevParticleSettings *d_settings = nullptr;
+    std::vector<StreamDesc> h_descs;
+    uint32_t emitters_cap = 0, n_emitters = 0;
+    std::vector<uint32_t> free_emitters;
+    fw_emission_settings *d_emitters = nullptr;
+    fw_collider *d_colliders = nullptr;
+    uint32_t n_colliders = 0;
+    TileEntry *d_tiles = nullptr;
+    unsigned long long *d_lookback = nullptr;
+    uint32_t tiles_cap = 0;
+    uint64_t tiles_needed = 0; // sum over streams of ceil(capacity / kTile)
+    PlanOut *d_plan = nullptr;
+    uint32_t device_error_flags = 0; // accumulated from the per-frame plan readbacks
+    unsigned long long *d_pack = nullptr; // n_rows + per-slot offsets
+    uint32_t pack_cap = 0;
+    unsigned long long *h_pack = nullptr; // pinned
+
+    std::map<uint32_t, std::vector<void *>> block_cache; // capacity -> free device blocks
+    FrameSlot ring[kRing];
+    uint64_t frame_no = 0; // frames submitted so far; epoch of the next frame = frame_no + 1
+    int grids[kNumVariants] = {0, 0, 0, 0};
+    uint32_t variant_streams[kNumVariants] = {0, 0, 0, 0};
+
+    // profile accumulators
+    fw_frame_profile prof_last{};
+    fw_frame_profile prof_sum{};
+    uint32_t prof_frames = 0;
+    // last exact state snapshot (valid after refresh_exact)
+    std::vector<StreamState> snapshot;
+};
+
+namespace {
+
+int fail(fw_context *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    g_global_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? FW_ERR_OUT_OF_MEMORY : FW_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+inline int enter(fw_context *ctx) {
+    if (!ctx) return fail(nullptr, FW_ERR_INVALID_ARGUMENT, "null context");
+    cudaError_t e = cudaSetDevice(ctx->device); // callable from any thread
+    if (e != cudaSuccess) return fail(ctx, FW_ERR_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    return FW_OK;
+}
+#define ENTER(ctx)                      \
+    do {                                \
+        int rc__ = enter(ctx);          \
+        if (rc__ != FW_OK) return rc__; \
+    } while (0)
+
+// ---- Rust f32 helpers used by emission pacing (core::f32::rem_euclid / div_euclid, `as usize`)
+inline float rem_euclid_f32(float a, float b) {
+    const float r = std::fmod(a, b);
+    return r < 0.0f ? r + std::fabs(b) : r;
+}
+inline float div_euclid_f32(float a, float b) {
+    const float q = std::trunc(a / b);
+    if (std::fmod(a, b) < 0.0f) return b > 0.0f ? q - 1.0f : q + 1.0f;
+    return q;
+}
+inline uint64_t f32_as_usize(float f) {
+    if (!(f > 0.0f)) return 0;
+    if (f >= 18446744073709551616.0f) return UINT64_MAX;
+    return (uint64_t)f;
+}
+// reference src/core.rs:553-575 compute_emission_count
+inline void compute_emission_count(float time_passed_in_cycle, float last_emission, float cycle_duration,
+                                   float offset_start, float offset_end, float particles_per_cycle,
+                                   uint64_t &times, float &next_last_emission) {
+    const float percent_passed = time_passed_in_cycle / cycle_duration;
+    const float last_emission_percent = last_emission / cycle_duration;
+    const float lo = std::fmax(last_emission_percent, offset_start);
+    const float percent_passed_since_emission = std::fmin(percent_passed, offset_end) - lo;
+    const float percent_between_emissions = (offset_end - offset_start) / particles_per_cycle;
+    const float times_needed_to_emit = div_euclid_f32(percent_passed_since_emission, percent_between_emissions);
+    times = f32_as_usize(times_needed_to_emit);
+    const float next_last_emission_percent = lo + times_needed_to_emit * percent_between_emissions;
+    next_last_emission = next_last_emission_percent * cycle_duration;
+}
+
+inline bool is_fifo(uint32_t v) { return v == kFifo || v == kFifoCollide; }
+
+inline uint32_t round_capacity(uint64_t want) {
+    // round up so that freed blocks are reusable: multiples of 1024 up to 64 Ki, then 1/8-octave
+    if (want < 1024) want = 1024;
+    if (want <= 65536) return (uint32_t)((want + 1023) / 1024 * 1024);
+    uint64_t p = 65536;
+    while (p * 2 <= want) p *= 2;
+    const uint64_t step = p / 8;
+    uint64_t r = (want + step - 1) / step * step;
+    if (r > 0xFFFFFF00ull) r = 0xFFFFFF00ull;
+    return (uint32_t)r;
+}
+inline size_t block_bytes(uint32_t cap) { return (size_t)cap * 100u; }
+inline void block_arrays(const Block &b, StreamDesc &d) {
+    uint8_t *p = (uint8_t *)b.base;
+    d.rows = (float4 *)p;
+    d.s0 = (float4 *)(p + (size_t)b.capacity * 64u);
+    d.s1 = (float4 *)(p + (size_t)b.capacity * 80u);
+    d.s2 = (float *)(p + (size_t)b.capacity * 96u);
+    d.capacity = b.capacity;
+}
+
+int alloc_block(fw_context *ctx, uint32_t capacity, Block &out) {
+    auto it = ctx->block_cache.find(capacity);
+    if (it != ctx->block_cache.end() && !it->second.empty()) {
+        out.base = it->second.back();
+        it->second.pop_back();
+        out.capacity = capacity;
+        return FW_OK;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, block_bytes(capacity));
+    if (e != cudaSuccess) {
+        // drop the cache and retry once
+        for (auto &kv : ctx->block_cache)
+            for (void *q : kv.second) cudaFree(q);
+        ctx->block_cache.clear();
+        (void)cudaGetLastError();
+        e = cudaMalloc(&p, block_bytes(capacity));
+    }
+    if (e != cudaSuccess) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "cudaMalloc of a %u-particle stream failed: %s", capacity, cudaGetErrorString(e));
+    out.base = p;
+    out.capacity = capacity;
+    return FW_OK;
+}
+void release_block(fw_context *ctx, Block &b) {
+    // all work is ordered on one CUDA stream, so a cached block can be handed out again at once
+    if (b.base) ctx->block_cache[b.capacity].push_back(b.base);
+    b.base = nullptr;
+    b.capacity = 0;
+}
+
+template <typename T>
+int grow_device_array(fw_context *ctx, T *&ptr, uint32_t old_n, uint32_t new_n) {
+    T *np = nullptr;
+    CU(ctx, cudaMalloc((void **)&np, sizeof(T) * (size_t)new_n));
+    CU(ctx, cudaMemsetAsync(np, 0, sizeof(T) * (size_t)new_n, ctx->stream));
+    if (ptr && old_n) CU(ctx, cudaMemcpyAsync(np, ptr, sizeof(T) * (size_t)old_n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ptr) CU(ctx, cudaFree(ptr));
+    ptr = np;
+    return FW_OK;
+}
+
+int ensure_slots(fw_context *ctx, uint32_t need) {
+    if (need <= ctx->slots_cap) return FW_OK;
+    uint32_t ncap = std::max(1024u, ctx->slots_cap * 2);
+    while (ncap < need) ncap *= 2;
+    int rc;
+    if ((rc = grow_device_array(ctx, ctx->d_descs, ctx->slots_cap, ncap))) return rc;
+    if ((rc = grow_device_array(ctx, ctx->d_states, ctx->slots_cap, ncap))) return rc;
+    if ((rc = grow_device_array(ctx, ctx->d_settings, ctx->slots_cap, ncap))) return rc;
+    ctx->h_descs.resize(ncap);
+    ctx->slot_owner.resize(ncap, nullptr);
+    ctx->slots_cap = ncap;
+    return FW_OK;
+}
+int ensure_emitters(fw_context *ctx, uint32_t need) {
+    if (need <= ctx->emitters_cap) return FW_OK;
+    uint32_t ncap = std::max(1024u, ctx->emitters_cap * 2);
+    while (ncap < need) ncap *= 2;
+    int rc = grow_device_array(ctx, ctx->d_emitters, ctx->emitters_cap, ncap);
+    if (rc) return rc;
+    ctx->emitters_cap = ncap;
+    return FW_OK;
+}
+int ensure_tiles(fw_context *ctx) {
+    const uint64_t need = ctx->tiles_needed + 16;
+    if (need <= ctx->tiles_cap) return FW_OK;
+    uint64_t ncap = std::max<uint64_t>(4096, (uint64_t)ctx->tiles_cap * 2);
+    while (ncap < need) ncap *= 2;
+    if (ncap > 0xFFFFFFFFull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "tile table too large");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_tiles) CU(ctx, cudaFree(ctx->d_tiles));
+    if (ctx->d_lookback) CU(ctx, cudaFree(ctx->d_lookback));
+    ctx->d_tiles = nullptr;
+    ctx->d_lookback = nullptr;
+    CU(ctx, cudaMalloc((void **)&ctx->d_tiles, sizeof(TileEntry) * ncap));
+    CU(ctx, cudaMalloc((void **)&ctx->d_lookback, sizeof(unsigned long long) * ncap));
+    CU(ctx, cudaMemsetAsync(ctx->d_lookback, 0, sizeof(unsigned long long) * ncap, ctx->stream));
+    ctx->tiles_cap = (uint32_t)ncap;
+    return FW_OK;
+}
+
+uint32_t pick_variant(const fw_particle_settings &ps) {
+    const bool collide = ps.collision.enabled != 0;
+    // deaths are a prefix of the Vec iff every particle has the same lifetime (ages are
+    // monotone in Vec order) and nothing else can kill a particle
+    const bool fifo = (ps.lifetime.min == ps.lifetime.max) && !(collide && ps.collision.destroy_on_collision) &&
+                      !ps.capture_destroyed;
+    if (fifo) return collide ? kFifoCollide : kFifo;
+    return collide ? kCompactCollide : kCompact;
+}
+
+void fill_dev_settings(const fw_particle_settings &ps, DevParticleSettings &d) {
+    memset(&d, 0, sizeof(d));
+    d.scale_curve = ps.scale_curve;
+    d.base_color = ps.base_color;
+    d.emissive_color = ps.emissive_color;
+    memcpy(d.acceleration, ps.acceleration, sizeof(float) * 3);
+    d.linear_drag = ps.linear_drag;
+    memcpy(d.angular_acceleration, ps.angular_acceleration, sizeof(float) * 3);
+    d.angular_drag = ps.angular_drag;
+    d.collision = ps.collision;
+    d.lifetime = ps.lifetime;
+    d.initial_scale = ps.initial_scale;
+}
+
+int validate_curve(fw_context *ctx, uint32_t kind, uint32_t n, const float *times, const char *what) {
+    if (kind > FW_CURVE_UNEVEN) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "%s: unknown curve kind %u", what, kind);
+    if (kind == FW_CURVE_CONSTANT) {
+        if (n < 1) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "%s: Cannot create curve from 0 samples", what);
+        return FW_OK;
+    }
+    if (n < 2 || n > FW_MAX_KNOTS) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "%s: %u samples (need 2..%u)", what, n, FW_MAX_KNOTS);
+    if (kind == FW_CURVE_UNEVEN)
+        for (uint32_t i = 0; i < n; i++) {
+            if (!std::isfinite(times[i])) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "%s: non-finite sample time", what);
+            if (i && !(times[i] > times[i - 1])) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "%s: sample times must be strictly increasing", what);
+        }
+    return FW_OK;
+}
+
+uint64_t estimate_capacity(const Spawner &sp, uint32_t type) {
+    const fw_particle_settings &ps = sp.streams[type].ps;
+    if (ps.capacity_hint) return ps.capacity_hint;
+    double est = 0.0;
+    const double life = std::max(0.0f, std::max(ps.lifetime.min, ps.lifetime.max));
+    for (const Emitter &e : sp.emitters) {
+        if (e.es.particle_index != type) continue;
+        if (e.es.pacing_kind == FW_PACING_ONE_SHOT) est += (double)e.es.one_shot_count;
+        else if (e.es.pacing_kind == FW_PACING_COUNT_OVER_DURATION && e.es.duration > 0.f && e.es.mode == FW_MODE_GLOBAL)
+            est += (double)e.es.count / e.es.duration * (life + 0.05) * 1.02 + 64.0;
+        else est += 1024.0;
+    }
+    if (est > 268435456.0) est = 268435456.0;
+    return (uint64_t)est + 256;
+}
+
+void free_stream(fw_context *ctx, Stream &st) {
+    ctx->tiles_needed -= (st.block.capacity + kTile - 1) / kTile;
+    ctx->variant_streams[st.variant]--;
+    release_block(ctx, st.block);
+    StreamDesc zero{};
+    ctx->h_descs[st.slot] = zero;
+    cudaMemcpyAsync(ctx->d_descs + st.slot, &zero, sizeof(zero), cudaMemcpyHostToDevice, ctx->stream);
+    ctx->slot_owner[st.slot] = nullptr;
+    ctx->free_slots.push_back(st.slot);
+}
+void free_spawner_resources(fw_context *ctx, Spawner &sp) {
+    for (Stream &st : sp.streams) free_stream(ctx, st);
+    for (Emitter &e : sp.emitters) ctx->free_emitters.push_back(e.dev_idx);
+    sp.streams.clear();
+    sp.emitters.clear();
+}
+
+int upload_desc(fw_context *ctx, const Stream &st) {
+    StreamDesc d{};
+    block_arrays(st.block, d);
+    d.settings_idx = st.slot;
+    d.variant = st.variant;
+    ctx->h_descs[st.slot] = d;
+    CU(ctx, cudaMemcpyAsync(ctx->d_descs + st.slot, &d, sizeof(d), cudaMemcpyHostToDevice, ctx->stream));
+    return FW_OK;
+}
+
+// wait for everything, read all stream states, make n_hi exact
+int refresh_exact(fw_context *ctx) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (FrameSlot &fs : ctx->ring) fs.in_flight = false;
+    ctx->snapshot.resize(ctx->n_slots);
+    if (ctx->n_slots)
+        CU(ctx, cudaMemcpy(ctx->snapshot.data(), ctx->d_states, sizeof(StreamState) * ctx->n_slots, cudaMemcpyDeviceToHost));
+    for (uint32_t s = 0; s < ctx->n_slots; s++)
+        if (Stream *st = ctx->slot_owner[s]) st->n_hi = ctx->snapshot[s].count - ctx->snapshot[s].dead;
+    return FW_OK;
+}
+
+// consume finished asynchronous state readbacks to tighten the n_hi bounds without a sync
+void poll_readbacks(fw_context *ctx) {
+    uint64_t newest = 0;
+    FrameSlot *best = nullptr;
+    for (FrameSlot &fs : ctx->ring) {
+        if (!fs.in_flight) continue;
+        if (cudaEventQuery(fs.done) == cudaSuccess) {
+            fs.in_flight = false;
+            if (fs.frame >= newest) { newest = fs.frame; best = &fs; }
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
+    if (!best) return;
+    const uint32_t n = std::min(best->states_slots, ctx->n_slots);
+    for (uint32_t s = 0; s < n; s++) {
+        Stream *st = ctx->slot_owner[s];
+        if (!st || st->born_frame > best->frame) continue;
+        uint64_t bound = best->states_host[s].count - best->states_host[s].dead;
+        for (const FrameSlot &g : ctx->ring)
+            if (g.frame > best->frame && g.frame <= ctx->frame_no && s < g.spawn_per_slot.size()) bound += g.spawn_per_slot[s];
+        if (bound < st->n_hi) st->n_hi = bound;
+    }
+}
+
+int grow_stream(fw_context *ctx, Stream &st, uint64_t need) {
+    // exact state is in ctx->snapshot (refresh_exact was just called)
+    const StreamState s = ctx->snapshot[st.slot];
+    const uint32_t live = s.count - s.dead;
+    const uint32_t first = (s.head + (is_fifo(st.variant) ? s.dead : 0u)) % std::max(1u, st.block.capacity);
+    const uint32_t ncap = round_capacity(std::max<uint64_t>(need + need / 4, (uint64_t)st.block.capacity * 2));
+    if ((uint64_t)ncap < need) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "stream would exceed 2^32 particles");
+    Block nb;
+    int rc = alloc_block(ctx, ncap, nb);
+    if (rc) return rc;
+    StreamDesc od{}, nd{};
+    block_arrays(st.block, od);
+    block_arrays(nb, nd);
+    const uint32_t seg1 = std::min(live, st.block.capacity - first), seg2 = live - seg1;
+    auto copy = [&](void *dst, const void *src, size_t elem) -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        if (seg1) e = cudaMemcpyAsync(dst, (const uint8_t *)src + (size_t)first * elem, (size_t)seg1 * elem, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess && seg2) e = cudaMemcpyAsync((uint8_t *)dst + (size_t)seg1 * elem, src, (size_t)seg2 * elem, cudaMemcpyDeviceToDevice, ctx->stream);
+        return e;
+    };
+    CU(ctx, copy(nd.rows, od.rows, 64));
+    CU(ctx, copy(nd.s0, od.s0, 16));
+    CU(ctx, copy(nd.s1, od.s1, 16));
+    CU(ctx, copy(nd.s2, od.s2, 4));
+    StreamState ns = s;
+    ns.head = 0;
+    ns.count = live;
+    ns.dead = 0;
+    CU(ctx, cudaMemcpyAsync(ctx->d_states + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->snapshot[st.slot] = ns;
+    ctx->tiles_needed -= (st.block.capacity + kTile - 1) / kTile;
+    release_block(ctx, st.block);
+    st.block = nb;
+    ctx->tiles_needed += (ncap + kTile - 1) / kTile;
+    return upload_desc(ctx, st);
+}
+
+int ensure_frame_slot(fw_context *ctx, FrameSlot &fs, size_t bytes) {
+    if (bytes > fs.bytes) {
+        size_t nb = std::max<size_t>(bytes * 2, 1 << 16);
+        if (fs.host) CU(ctx, cudaFreeHost(fs.host));
+        if (fs.dev) CU(ctx, cudaFree(fs.dev));
+        fs.host = nullptr;
+        fs.dev = nullptr;
+        CU(ctx, cudaMallocHost((void **)&fs.host, nb));
+        CU(ctx, cudaMalloc((void **)&fs.dev, nb));
+        fs.bytes = nb;
+    }
+    if (fs.states_slots < ctx->slots_cap) {
+        if (fs.states_host) CU(ctx, cudaFreeHost(fs.states_host));
+        fs.states_host = nullptr;
+        CU(ctx, cudaMallocHost((void **)&fs.states_host, sizeof(StreamState) * ctx->slots_cap));
+        fs.states_slots = ctx->slots_cap;
+    }
+    return FW_OK;
+}
+
+void absorb_profile(fw_context *ctx, FrameSlot &fs) {
+    if (!fs.profiled) return;
+    fs.profiled = false;
+    fw_frame_profile p{};
+    cudaEventElapsedTime(&p.plan_ms, fs.ev[0], fs.ev[1]);
+    cudaEventElapsedTime(&p.spawn_ms, fs.ev[1], fs.ev[2]);
+    cudaEventElapsedTime(&p.update_ms, fs.ev[2], fs.ev[3]);
+    cudaEventElapsedTime(&p.total_ms, fs.ev[0], fs.ev[3]);
+    p.kernel_launches = fs.launches;
+    p.particles_spawned = fs.particles_spawned;
+    p.particles_updated = fs.plan_host ? fs.plan_host->total_update : 0;
+    ctx->prof_last = p;
+    ctx->prof_sum.plan_ms += p.plan_ms;
+    ctx->prof_sum.spawn_ms += p.spawn_ms;
+    ctx->prof_sum.update_ms += p.update_ms;
+    ctx->prof_sum.total_ms += p.total_ms;
+    ctx->prof_sum.kernel_launches += p.kernel_launches;
+    ctx->prof_sum.particles_spawned += p.particles_spawned;
+    ctx->prof_sum.particles_updated += p.particles_updated;
+    ctx->prof_frames++;
+}
+
+// ParticleSpawnerData::active (reference src/core.rs:288-302); any_particles only matters for
+// nested emitters
+bool spawner_active(const Spawner &sp, bool any_particles) {
+    bool enabled = false;
+    for (const Emitter &e : sp.emitters) {
+        if (e.emits_on_other_particles) enabled |= (e.enabled && any_particles);
+        else enabled |= e.enabled;
+    }
+    return enabled;
+}
+
+Spawner *find(fw_context *ctx, uint32_t key) {
+    auto it = ctx->by_key.find(key);
+    return it == ctx->by_key.end() ? nullptr : it->second;
+}
+
+// stream rows -> host arrays (ring unwrapped), after a sync
+int read_stream_arrays(fw_context *ctx, const Stream &st, std::vector<float> &rows, std::vector<float> &s0,
+                       std::vector<float> &s1, std::vector<float> &s2, uint32_t &live) {
+    int rc = refresh_exact(ctx);
+    if (rc) return rc;
+    const StreamState s = ctx->snapshot[st.slot];
+    live = s.count - s.dead;
+    const uint32_t cap = st.block.capacity;
+    const uint32_t first = (s.head + (is_fifo(st.variant) ? s.dead : 0u)) % std::max(1u, cap);
+    rows.resize((size_t)live * 16);
+    s0.resize((size_t)live * 4);
+    s1.resize((size_t)live * 4);
+    s2.resize(live);
+    if (!live) return FW_OK;
+    StreamDesc d{};
+    block_arrays(st.block, d);
+    const uint32_t seg1 = std::min(live, cap - first), seg2 = live - seg1;
+    auto copy = [&](void *dst, const void *src, size_t elem) -> cudaError_t {
+        cudaError_t e = cudaMemcpy(dst, (const uint8_t *)src + (size_t)first * elem, (size_t)seg1 * elem, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && seg2) e = cudaMemcpy((uint8_t *)dst + (size_t)seg1 * elem, src, (size_t)seg2 * elem, cudaMemcpyDeviceToHost);
+        return e;
+    };
+    CU(ctx, copy(rows.data(), d.rows, 64));
+    CU(ctx, copy(s0.data(), d.s0, 16));
+    CU(ctx, copy(s1.data(), d.s1, 16));
+    CU(ctx, copy(s2.data(), d.s2, 4));
+    return FW_OK;
+}
+
+inline float dec_f32(uint32_t u) {
+    const uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+
+} // namespace
+
+// =============================================================================== exports
+extern "C" {
+
+const char *fw_last_global_error(void) { return g_global_error.c_str(); }
+const char *fw_last_error(const fw_context *ctx) { return ctx ? ctx->error.c_str() : g_global_error.c_str(); }
+uint32_t fw_abi_version(void) { return FW_ABI_VERSION; }
+
+uint32_t fw_abi_sizeof(const char *name) {
+    if (!name) return 0;
+#define SZ(T) \
+    if (!strcmp(name, #T)) return (uint32_t)sizeof(T);
+    SZ(fw_rand_f32) SZ(fw_rand_vec3) SZ(fw_curve_f32) SZ(fw_gradient) SZ(fw_collision_settings)
+    SZ(fw_particle_settings) SZ(fw_emission_settings) SZ(fw_spawner_frame_input) SZ(fw_particle_data)
+    SZ(fw_particle_instance) SZ(fw_collider) SZ(fw_config) SZ(fw_spawner_status) SZ(fw_frame_profile)
+#undef SZ
+    return 0;
+}
+
+int fw_create(const fw_config *cfg, fw_context **out_ctx) {
+    if (!cfg || !out_ctx) return fail(nullptr, FW_ERR_INVALID_ARGUMENT, "fw_create: null argument");
+    *out_ctx = nullptr;
+    if (cfg->abi_version != FW_ABI_VERSION) return fail(nullptr, FW_ERR_INVALID_ARGUMENT, "fw_create: ABI version %u, library is %u", cfg->abi_version, FW_ABI_VERSION);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, FW_ERR_NO_DEVICE, "fw_create: no CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, FW_ERR_INVALID_ARGUMENT, "fw_create: device %d out of range (0..%d)", cfg->device, n_dev - 1);
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(nullptr, FW_ERR_NO_DEVICE, "fw_create: device %d is sm_%d%d; this build carries sm_100a code only", cfg->device, prop.major, prop.minor);
+    std::unique_ptr<fw_context> ctx(new fw_context());
+    ctx->device = cfg->device;
+    ctx->seed = cfg->seed;
+    ctx->flags = cfg->flags;
+    CU(nullptr, cudaSetDevice(cfg->device));
+    if (cfg->external_stream) {
+        ctx->stream = (cudaStream_t)cfg->external_stream;
+    } else {
+        CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->owns_stream = true;
+    }
+    fw_context *c = ctx.get();
+    CU(c, cudaMalloc((void **)&c->d_plan, sizeof(PlanOut)));
+    CU(c, cudaMemsetAsync(c->d_plan, 0, sizeof(PlanOut), c->stream));
+    for (FrameSlot &fs : c->ring) {
+        CU(c, cudaMallocHost((void **)&fs.plan_host, sizeof(PlanOut)));
+        memset(fs.plan_host, 0, sizeof(PlanOut));
+        CU(c, cudaEventCreateWithFlags(&fs.done, cudaEventDisableTiming));
+        for (auto &ev : fs.ev) CU(c, cudaEventCreate(&ev));
+    }
+    int rc;
+    if ((rc = ensure_slots(c, 1))) { g_global_error = c->error; return rc; }
+    if ((rc = ensure_emitters(c, 1))) { g_global_error = c->error; return rc; }
+    if ((rc = ensure_tiles(c))) { g_global_error = c->error; return rc; }
+    CU(c, update_grid_size(c->device, c->grids));
+    *out_ctx = ctx.release();
+    return FW_OK;
+}
+
+int fw_destroy(fw_context *ctx) {
+    if (!ctx) return FW_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &sp : ctx->spawners)
+        for (Stream &st : sp->streams)
+            if (st.block.base) cudaFree(st.block.base);
+    for (auto &kv : ctx->block_cache)
+        for (void *p : kv.second) cudaFree(p);
+    for (FrameSlot &fs : ctx->ring) {
+        if (fs.host) cudaFreeHost(fs.host);
+        if (fs.dev) cudaFree(fs.dev);
+        if (fs.states_host) cudaFreeHost(fs.states_host);
+        if (fs.plan_host) cudaFreeHost(fs.plan_host);
+        if (fs.done) cudaEventDestroy(fs.done);
+        for (auto &ev : fs.ev)
+            if (ev) cudaEventDestroy(ev);
+    }
+    cudaFree(ctx->d_descs);
+    cudaFree(ctx->d_states);
+    cudaFree(ctx->d_settings);
+    cudaFree(ctx->d_emitters);
+    cudaFree(ctx->d_colliders);
+    cudaFree(ctx->d_tiles);
+    cudaFree(ctx->d_lookback);
+    cudaFree(ctx->d_plan);
+    cudaFree(ctx->d_pack);
+    if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return FW_OK;
+}
+
+int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *ps, uint32_t n_types,
+                     const fw_emission_settings *es, uint32_t n_emitters, uint32_t starts_enabled) {
+    ENTER(ctx);
+    if ((n_types && !ps) || (n_emitters && !es)) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_spawner_reset: null settings");
+    // validate before touching any state (the reference panics at curve construction,
+    // src/curve.rs:45,50,61,67; here the call fails and leaves the spawner as it was)
+    for (uint32_t i = 0; i < n_types; i++) {
+        int rc;
+        if ((rc = validate_curve(ctx, ps[i].scale_curve.kind, ps[i].scale_curve.n, ps[i].scale_curve.times, "scale_curve"))) return rc;
+        if ((rc = validate_curve(ctx, ps[i].base_color.kind, ps[i].base_color.n, ps[i].base_color.times, "base_color"))) return rc;
+        if ((rc = validate_curve(ctx, ps[i].emissive_color.kind, ps[i].emissive_color.n, ps[i].emissive_color.times, "emissive_color"))) return rc;
+    }
+    for (uint32_t i = 0; i < n_emitters; i++) {
+        if (es[i].particle_index >= n_types) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "emitter %u: particle_index %u out of range", i, es[i].particle_index);
+        if (es[i].pacing_kind > FW_PACING_COUNT_OVER_DURATION) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "emitter %u: unknown pacing", i);
+        if (es[i].shape_kind > FW_SHAPE_CIRCLE) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "emitter %u: unknown shape", i);
+        if (es[i].mode == FW_MODE_NESTED) return fail(ctx, FW_ERR_UNSUPPORTED, "emitter %u: EmissionMode::Nested is not implemented yet", i);
+        if (es[i].mode > FW_MODE_NESTED) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "emitter %u: unknown emission mode", i);
+    }
+    Spawner *sp = find(ctx, key);
+    if (!sp) {
+        ctx->spawners.emplace_back(new Spawner());
+        sp = ctx->spawners.back().get();
+        sp->key = key;
+        memset(&sp->input, 0, sizeof(sp->input));
+        sp->input.rotation[3] = 1.0f;
+        sp->input.modifier_scale = 1.0f;
+        sp->input.modifier_speed = 1.0f;
+        ctx->by_key[key] = sp;
+    } else {
+        free_spawner_resources(ctx, *sp); // data.particles = vec![Vec::new(); n]  (src/core.rs:360)
+    }
+    sp->initialized = true; // :361-363
+    sp->emitters.resize(n_emitters);
+    for (uint32_t i = 0; i < n_emitters; i++) { // :347-359
+        Emitter &e = sp->emitters[i];
+        e.es = es[i];
+        e.last_emission = 0.f;
+        e.time_passed_in_cycle = 0.f;
+        e.enabled = starts_enabled != 0;
+        e.emits_on_other_particles = es[i].mode == FW_MODE_NESTED;
+        e.serial = 0;
+        if (!ctx->free_emitters.empty()) {
+            e.dev_idx = ctx->free_emitters.back();
+            ctx->free_emitters.pop_back();
+        } else {
+            int rc = ensure_emitters(ctx, ctx->n_emitters + 1);
+            if (rc) return rc;
+            e.dev_idx = ctx->n_emitters++;
+        }
+        CU(ctx, cudaMemcpyAsync(ctx->d_emitters + e.dev_idx, &es[i], sizeof(fw_emission_settings), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    sp->streams.resize(n_types);
+    for (uint32_t t = 0; t < n_types; t++) {
+        Stream &st = sp->streams[t];
+        st.type = t;
+        st.ps = ps[t];
+        st.variant = pick_variant(ps[t]);
+        st.n_hi = 0;
+        st.born_frame = ctx->frame_no + 1;
+    }
+    for (uint32_t t = 0; t < n_types; t++) {
+        Stream &st = sp->streams[t];
+        if (!ctx->free_slots.empty()) {
+            st.slot = ctx->free_slots.back();
+            ctx->free_slots.pop_back();
+        } else {
+            int rc = ensure_slots(ctx, ctx->n_slots + 1);
+            if (rc) return rc;
+            st.slot = ctx->n_slots++;
+        }
+        int rc = alloc_block(ctx, round_capacity(estimate_capacity(*sp, t)), st.block);
+        if (rc) return rc;
+        ctx->tiles_needed += (st.block.capacity + kTile - 1) / kTile;
+        ctx->variant_streams[st.variant]++;
+        ctx->slot_owner[st.slot] = &st;
+        DevParticleSettings ds;
+        fill_dev_settings(ps[t], ds);
+        CU(ctx, cudaMemcpyAsync(ctx->d_settings + st.slot, &ds, sizeof(ds), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemsetAsync(ctx->d_states + st.slot, 0, sizeof(StreamState), ctx->stream));
+        if ((rc = upload_desc(ctx, st))) return rc;
+    }
+    sp->finished_notified = false;
+    sp->manual_queued_count = 0;
+    return ensure_tiles(ctx);
+}
+
+int fw_spawner_remove(fw_context *ctx, uint32_t key) {
+    ENTER(ctx);
+    Spawner *sp = find(ctx, key);
+    if (!sp) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_spawner_remove: unknown spawner %u", key);
+    free_spawner_resources(ctx, *sp);
+    ctx->by_key.erase(key);
+    for (size_t i = 0; i < ctx->spawners.size(); i++)
+        if (ctx->spawners[i].get() == sp) {
+            ctx->spawners.erase(ctx->spawners.begin() + (long)i);
+            break;
+        }
+    return FW_OK;
+}
+
+int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) {
+    ENTER(ctx);
+    if (n && !colliders) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_set_colliders: null");
+    for (uint32_t i = 0; i < n; i++)
+        if (colliders[i].kind > FW_COLLIDER_SPHERE) return fail(ctx, FW_ERR_UNSUPPORTED, "collider %u: only cuboids and spheres are supported", i);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_colliders) CU(ctx, cudaFree(ctx->d_colliders));
+    ctx->d_colliders = nullptr;
+    ctx->n_colliders = n;
+    if (n) {
+        CU(ctx, cudaMalloc((void **)&ctx->d_colliders, sizeof(fw_collider) * n));
+        CU(ctx, cudaMemcpy(ctx->d_colliders, colliders, sizeof(fw_collider) * n, cudaMemcpyHostToDevice));
+    }
+    return FW_OK;
+}
+
+int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, uint32_t n_inputs) {
+    ENTER(ctx);
+    if (n_inputs && !inputs) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_frame: null inputs");
+    for (uint32_t k = 0; k < n_inputs; k++) {
+        Spawner *sp = find(ctx, inputs[k].spawner_key);
+        if (!sp) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_frame: unknown spawner %u", inputs[k].spawner_key);
+    }
+    for (uint32_t k = 0; k < n_inputs; k++) {
+        Spawner *sp = find(ctx, inputs[k].spawner_key);
+        memcpy(sp->input.translation, inputs[k].origin_translation, sizeof(float) * 3);
+        memcpy(sp->input.rotation, inputs[k].origin_rotation, sizeof(float) * 4);
+        memcpy(sp->input.parent_velocity, inputs[k].parent_velocity, sizeof(float) * 3);
+        sp->input.modifier_scale = inputs[k].modifier_scale;
+        sp->input.modifier_speed = inputs[k].modifier_speed;
+        sp->manual_queued_count += inputs[k].queue_particles; // src/core.rs:284-286
+    }
+    poll_readbacks(ctx);
+
+    FrameSlot &fs = ctx->ring[ctx->frame_no % kRing];
+    if (fs.in_flight) { // the host is kRing frames ahead: wait for that slot
+        CU(ctx, cudaEventSynchronize(fs.done));
+        fs.in_flight = false;
+    }
+    absorb_profile(ctx, fs);
+
+    // ---- spawn_particles, host part (reference src/core.rs:377-428)
+    std::vector<SpawnCmd> cmds;
+    std::vector<SpawnerInput> sinputs;
+    fs.spawn_per_slot.assign(ctx->n_slots, 0u);
+    uint64_t total_spawn = 0;
+    for (auto &spp : ctx->spawners) {
+        Spawner &sp = *spp;
+        if (!spawner_active(sp, true)) continue; // :378
+        int input_idx = -1;
+        for (uint32_t i = 0; i < sp.emitters.size(); i++) { // :386
+            Emitter &e = sp.emitters[i];
+            if (!e.enabled) continue; // :388-390
+            uint64_t n = 0;
+            if (e.es.pacing_kind == FW_PACING_ONE_SHOT) { // :397-400
+                e.enabled = false;
+                n = e.es.one_shot_count;
+            } else if (e.es.pacing_kind == FW_PACING_ON_DEMAND) { // :401-405
+                n = sp.manual_queued_count;
+                sp.manual_queued_count = 0;
+            } else { // :406-427
+                e.time_passed_in_cycle = rem_euclid_f32(e.time_passed_in_cycle + dt, e.es.duration);
+                float next_last;
+                compute_emission_count(e.time_passed_in_cycle, e.last_emission, e.es.duration, e.es.offset_start,
+                                       e.es.offset_end, e.es.count, n, next_last);
+                e.last_emission = next_last;
+            }
+            if (n == 0) continue;
+            Stream &st = sp.streams[e.es.particle_index];
+            if (n > 0xFFFFFF00ull - st.n_hi) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "spawner %u would exceed 2^32 particles in one stream", sp.key);
+            if (input_idx < 0) {
+                input_idx = (int)sinputs.size();
+                sinputs.push_back(sp.input);
+            }
+            SpawnCmd c{};
+            c.stream = st.slot;
+            c.emitter_idx = e.dev_idx;
+            c.input_idx = (uint32_t)input_idx;
+            c.count = (uint32_t)n;
+            c.first = (uint32_t)total_spawn;
+            c.dst_off = fs.spawn_per_slot[st.slot];
+            c.spawner_key = sp.key;
+            c.emitter_local = i;
+            c.serial_base = e.serial;
+            cmds.push_back(c);
+            e.serial += n;
+            fs.spawn_per_slot[st.slot] += (uint32_t)n;
+            total_spawn += n;
+            if (total_spawn > 0xFFFFFF00ull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "more than 2^32 particles spawned in one frame");
+        }
+    }
+    // ---- capacity: grow a ring before it could overflow (bounds first, exact state on demand)
+    bool exact = false;
+    for (const SpawnCmd &c : cmds) {
+        Stream *st = ctx->slot_owner[c.stream];
+        const uint64_t need = st->n_hi + fs.spawn_per_slot[c.stream];
+        if (need <= st->block.capacity) continue;
+        if (!exact) {
+            int rc = refresh_exact(ctx);
+            if (rc) return rc;
+            exact = true;
+        }
+        const uint64_t need2 = st->n_hi + fs.spawn_per_slot[c.stream];
+        if (need2 > st->block.capacity) {
+            int rc = grow_stream(ctx, *st, need2);
+            if (rc) return rc;
+        }
+    }
+    {
+        int rc = ensure_tiles(ctx);
+        if (rc) return rc;
+    }
+    for (uint32_t s = 0; s < ctx->n_slots; s++)
+        if (fs.spawn_per_slot[s]) ctx->slot_owner[s]->n_hi += fs.spawn_per_slot[s];
+
+    // ---- parameter block of the frame: header | spawn_per_slot | cmds | inputs
+    auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t off_spawn = align16(sizeof(FrameHeader));
+    const size_t off_cmds = align16(off_spawn + sizeof(uint32_t) * std::max(1u, ctx->n_slots));
+    const size_t off_inputs = align16(off_cmds + sizeof(SpawnCmd) * std::max<size_t>(1, cmds.size()));
+    const size_t bytes = align16(off_inputs + sizeof(SpawnerInput) * std::max<size_t>(1, sinputs.size()));
+    {
+        int rc = ensure_frame_slot(ctx, fs, bytes);
+        if (rc) return rc;
+    }
+    FrameHeader *h = (FrameHeader *)fs.host;
+    memset(h, 0, sizeof(*h));
+    h->dt = dt;
+    h->n_slots = ctx->n_slots;
+    h->n_cmds = (uint32_t)cmds.size();
+    h->total_spawn = (uint32_t)total_spawn;
+    h->epoch = (uint32_t)((ctx->frame_no + 1) & 0x3FFFFFFFu);
+    if (ctx->n_slots) memcpy(fs.host + off_spawn, fs.spawn_per_slot.data(), sizeof(uint32_t) * ctx->n_slots);
+    if (!cmds.empty()) memcpy(fs.host + off_cmds, cmds.data(), sizeof(SpawnCmd) * cmds.size());
+    if (!sinputs.empty()) memcpy(fs.host + off_inputs, sinputs.data(), sizeof(SpawnerInput) * sinputs.size());
+    CU(ctx, cudaMemcpyAsync(fs.dev, fs.host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+
+    DeviceTables t{};
+    t.descs = ctx->d_descs;
+    t.states = ctx->d_states;
+    t.settings = ctx->d_settings;
+    t.emitters = ctx->d_emitters;
+    t.colliders = ctx->d_colliders;
+    t.n_colliders = ctx->n_colliders;
+    t.tiles = ctx->d_tiles;
+    t.tiles_capacity = ctx->tiles_cap;
+    t.plan = ctx->d_plan;
+    t.lookback = ctx->d_lookback;
+    t.seed = ctx->seed;
+    FrameDeviceInputs f{};
+    f.header = (const FrameHeader *)fs.dev;
+    f.spawn_per_slot = (const uint32_t *)(fs.dev + off_spawn);
+    f.cmds = (const SpawnCmd *)(fs.dev + off_cmds);
+    f.inputs = (const SpawnerInput *)(fs.dev + off_inputs);
+
+    const bool prof = (ctx->flags & FW_FLAG_PROFILE) != 0;
+    uint32_t launches = 0;
+    if (prof) CU(ctx, cudaEventRecord(fs.ev[0], ctx->stream));
+    CU(ctx, launch_plan(t, f, ctx->stream));
+    launches++;
+    if (prof) CU(ctx, cudaEventRecord(fs.ev[1], ctx->stream));
+    if (total_spawn) {
+        CU(ctx, launch_spawn(t, f, (uint32_t)total_spawn, ctx->stream));
+        launches++;
+    }
+    if (prof) CU(ctx, cudaEventRecord(fs.ev[2], ctx->stream));
+    for (uint32_t v = 0; v < kNumVariants; v++) {
+        if (!ctx->variant_streams[v]) continue;
+        CU(ctx, launch_update(t, f, v, ctx->grids[v], ctx->stream));
+        launches++;
+    }
+    if (prof) CU(ctx, cudaEventRecord(fs.ev[3], ctx->stream));
+    // asynchronous readback of the stream states (bounds for the next frames) + plan output
+    if (ctx->n_slots) CU(ctx, cudaMemcpyAsync(fs.states_host, ctx->d_states, sizeof(StreamState) * ctx->n_slots, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(fs.plan_host, ctx->d_plan, sizeof(PlanOut), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaEventRecord(fs.done, ctx->stream));
+    ctx->frame_no++;
+    fs.in_flight = true;
+    fs.frame = ctx->frame_no;
+    fs.profiled = prof;
+    fs.launches = launches;
+    fs.particles_spawned = total_spawn;
+    return FW_OK;
+}
+
+int fw_sync(fw_context *ctx) {
+    ENTER(ctx);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (FrameSlot &fs : ctx->ring) {
+        ctx->device_error_flags |= fs.plan_host->error_flags;
+        fs.plan_host->error_flags = 0;
+    }
+    if (ctx->device_error_flags) {
+        const uint32_t fl = ctx->device_error_flags;
+        ctx->device_error_flags = 0;
+        cudaMemsetAsync(&ctx->d_plan->error_flags, 0, sizeof(uint32_t), ctx->stream);
+        return fail(ctx, FW_ERR_INTERNAL, "device reported error flags 0x%x (1 = ring overflow, 2 = tile table overflow)", fl);
+    }
+    return FW_OK;
+}
+
+int fw_counts(fw_context *ctx, uint32_t key, uint32_t *out, uint32_t n_types) {
+    ENTER(ctx);
+    Spawner *sp = find(ctx, key);
+    if (!sp) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_counts: unknown spawner %u", key);
+    if (n_types < sp->streams.size() || !out) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_counts: need room for %zu counts", sp->streams.size());
+    int rc = refresh_exact(ctx);
+    if (rc) return rc;
+    for (size_t t = 0; t < sp->streams.size(); t++) out[t] = (uint32_t)sp->streams[t].n_hi;
+    return FW_OK;
+}
+
+int fw_counts_all(fw_context *ctx, uint32_t *keys, uint32_t *types, uint32_t *counts, uint32_t cap, uint32_t *n_streams) {
+    ENTER(ctx);
+    int rc = refresh_exact(ctx);
+    if (rc) return rc;
+    uint32_t n = 0;
+    for (auto &sp : ctx->spawners) n += (uint32_t)sp->streams.size();
+    if (n_streams) *n_streams = n;
+    if (n > cap) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_counts_all: %u streams, room for %u", n, cap);
+    uint32_t k = 0;
+    for (auto &sp : ctx->spawners)
+        for (Stream &st : sp->streams) {
+            if (keys) keys[k] = sp->key;
+            if (types) types[k] = st.type;
+            if (counts) counts[k] = (uint32_t)st.n_hi;
+            k++;
+        }
+    return FW_OK;
+}
+
+int fw_total_live(fw_context *ctx, uint64_t *out) {
+    ENTER(ctx);
+    int rc = refresh_exact(ctx);
+    if (rc) return rc;
+    uint64_t n = 0;
+    for (auto &sp : ctx->spawners)
+        for (Stream &st : sp->streams) n += st.n_hi;
+    if (out) *out = n;
+    return FW_OK;
+}
+
+int fw_spawner_status_get(fw_context *ctx, uint32_t key, fw_spawner_status *out) {
+    ENTER(ctx);
+    Spawner *sp = find(ctx, key);
+    if (!sp || !out) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_spawner_status_get: unknown spawner %u", key);
+    int rc = refresh_exact(ctx);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    uint64_t live = 0;
+    for (Stream &st : sp->streams) live += st.n_hi;
+    out->live_particles = live;
+    out->all_empty = live == 0; // src/core.rs:679
+    out->active = spawner_active(*sp, live != 0);
+    out->finished = (out->all_empty && !out->active && sp->initialized && !sp->finished_notified) ? 1u : 0u; // :679-682
+    out->finished_notified = sp->finished_notified;
+    return FW_OK;
+}
+
+int fw_spawner_mark_finished_notified(fw_context *ctx, uint32_t key) {
+    ENTER(ctx);
+    Spawner *sp = find(ctx, key);
+    if (!sp) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "unknown spawner %u", key);
+    sp->finished_notified = true; // src/core.rs:685
+    return FW_OK;
+}
+
+int fw_read_particles(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_data *out, uint64_t cap, uint64_t *n) {
+    ENTER(ctx);
+    Spawner *sp = find(ctx, key);
+    if (!sp || type >= sp->streams.size()) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_read_particles: unknown spawner %u / type %u", key, type);
+    const Stream &st = sp->streams[type];
+    std::vector<float> rows, s0, s1, s2;
+    uint32_t live = 0;
+    int rc = read_stream_arrays(ctx, st, rows, s0, s1, s2, live);
+    if (rc) return rc;
+    if (n) *n = live;
+    if (live > cap || (live && !out)) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_read_particles: %u particles, room for %llu", live, (unsigned long long)cap);
+    for (uint32_t i = 0; i < live; i++) {
+        fw_particle_data &p = out[i];
+        const float *r = &rows[(size_t)i * 16];
+        memcpy(p.position, r, 12);
+        p.scale = r[3];
+        memcpy(p.rotation, r + 4, 16);
+        memcpy(p.base_color, r + 8, 16);
+        memcpy(p.emissive_color, r + 12, 16);
+        memcpy(p.velocity, &s0[(size_t)i * 4], 12);
+        p.age = s0[(size_t)i * 4 + 3];
+        memcpy(p.angular_velocity, &s1[(size_t)i * 4], 12);
+        p.lifetime = s1[(size_t)i * 4 + 3];
+        p.initial_scale = s2[i];
+        p.pbr = st.ps.pbr; // src/core.rs:462: a copy of the type's setting
+    }
+    return FW_OK;
+}
+
+int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_particle_data *in, uint64_t n) {
+    ENTER(ctx);
+    Spawner *sp = find(ctx, key);
+    if (!sp || type >= sp->streams.size()) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_write_particles: unknown spawner %u / type %u", key, type);
+    if (n && !in) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_write_particles: null");
+    if (n > 0xFFFFFF00ull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "too many particles");
+    Stream &st = sp->streams[type];
+    int rc = refresh_exact(ctx);
+    if (rc) return rc;
+    if (n > st.block.capacity) {
+        ctx->snapshot[st.slot].count = 0;
+        ctx->snapshot[st.slot].dead = 0;
+        if ((rc = grow_stream(ctx, st, n))) return rc;
+        if ((rc = ensure_tiles(ctx))) return rc;
+    }
+    std::vector<float> rows((size_t)n * 16), s0((size_t)n * 4), s1((size_t)n * 4), s2(n);
+    for (uint64_t i = 0; i < n; i++) {
+        const fw_particle_data &p = in[i];
+        float *r = &rows[(size_t)i * 16];
+        memcpy(r, p.position, 12);
+        r[3] = p.scale;
+        memcpy(r + 4, p.rotation, 16);
+        memcpy(r + 8, p.base_color, 16);
+        memcpy(r + 12, p.emissive_color, 16);
+        memcpy(&s0[(size_t)i * 4], p.velocity, 12);
+        s0[(size_t)i * 4 + 3] = p.age;
+        memcpy(&s1[(size_t)i * 4], p.angular_velocity, 12);
+        s1[(size_t)i * 4 + 3] = p.lifetime;
+        s2[i] = p.initial_scale;
+    }
+    StreamDesc d{};
+    block_arrays(st.block, d);
+    if (n) {
+        CU(ctx, cudaMemcpy(d.rows, rows.data(), (size_t)n * 64, cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(d.s0, s0.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(d.s1, s1.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(d.s2, s2.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    }
+    StreamState ns{};
+    ns.count = (uint32_t)n;
+    ns.aabb_min[0] = ns.aabb_min[1] = ns.aabb_min[2] = 0xFFFFFFFFu;
+    CU(ctx, cudaMemcpy(ctx->d_states + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice));
+    st.n_hi = n;
+    st.born_frame = ctx->frame_no + 1;
+    return FW_OK;
+}
+
+int fw_read_instances(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_instance *out, uint64_t cap, uint64_t *n) {
+    ENTER(ctx);
+    Spawner *sp = find(ctx, key);
+    if (!sp || type >= sp->streams.size()) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_read_instances: unknown spawner %u / type %u", key, type);
+    const Stream &st = sp->streams[type];
+    int rc = refresh_exact(ctx);
+    if (rc) return rc;
+    const StreamState s = ctx->snapshot[st.slot];
+    const uint32_t live = s.count - s.dead;
+    if (n) *n = live;
+    if (live > cap || (live && !out)) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_read_instances: %u rows, room for %llu", live, (unsigned long long)cap);
+    if (!live) return FW_OK;
+    const uint32_t capn = st.block.capacity;
+    const uint32_t first = (s.head + (is_fifo(st.variant) ? s.dead : 0u)) % capn;
+    const uint32_t seg1 = std::min(live, capn - first), seg2 = live - seg1;
+    StreamDesc d{};
+    block_arrays(st.block, d);
+    CU(ctx, cudaMemcpy(out, (const uint8_t *)d.rows + (size_t)first * 64, (size_t)seg1 * 64, cudaMemcpyDeviceToHost));
+    if (seg2) CU(ctx, cudaMemcpy((uint8_t *)out + (size_t)seg1 * 64, d.rows, (size_t)seg2 * 64, cudaMemcpyDeviceToHost));
+    return FW_OK;
+}
+
+int fw_read_destroyed(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_data *, uint64_t, uint64_t *n) {
+    ENTER(ctx);
+    Spawner *sp = find(ctx, key);
+    if (!sp || type >= sp->streams.size()) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_read_destroyed: unknown spawner %u / type %u", key, type);
+    if (n) *n = 0;
+    return fail(ctx, FW_ERR_UNSUPPORTED, "fw_read_destroyed: the destroyed-particle stream is not implemented yet");
+}
+
+int fw_read_aabb(fw_context *ctx, uint32_t key, float out_min[3], float out_max[3], uint32_t *empty) {
+    ENTER(ctx);
+    Spawner *sp = find(ctx, key);
+    if (!sp) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_read_aabb: unknown spawner %u", key);
+    int rc = refresh_exact(ctx);
+    if (rc) return rc;
+    float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f};
+    float mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    uint64_t live = 0;
+    for (Stream &st : sp->streams) {
+        const StreamState &s = ctx->snapshot[st.slot];
+        if (s.count - s.dead == 0) continue;
+        live += s.count - s.dead;
+        for (int k = 0; k < 3; k++) {
+            mn[k] = std::fmin(mn[k], dec_f32(s.aabb_min[k]));
+            mx[k] = std::fmax(mx[k], dec_f32(s.aabb_max[k]));
+        }
+    }
+    if (out_min) memcpy(out_min, mn, sizeof(mn));
+    if (out_max) memcpy(out_max, mx, sizeof(mx));
+    if (empty) *empty = live == 0;
+    return FW_OK;
+}
+
+int fw_pack_instances_device(fw_context *ctx, void *device_dst, uint64_t cap_rows, uint64_t *n_rows) {
+    ENTER(ctx);
+    if (!device_dst && cap_rows) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_pack_instances_device: null destination");
+    if (ctx->pack_cap < ctx->n_slots + 2) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_pack) CU(ctx, cudaFree(ctx->d_pack));
+        ctx->d_pack = nullptr;
+        ctx->pack_cap = std::max(1024u, (ctx->n_slots + 2) * 2);
+        CU(ctx, cudaMalloc((void **)&ctx->d_pack, sizeof(unsigned long long) * ctx->pack_cap));
+        if (!ctx->h_pack) CU(ctx, cudaMallocHost((void **)&ctx->h_pack, sizeof(unsigned long long)));
+    }
+    DeviceTables t{};
+    t.descs = ctx->d_descs;
+    t.states = ctx->d_states;
+    CU(ctx, launch_pack_instances(t, ctx->n_slots, (float4 *)device_dst, cap_rows, ctx->d_pack, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->h_pack, ctx->d_pack, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_rows) *n_rows = *ctx->h_pack;
+    if (*ctx->h_pack > cap_rows) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_pack_instances_device: %llu rows, room for %llu", *ctx->h_pack, (unsigned long long)cap_rows);
+    return FW_OK;
+}
+
+int fw_profile_last(fw_context *ctx, fw_frame_profile *out) {
+    ENTER(ctx);
+    if (!(ctx->flags & FW_FLAG_PROFILE)) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "context was created without FW_FLAG_PROFILE");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    // absorb in submission order
+    for (uint32_t k = 0; k < kRing; k++) absorb_profile(ctx, ctx->ring[(ctx->frame_no + k) % kRing]);
+    if (out) *out = ctx->prof_last;
+    return FW_OK;
+}
+int fw_profile_sum(fw_context *ctx, fw_frame_profile *out, uint32_t *n_frames) {
+    int rc = fw_profile_last(ctx, nullptr);
+    if (rc) return rc;
+    if (out) *out = ctx->prof_sum;
+    if (n_frames) *n_frames = ctx->prof_frames;
+    return FW_OK;
+}
+int fw_profile_reset(fw_context *ctx) {
+    ENTER(ctx);
+    if (ctx->flags & FW_FLAG_PROFILE) {
+        int rc = fw_profile_last(ctx, nullptr);
+        if (rc) return rc;
+    }
+    memset(&ctx->prof_sum, 0, sizeof(ctx->prof_sum));
+    memset(&ctx->prof_last, 0, sizeof(ctx->prof_last));
+    ctx->prof_frames = 0;
+    return FW_OK;
+}
+
+void *fw_stream_handle(fw_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+} // extern "C"

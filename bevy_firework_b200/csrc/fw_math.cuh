@@ -1,0 +1,355 @@
+// fw_math.cuh -- device-side fp32 helpers of the particle kernels.
+//
+// This translation unit is compiled with -fmad=false: every a*b+c below is two correctly
+// rounded IEEE operations, in the operation order of the reference's Rust expressions
+// (glam 0.32 scalar formulas), so position / velocity / age / scale / colours can be compared
+// bit-for-bit with a CPU evaluation of the same expressions. Only sinf/cosf (rotation, spawn
+// shapes) are library functions whose last ulp may differ from a host libm.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "fw_internal.h"
+
+namespace fw {
+
+struct V3 {
+    float x, y, z;
+};
+struct Q4 {
+    float x, y, z, w;
+};
+
+__device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return v3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+__device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
+__device__ __forceinline__ bool is_zero(V3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }
+// glam Vec3::normalize = self * length_recip()
+__device__ __forceinline__ V3 normalize(V3 a) { return a * (1.0f / length(a)); }
+// glam Vec3::normalize_or_zero
+__device__ __forceinline__ V3 normalize_or_zero(V3 a) {
+    float rcp = 1.0f / length(a);
+    if (isfinite(rcp) && rcp > 0.0f) return a * rcp;
+    return v3(0.0f, 0.0f, 0.0f);
+}
+// glam Vec3::project_onto / reject_from
+__device__ __forceinline__ V3 project_onto(V3 a, V3 rhs) {
+    float other_len_sq_rcp = 1.0f / dot(rhs, rhs);
+    return (rhs * dot(a, rhs)) * other_len_sq_rcp;
+}
+__device__ __forceinline__ V3 reject_from(V3 a, V3 rhs) { return a - project_onto(a, rhs); }
+
+// glam Quat::mul_quat (scalar form)
+__device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
+    Q4 r;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+    r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    return r;
+}
+// glam Quat::mul_vec3 (scalar form)
+__device__ __forceinline__ V3 qrot(Q4 q, V3 v) {
+    float w = q.w;
+    V3 b = v3(q.x, q.y, q.z);
+    float b2 = dot(b, b);
+    V3 r = v * (w * w - b2);
+    r = r + b * (dot(v, b) * 2.0f);
+    r = r + cross(b, v) * (w * 2.0f);
+    return r;
+}
+__device__ __forceinline__ Q4 qconj(Q4 q) { return Q4{-q.x, -q.y, -q.z, q.w}; }
+__device__ __forceinline__ Q4 q_from_axis_angle(V3 axis, float angle) {
+    float s, c;
+    sincosf(angle * 0.5f, &s, &c);
+    return Q4{axis.x * s, axis.y * s, axis.z * s, c};
+}
+// glam Quat::from_scaled_axis (reference src/core.rs:646)
+__device__ __forceinline__ Q4 q_from_scaled_axis(V3 v) {
+    float len = length(v);
+    if (len == 0.0f) return Q4{0.0f, 0.0f, 0.0f, 1.0f};
+    return q_from_axis_angle(v / len, len);
+}
+__device__ __forceinline__ Q4 q_from_rotation_y(float angle) {
+    float s, c;
+    sincosf(angle * 0.5f, &s, &c);
+    return Q4{0.0f, s, 0.0f, c};
+}
+__device__ __forceinline__ V3 any_orthonormal(V3 n) {
+    float sign = copysignf(1.0f, n.z);
+    float a = -1.0f / (sign + n.z);
+    float b = n.x * n.y * a;
+    return v3(b, sign + n.y * n.y * a, -n.y);
+}
+// glam Quat::from_rotation_arc
+__device__ __forceinline__ Q4 q_from_rotation_arc(V3 from, V3 to) {
+    const float kOneMinusEps = 1.0f - 2.0f * FLT_EPSILON;
+    float d = dot(from, to);
+    if (d > kOneMinusEps) return Q4{0.0f, 0.0f, 0.0f, 1.0f};
+    if (d < -kOneMinusEps) return q_from_axis_angle(any_orthonormal(from), 3.14159265358979323846f);
+    V3 c = cross(from, to);
+    Q4 q{c.x, c.y, c.z, 1.0f + d};
+    float len = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    float rcp = 1.0f / len;
+    q.x *= rcp;
+    q.y *= rcp;
+    q.z *= rcp;
+    q.w *= rcp;
+    return q;
+}
+
+// ---- curve cores (bevy_math EvenCore / UnevenCore semantics; reference src/curve.rs)
+struct Interp {
+    uint32_t lo, hi;
+    float s;
+    bool between;
+};
+__device__ __forceinline__ float clamp01(float t) {
+    if (!(t > 0.0f)) return 0.0f;
+    if (t > 1.0f) return 1.0f;
+    return t;
+}
+__device__ __forceinline__ Interp even_interp(uint32_t n, float t) {
+    Interp r{0u, 0u, 0.0f, false};
+    uint32_t subdivs = n - 1u;
+    float step = (1.0f - 0.0f) / (float)subdivs;
+    float steps_taken = (t - 0.0f) / step;
+    if (!(steps_taken > 0.0f)) return r;
+    if (steps_taken >= (float)subdivs) {
+        r.lo = n - 1u;
+        return r;
+    }
+    float fl = floorf(steps_taken);
+    r.lo = (uint32_t)fl;
+    r.hi = r.lo + 1u;
+    r.s = steps_taken - fl;
+    r.between = (r.s != 0.0f);
+    return r;
+}
+__device__ __forceinline__ Interp uneven_interp(const float *times, uint32_t n, float t) {
+    Interp r{0u, 0u, 0.0f, false};
+    uint32_t idx = 0;
+    while (idx < n && times[idx] < t) idx++;
+    if (idx < n && times[idx] == t) {
+        r.lo = idx;
+        return r;
+    }
+    if (idx == 0u) return r;
+    if (idx >= n) {
+        r.lo = n - 1u;
+        return r;
+    }
+    float t_lower = times[idx - 1u], t_upper = times[idx];
+    r.lo = idx - 1u;
+    r.hi = idx;
+    r.s = (t - t_lower) / (t_upper - t_lower);
+    r.between = true;
+    return r;
+}
+// FireworkCurve<f32>::sample_clamped (reference src/core.rs:603)
+__device__ __forceinline__ float sample_curve(const fw_curve_f32 &c, float t) {
+    if (c.kind == FW_CURVE_CONSTANT) return c.values[0];
+    t = clamp01(t);
+    Interp it = (c.kind == FW_CURVE_EVEN) ? even_interp(c.n, t) : uneven_interp(c.times, c.n, t);
+    float a = c.values[it.lo];
+    if (!it.between) return a;
+    float b = c.values[it.hi];
+    return a + (b - a) * it.s;
+}
+// FireworkGradient<LinearRgba>::sample_clamped (reference src/core.rs:460-461,653,655);
+// bevy_color Mix: a*(1-s) + b*s per channel
+__device__ __forceinline__ float4 sample_gradient(const fw_gradient &g, float t) {
+    const float4 *colors = reinterpret_cast<const float4 *>(&g.colors[0][0]);
+    if (g.kind == FW_CURVE_CONSTANT) return colors[0];
+    t = clamp01(t);
+    Interp it = (g.kind == FW_CURVE_EVEN) ? even_interp(g.n, t) : uneven_interp(g.times, g.n, t);
+    float4 a = colors[it.lo];
+    if (!it.between) return a;
+    float4 b = colors[it.hi];
+    float nf = 1.0f - it.s;
+    return make_float4(a.x * nf + b.x * it.s, a.y * nf + b.y * it.s, a.z * nf + b.z * it.s,
+                       a.w * nf + b.w * it.s);
+}
+
+// ---- Philox4x32-10 (Salmon et al. SC'11) -- the spawn RNG protocol of DESIGN.md
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// ---- order-preserving float <-> uint (for atomicMin/Max and REDUX on AABB bounds)
+__device__ __forceinline__ uint32_t enc_f32(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ---- ray casting against the static colliders (avian cast_ray / parry shapes semantics,
+// closest hit, solid = true). Lowest collider index wins ties.
+__device__ __forceinline__ bool ray_cuboid_local(V3 he, V3 o, V3 d, float max_toi, float &toi, V3 &normal) {
+    float tmax = FLT_MAX, tmin = -FLT_MAX;
+    int near_side = 0;
+    bool near_diag = false;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z}, hh[3] = {he.x, he.y, he.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float mn = -hh[i], mx = hh[i];
+        if (dd[i] == 0.0f) {
+            if (oo[i] < mn || oo[i] > mx) return false;
+        } else {
+            float denom = 1.0f / dd[i];
+            float t_near = (mn - oo[i]) * denom;
+            float t_far = (mx - oo[i]) * denom;
+            bool flip = t_near > t_far;
+            if (flip) {
+                float tmp = t_near;
+                t_near = t_far;
+                t_far = tmp;
+            }
+            if (t_near > tmin) {
+                tmin = t_near;
+                near_side = flip ? -(i + 1) : (i + 1);
+                near_diag = false;
+            } else if (t_near == tmin) {
+                near_diag = true;
+            }
+            if (t_far < tmax) tmax = t_far;
+            if (tmax < 0.0f || tmin > tmax) return false;
+        }
+    }
+    if (tmin < 0.0f) {
+        toi = 0.0f;
+        normal = v3(0.0f, 0.0f, 0.0f);
+        return true;
+    }
+    if (tmin <= max_toi) {
+        float nx = 0.0f, ny = 0.0f, nz = 0.0f;
+        if (!near_diag && near_side != 0) {
+            float sgn = near_side < 0 ? 1.0f : -1.0f;
+            int ax = (near_side < 0 ? -near_side : near_side) - 1;
+            if (ax == 0) nx = sgn;
+            else if (ax == 1) ny = sgn;
+            else nz = sgn;
+        }
+        toi = tmin;
+        normal = v3(nx, ny, nz);
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ bool ray_ball_local(float radius, V3 o, V3 d, float max_toi, float &toi, V3 &normal) {
+    float a = dot(d, d);
+    float b = dot(o, d);
+    float c = dot(o, o) - radius * radius;
+    float t;
+    bool inside = false;
+    if (a == 0.0f) {
+        if (c > 0.0f) return false;
+        t = 0.0f;
+        inside = true;
+    } else if (c > 0.0f && b > 0.0f) {
+        return false;
+    } else {
+        float delta = b * b - a * c;
+        if (delta < 0.0f) return false;
+        t = (-b - sqrtf(delta)) / a;
+        if (t <= 0.0f) {
+            t = 0.0f;
+            inside = true;
+        }
+    }
+    if (!(t <= max_toi)) return false;
+    V3 pos = o + d * t;
+    V3 n = normalize(pos);
+    if (inside) n = v3(-n.x, -n.y, -n.z);
+    toi = t;
+    normal = n;
+    return true;
+}
+__device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ colliders, uint32_t n,
+                                         uint32_t filter_mask, V3 o, V3 d, float max_distance,
+                                         float &distance, V3 &normal) {
+    bool found = false;
+    float best = 0.0f;
+    V3 best_n = v3(0.0f, 0.0f, 0.0f);
+    for (uint32_t i = 0; i < n; i++) {
+        const fw_collider &c = colliders[i];
+        if ((c.layers & filter_mask) == 0u) continue;
+        Q4 rot{c.rotation[0], c.rotation[1], c.rotation[2], c.rotation[3]};
+        Q4 inv = qconj(rot);
+        V3 tr = v3(c.translation[0], c.translation[1], c.translation[2]);
+        V3 ol = qrot(inv, o - tr);
+        V3 dl = qrot(inv, d);
+        float toi;
+        V3 nl;
+        bool hit;
+        if (c.kind == FW_COLLIDER_SPHERE) hit = ray_ball_local(c.half_extents[0], ol, dl, max_distance, toi, nl);
+        else hit = ray_cuboid_local(v3(c.half_extents[0], c.half_extents[1], c.half_extents[2]), ol, dl, max_distance, toi, nl);
+        if (hit && (!found || toi < best)) {
+            found = true;
+            best = toi;
+            best_n = qrot(rot, nl);
+        }
+    }
+    distance = best;
+    normal = best_n;
+    return found;
+}
+
+// reference src/core.rs:744-800 particle_collision
+__device__ __forceinline__ void particle_collision(const fw_collider *__restrict__ colliders, uint32_t n_colliders,
+                                                   const fw_collision_settings &cs, V3 &pos, V3 &vel,
+                                                   float delta, bool &should_destroy) {
+    const float orig_delta = delta;
+    int n_steps = 0;
+    should_destroy = false;
+    while (delta > 0.0f && n_steps < 4) {
+        float len = length(vel);
+        V3 dir = (isfinite(len) && len > 0.0f) ? vel / len : v3(0.0f, 1.0f, 0.0f);
+        float distance;
+        V3 hit_normal;
+        if (cast_ray(colliders, n_colliders, cs.filter_mask, pos, dir, length(vel) * delta, distance, hit_normal)) {
+            if (distance == 0.0f) {
+                V3 normal = hit_normal;
+                if (is_zero(normal)) {
+                    if (!is_zero(vel)) normal = normalize(vel);
+                    else normal = v3(0.0f, 1.0f, 0.0f);
+                }
+                pos = pos + (normal * fmaxf(length(vel), 1.0f)) * delta;
+            } else {
+                pos = pos + normalize_or_zero(vel) * distance;
+                V3 vel_reject = reject_from(vel, hit_normal);
+                V3 vel_project = project_onto(vel, hit_normal);
+                float friction_dv = fminf(length(vel_project), length(vel_reject)) * cs.friction;
+                vel = (vel_reject - normalize_or_zero(vel_reject) * friction_dv) - vel_project * cs.restitution;
+                pos = pos + hit_normal * 0.0001f;
+                delta = delta - distance;
+                if (delta < 0.0f) delta = 0.0f;
+                if (delta > orig_delta) delta = orig_delta;
+            }
+            should_destroy = cs.destroy_on_collision != 0u;
+            if (should_destroy) return;
+        } else {
+            pos = pos + vel * delta;
+            delta = 0.0f;
+        }
+        n_steps += 1;
+    }
+}
+
+} // namespace fw

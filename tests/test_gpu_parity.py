@@ -1,0 +1,397 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle. GPU only.
+
+Bars: counts exact every frame; position / velocity / age / scale / colours bit-exact whenever
+the inputs are bit-identical (pre-filled state); 1e-5 (abs+rel) where a value passes through
+sinf/cosf (rotation, spawn shapes)."""
+import math
+
+import numpy as np
+import pytest
+
+from bevy_firework_b200 import (EmissionPacing, EmissionSettings, EmissionShape, FireworkCurve,
+                                FireworkGradient, LinearRgba, ParticleCollisionSettings,
+                                ParticleSettings, ParticleSpawner, RandF32, RandVec3, _abi)
+from bevy_firework_b200._native import frame_input
+from bevy_firework_b200.workloads import (collision_ring, collision_scene_colliders, collision_spawner,
+                                          cuboid, grid_positions, one_shot_spawner, sparks_spawner,
+                                          sphere, stress_spawner)
+from _parity import assert_rows_match, random_rows, reset_both
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+DT = float(f32(1.0) / f32(60.0))
+NO_TRIG = ("position", "velocity", "angular_velocity", "initial_scale", "scale", "age", "lifetime",
+           "base_color", "emissive_color")
+
+
+def _idle_spawner(**ps_kwargs):
+    """a spawner that never emits: state is injected with write_particles"""
+    return ParticleSpawner(particle_settings=[ParticleSettings(**ps_kwargs)],
+                           emission_settings=[EmissionSettings(emission_pacing=EmissionPacing.OneShot(0))])
+
+
+CURVES = {
+    "constant": (FireworkCurve.constant(1.0), FireworkGradient.constant(LinearRgba(0.3, 0.4, 0.5, 1.0))),
+    "even": (FireworkCurve.even_samples([1.0, 2.0, 0.5]),
+             FireworkGradient.even_samples([LinearRgba(1, 0, 0, 1), LinearRgba(0, 1, 0, 1), LinearRgba(0, 0, 1, 0)])),
+    "uneven": (FireworkCurve.uneven_samples([(0.0, 0.2), (0.3, 1.0), (1.0, 0.0)]),
+               stress_spawner().particle_settings[0].base_color),
+}
+
+
+@pytest.mark.parametrize("kind", ["constant", "even", "uneven"])
+@pytest.mark.parametrize("n", [1, 31, 257, 10037])
+def test_single_step_prefilled_bitexact(engine, oracle, kind, n):
+    """R2 on identical input state: everything but the rotation quaternion is bit-exact."""
+    curve, grad = CURVES[kind]
+    sp = _idle_spawner(lifetime=RandF32(0.5, 3.0), scale_curve=curve, base_color=grad, emissive_color=grad,
+                       linear_drag=0.1, angular_drag=0.3, angular_acceleration=(0.1, -0.2, 0.3))
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 5, sp)
+    rows = random_rows(np.random.default_rng(n), n)
+    engine.write_particles(5, 0, rows)
+    w.write_particles(5, 0, rows)
+    assert_rows_match(engine.read_particles(5, 0), rows, exact=NO_TRIG + ("rotation",), what="write/read roundtrip")
+    engine.frame(DT, [])
+    w.frame(DT, [])
+    got, want = engine.read_particles(5, 0), w.read_particles(5, 0)
+    assert_rows_match(got, want, exact=NO_TRIG, what=f"{kind} n={n}")
+    inst = engine.read_instances(5, 0)
+    for f in ("position", "scale", "rotation", "base_color", "emissive_color"):
+        assert (inst[f] == got[f]).all()          # ParticleInstance row == From<&ParticleData> (src/render.rs:105-115)
+
+
+def test_600_steps_trajectory_with_deaths(engine, oracle):
+    """random lifetimes -> compact variant: survivors keep the reference's Vec order."""
+    sp = _idle_spawner(lifetime=RandF32(0.5, 8.0), base_color=CURVES["uneven"][1], linear_drag=0.2)
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 1, sp)
+    rows = random_rows(np.random.default_rng(3), 5000, lifetime=(0.5, 8.0))
+    engine.write_particles(1, 0, rows)
+    w.write_particles(1, 0, rows)
+    for k in range(600):
+        engine.frame(DT, [])
+        w.frame(DT, [])
+        if k % 50 == 49 or k < 3:
+            assert engine.counts(1) == w.counts(1), f"frame {k}"
+            assert_rows_match(engine.read_particles(1, 0), w.read_particles(1, 0), exact=NO_TRIG, what=f"frame {k}")
+    assert engine.counts(1)[0] == 0 or engine.counts(1)[0] < 5000
+
+
+def test_zero_angular_velocity_keeps_rotation_exact(engine, oracle):
+    sp = _idle_spawner(lifetime=RandF32.constant(5.0))
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 1, sp)
+    rows = random_rows(np.random.default_rng(1), 1000, angular=False)
+    rows["lifetime"] = 5.0
+    rows["age"] = np.sort(rows["age"])[::-1]
+    engine.write_particles(1, 0, rows)
+    w.write_particles(1, 0, rows)
+    for _ in range(10):
+        engine.frame(DT, [])
+        w.frame(DT, [])
+    assert_rows_match(engine.read_particles(1, 0), w.read_particles(1, 0), exact=NO_TRIG + ("rotation",))
+
+
+@pytest.mark.parametrize("lifetime,frame", [(0.75, 46), (1.0, 61), (2.0, 121), (2.5, 151)])
+def test_death_frames(engine, lifetime, frame):
+    """sequential f32 age accumulation decides the death frame."""
+    sp = ParticleSpawner(particle_settings=[ParticleSettings(lifetime=RandF32.constant(lifetime))],
+                         emission_settings=[EmissionSettings(emission_pacing=EmissionPacing.OneShot(300))])
+    ps, nt, es, ne = sp.pods()
+    engine.spawner_reset(1, ps, nt, es, ne, True)
+    for k in range(1, frame + 2):
+        engine.frame(DT, [frame_input(1)])
+        if k in (frame - 1, frame):
+            assert engine.counts(1)[0] == (300 if k < frame else 0), k
+    st = engine.status(1)
+    assert st.all_empty and not st.active and st.finished
+
+
+@pytest.mark.parametrize("rate", [1000.0, 15625.0, 160000.0])
+def test_emission_counts_every_frame(engine, oracle, rate):
+    """R5 + deaths: data.particles[i].len() equals the oracle's on every one of 130 frames."""
+    sp = stress_spawner(rate=rate)
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 9, sp)
+    inp = [frame_input(9, (0.0, 0.1, 0.0))]
+    for k in range(130):
+        engine.frame(DT, inp)
+        w.frame(DT, inp)
+        assert engine.counts(9) == w.counts(9), f"frame {k}"
+    assert_rows_match(engine.read_particles(9, 0), w.read_particles(9, 0),
+                      exact=("age", "lifetime", "initial_scale", "scale", "base_color", "emissive_color", "angular_velocity"))
+
+
+def test_spawn_parity_all_shapes(engine, oracle):
+    """R4/R8/R9 under the Philox protocol: same uniforms -> same particles (trig within 1e-5)."""
+    q = (0.0, math.sin(0.4), 0.0, math.cos(0.4))
+    emitters = [
+        EmissionSettings(emission_pacing=EmissionPacing.OneShot(1000), emission_shape=EmissionShape.Point,
+                         initial_velocity=RandVec3(RandF32(1.0, 4.0), (1.0, 2.0, 0.5), 0.7),
+                         initial_angular_velocity=RandVec3(RandF32(0.5, 2.0), (0.0, 0.0, 1.0), 0.3),
+                         initial_rotation=q),
+        EmissionSettings(emission_pacing=EmissionPacing.OneShot(777), emission_shape=EmissionShape.Sphere(2.0),
+                         initial_velocity_radial=RandF32(0.5, 3.0), inherit_parent_velocity=False),
+        EmissionSettings(emission_pacing=EmissionPacing.OneShot(555),
+                         emission_shape=EmissionShape.Circle((0.3, 0.8, -0.2), 1.5), particle_index=1,
+                         initial_velocity=RandVec3.constant((0.0, 2.0, 0.0))),
+    ]
+    sp = ParticleSpawner(particle_settings=[ParticleSettings(lifetime=RandF32(1.0, 2.0), initial_scale=RandF32(0.1, 0.4)),
+                                            ParticleSettings(base_color=CURVES["uneven"][1])],
+                         emission_settings=emitters)
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 77, sp)
+    inp = [frame_input(77, (1.0, 2.0, 3.0), (math.sin(0.3), 0.0, 0.0, math.cos(0.3)), (0.5, 0.0, -0.5), 1.5, 0.8)]
+    engine.frame(DT, inp)
+    w.frame(DT, inp)
+    assert engine.counts(77) == w.counts(77) == [1777, 555]
+    for t in (0, 1):
+        assert_rows_match(engine.read_particles(77, t), w.read_particles(77, t),
+                          exact=("age", "lifetime", "initial_scale", "scale", "base_color", "emissive_color"),
+                          what=f"type {t}")
+
+
+def test_sparks_trajectory_c1(engine, oracle):
+    """C1 examples/sparks.rs: 240 frames, counts exact every frame, state within 1e-5."""
+    sp = sparks_spawner(1000.0)
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 1, sp)
+    inp = [frame_input(1, (0.0, 0.1, 0.0))]
+    for k in range(240):
+        engine.frame(DT, inp)
+        w.frame(DT, inp)
+        assert engine.counts(1) == w.counts(1), f"frame {k}"
+        if k % 60 == 59:
+            assert_rows_match(engine.read_particles(1, 0), w.read_particles(1, 0), exact=("age", "lifetime", "initial_scale", "scale", "base_color", "emissive_color"), what=f"frame {k}")
+    bb, ob = engine.read_aabb(1), w.read_aabb(1)
+    assert np.allclose(bb[0], ob[0], atol=1e-4) and np.allclose(bb[1], ob[1], atol=1e-4)
+
+
+def test_stress_64_spawners_c2_reduced(engine, oracle):
+    """C2 layout (64 spawners on a grid) at a reduced rate so the oracle finishes in seconds."""
+    w = oracle.OracleWorld(n_threads=8)
+    sp = stress_spawner(rate=1500.0)
+    pos = grid_positions(64)
+    inputs = []
+    for i, p in enumerate(pos):
+        reset_both(engine, w, 100 + i, sp)
+        inputs.append(frame_input(100 + i, p))
+    for k in range(150):
+        engine.frame(DT, inputs)
+        w.frame(DT, inputs)
+    keys, types, counts = engine.counts_all()
+    assert list(keys) == [100 + i for i in range(64)]
+    assert [int(c) for c in counts] == [w.counts(100 + i)[0] for i in range(64)]
+    assert engine.total_live() == w.total_live()
+    for i in (0, 17, 63):
+        assert_rows_match(engine.read_particles(100 + i, 0), w.read_particles(100 + i, 0),
+                          exact=("age", "lifetime", "initial_scale", "scale", "base_color", "emissive_color"))
+
+
+def test_one_shot_bursts_c4_reduced(engine, oracle):
+    """C4: a new OneShot spawner every frame, retired when finished (examples/one_shot.rs:137-141)."""
+    w = oracle.OracleWorld()
+    sp = one_shot_spawner(count=3000, lifetime=0.5)
+    live = []
+    for k in range(80):
+        key = 1000 + k
+        reset_both(engine, w, key, sp)
+        live.append(key)
+        q = (0.0, 0.0, math.sin(0.1 * k), math.cos(0.1 * k))
+        inputs = [frame_input(key, (0.1 * k, 1.0, 0.0), q)]
+        engine.frame(DT, inputs)
+        w.frame(DT, inputs)
+        for key2 in list(live):
+            st, ost = engine.status(key2), w.status(key2)
+            assert (st.finished, st.active, st.live_particles) == (ost.finished, ost.active, ost.live_particles)
+            if st.finished:
+                engine.spawner_remove(key2)
+                w.spawner_remove(key2)
+                live.remove(key2)
+        if k % 20 == 19:
+            assert engine.total_live() == w.total_live()
+            assert_rows_match(engine.read_particles(live[0], 0), w.read_particles(live[0], 0),
+                              exact=("age", "lifetime", "initial_scale", "base_color", "emissive_color"))
+    assert len(live) == 31  # lifetime 0.5 s -> removed on update #31
+
+
+def test_random_lifetime_compaction(engine, oracle):
+    """random lifetimes: deaths anywhere in the Vec; order and counts must match every frame."""
+    sp = stress_spawner(rate=20000.0)
+    sp.particle_settings[0].lifetime = RandF32(0.2, 1.2)
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 3, sp)
+    inp = [frame_input(3, (0.0, 0.1, 0.0))]
+    for k in range(120):
+        engine.frame(DT, inp)
+        w.frame(DT, inp)
+        assert engine.counts(3) == w.counts(3), f"frame {k}"
+        if k % 40 == 39:
+            assert_rows_match(engine.read_particles(3, 0), w.read_particles(3, 0),
+                              exact=("age", "lifetime", "initial_scale", "scale", "base_color", "emissive_color"), what=f"frame {k}")
+
+
+def test_ring_wrap_and_growth(engine, oracle):
+    """a deliberately tiny capacity hint forces ring wrap-around and several growths."""
+    sp = stress_spawner(rate=6000.0, lifetime=0.4)
+    sp.particle_settings[0].capacity_hint = 64
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 3, sp)
+    inp = [frame_input(3, (0.0, 0.1, 0.0))]
+    for k in range(200):
+        engine.frame(DT, inp)
+        w.frame(DT, inp)
+        if k % 10 == 0:
+            assert engine.counts(3) == w.counts(3), f"frame {k}"
+    engine.sync()
+    assert_rows_match(engine.read_particles(3, 0), w.read_particles(3, 0),
+                      exact=("age", "lifetime", "initial_scale", "scale", "base_color", "emissive_color"))
+
+
+def test_collision_single_step_prefilled(engine, oracle):
+    """R3 on identical input state: bit-exact positions/velocities against the oracle's ray caster."""
+    sp = _idle_spawner(lifetime=RandF32.constant(100.0), linear_drag=0.15,
+                       collision_settings=ParticleCollisionSettings(0.6, 0.2, False))
+    cols = [cuboid((8, 1, 8), (0, -0.5, 0)), cuboid((1, 1, 1), (0, 0.5, 0), (0.3535534, 0.3535534, 0.1464466, 0.8535534)),
+            sphere(0.7, (2.0, 0.7, 0.0))]
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 1, sp)
+    engine.set_colliders(cols)
+    w.set_colliders(cols)
+    rng = np.random.default_rng(11)
+    rows = random_rows(rng, 20000, angular=False)
+    rows["position"] = rng.uniform(-3, 3, (20000, 3))
+    rows["position"][:, 1] = rng.uniform(-0.2, 2.0, 20000)
+    rows["velocity"] = rng.uniform(-8, 8, (20000, 3))
+    rows["lifetime"] = 100.0
+    rows["age"] = 1.0
+    engine.write_particles(1, 0, rows)
+    w.write_particles(1, 0, rows)
+    for k in range(3):
+        engine.frame(DT, [])
+        w.frame(DT, [])
+        assert_rows_match(engine.read_particles(1, 0), w.read_particles(1, 0), exact=NO_TRIG + ("rotation",), what=f"step {k}")
+
+
+def test_collision_destroy_on_collision(engine, oracle):
+    sp = _idle_spawner(lifetime=RandF32.constant(100.0),
+                       collision_settings=ParticleCollisionSettings(0.6, 0.2, True))
+    cols = [cuboid((8, 1, 8), (0, -0.5, 0))]
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 1, sp)
+    engine.set_colliders(cols)
+    w.set_colliders(cols)
+    rng = np.random.default_rng(5)
+    rows = random_rows(rng, 3000, angular=False)
+    rows["position"][:, 1] = rng.uniform(0.05, 3.0, 3000)
+    rows["lifetime"] = 100.0
+    rows["age"] = 0.0
+    engine.write_particles(1, 0, rows)
+    w.write_particles(1, 0, rows)
+    for k in range(30):
+        engine.frame(DT, [])
+        w.frame(DT, [])
+        assert engine.counts(1) == w.counts(1), k
+    assert 0 < engine.counts(1)[0] < 3000
+    assert_rows_match(engine.read_particles(1, 0), w.read_particles(1, 0), exact=NO_TRIG + ("rotation",))
+
+
+def test_collision_scene_c5_reduced(engine, oracle):
+    """C5: ring of tilted spawners over the ground slab + rotated unit cubes, 120 frames."""
+    w = oracle.OracleWorld(n_threads=8)
+    sp = collision_spawner(rate=600.0)
+    cols = collision_scene_colliders(64)
+    engine.set_colliders(cols)
+    w.set_colliders(cols)
+    inputs = []
+    for i, (t, r) in enumerate(collision_ring(8)):
+        reset_both(engine, w, 10 + i, sp)
+        inputs.append(frame_input(10 + i, t, r))
+    for k in range(150):
+        engine.frame(DT, inputs)
+        w.frame(DT, inputs)
+    assert engine.total_live() == w.total_live()
+    # spawn uses sinf/cosf, so inputs differ in the last ulp and a particle grazing an edge may
+    # take the other branch: require 99.5 % of rows within tolerance, all ages exact
+    bad = tot = 0
+    for i in range(8):
+        g, o = engine.read_particles(10 + i, 0), w.read_particles(10 + i, 0)
+        assert (g["age"] == o["age"]).all()
+        ok = np.abs(g["position"].astype(np.float64) - o["position"]).max(axis=1) <= 1e-4
+        bad += int((~ok).sum())
+        tot += len(g)
+    assert bad <= 0.005 * tot, (bad, tot)
+
+
+def test_on_demand_and_modifier(engine, oracle):
+    """OnDemand pacing drains manual_queued_count (src/core.rs:401-405); EffectModifier scales."""
+    sp = ParticleSpawner(particle_settings=[ParticleSettings(lifetime=RandF32.constant(1.0), initial_scale=RandF32(0.5, 1.0))],
+                         emission_settings=[EmissionSettings(emission_pacing=EmissionPacing.OnDemand,
+                                                             initial_velocity=RandVec3.constant((0.0, 3.0, 0.0)))])
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 4, sp)
+    for k, q in enumerate([0, 5, 0, 120, 1, 0]):
+        inp = [frame_input(4, (0, 0, 0), modifier_scale=2.0, modifier_speed=0.5, queue_particles=q)]
+        engine.frame(DT, inp)
+        w.frame(DT, inp)
+        assert engine.counts(4) == w.counts(4)
+    assert engine.counts(4)[0] == 126
+    assert_rows_match(engine.read_particles(4, 0), w.read_particles(4, 0), exact=NO_TRIG + ("rotation",))
+
+
+def test_reset_drops_particles(engine):
+    """sync_spawner_data on a changed spawner drops all particles (src/core.rs:360)."""
+    sp = stress_spawner(rate=5000.0)
+    ps, nt, es, ne = sp.pods()
+    engine.spawner_reset(1, ps, nt, es, ne, True)
+    for _ in range(20):
+        engine.frame(DT, [frame_input(1)])
+    assert engine.counts(1)[0] > 1000
+    engine.spawner_reset(1, ps, nt, es, ne, True)
+    assert engine.counts(1)[0] == 0
+    engine.frame(DT, [frame_input(1)])
+    assert 80 <= engine.counts(1)[0] <= 90
+
+
+def test_error_behaviour(engine):
+    from bevy_firework_b200._native import FireworkError
+
+    with pytest.raises(FireworkError) as e:
+        engine.counts(12345, 1)
+    assert e.value.code == _abi.FW_ERR_UNKNOWN_SPAWNER
+    with pytest.raises(FireworkError) as e:
+        engine.frame(DT, [frame_input(4242)])
+    assert e.value.code == _abi.FW_ERR_UNKNOWN_SPAWNER
+    sp = stress_spawner()
+    ps, nt, es, ne = sp.pods()
+    ps[0].base_color.times[2] = 0.1  # not increasing: the reference's UnevenCore would reject it
+    with pytest.raises(FireworkError) as e:
+        engine.spawner_reset(1, ps, nt, es, ne, True)
+    assert e.value.code == _abi.FW_ERR_INVALID_ARGUMENT
+    ps[0].base_color.n = 0
+    with pytest.raises(FireworkError):
+        engine.spawner_reset(1, ps, nt, es, ne, True)
+    es[0].particle_index = 3
+    with pytest.raises(FireworkError):
+        engine.spawner_reset(1, *sp.pods()[:1], nt, es, ne, True)
+
+
+def test_pack_instances_device(engine):
+    import torch
+
+    sp = stress_spawner(rate=3000.0)
+    keys = [1, 2, 3]
+    for k in keys:
+        ps, nt, es, ne = sp.pods()
+        engine.spawner_reset(k, ps, nt, es, ne, True)
+    inputs = [frame_input(k, (float(k), 0.0, 0.0)) for k in keys]
+    for _ in range(70):
+        engine.frame(DT, inputs)
+    total = engine.total_live()
+    buf = torch.zeros((total + 10, 16), dtype=torch.float32, device="cuda:0")
+    n = engine.pack_instances_device(buf.data_ptr(), total + 10)
+    assert n == total
+    host = buf.cpu().numpy()[:n].view(_abi.particle_instance_dtype()).reshape(-1)
+    want = np.concatenate([engine.read_instances(k, 0) for k in keys])
+    assert host.tobytes() == want.tobytes()
