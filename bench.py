@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- particles updated/sec of the fused per-frame step (spawn + update) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1|c4|c5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one frame of the hot path (fw_frame = plan + spawn + update kernels) over the whole
+workload at fixed dt = fl32(1/60). Default workload: C3 = examples/stress_test.rs settings,
+512 spawners x rate 19531 => ~10 M live particles PER GPU (1.6 GB of state, >> the 126 MB L2, so
+no L2 flush is needed between steps). With N > 1 every rank owns its own 512 spawners (sharded by
+spawner, no data-path collective): weak scaling.
+
+One JSON line on rank 0 (see the contract in the task statement): value = whole-job particles/s
+with state resident in HBM; e2e = same metric through the C ABI with host input structs and a
+device->host read of the per-frame results (counts + AABBs) every step; roofline for the update
+kernel from CUDA events recorded around it inside the timed region; cpu_baseline = the CPU oracle
+(a C restatement of the reference loop; no Rust toolchain exists here) timed on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from bevy_firework_b200 import workloads as W  # noqa: E402
+
+ALGO_BYTES_PER_PARTICLE = 156  # 64 B read + 92 B written
+DT = float(np.float32(1.0) / np.float32(60.0))
+
+
+# ------------------------------------------------------------------------------ workloads
+def make_workload(name: str, rank: int):
+    """-> (label, [(key, ParticleSpawner, translation, rotation)], colliders, fill_frames, bursts)"""
+    base = 1 + rank * 100000
+    ident = (0.0, 0.0, 0.0, 1.0)
+    if name == "c3":
+        sp = W.stress_spawner(rate=19531.0)
+        pos = W.grid_positions(512)
+        return ("C3 stress_test.rs x512 spawners, rate 19531/s, lifetime 1 s (~10 M live particles per GPU)",
+                [(base + i, sp, p, ident) for i, p in enumerate(pos)], None, 64, None)
+    if name == "c2":
+        sp = W.stress_spawner(rate=15625.0)
+        pos = W.grid_positions(64)
+        return ("C2 stress_test.rs x64 spawners, rate 15625/s, lifetime 1 s (~1 M live particles per GPU)",
+                [(base + i, sp, p, ident) for i, p in enumerate(pos)], None, 64, None)
+    if name == "c1":
+        return ("C1 sparks.rs, 1 spawner, rate 6667/s, lifetime 0.75 s (~5 k live particles)",
+                [(base, W.sparks_spawner(6667.0), (0.0, 0.1, 0.0), ident)], None, 50, None)
+    if name == "c5":
+        sp = W.collision_spawner(rate=63000.0)
+        return ("C5 stress_test_collision.rs x8 spawners, rate 63000/s, lifetime 2 s, 256 cuboid colliders (~1 M live)",
+                [(base + i, sp, t, r) for i, (t, r) in enumerate(W.collision_ring(8))],
+                W.collision_scene_colliders(256), 124, None)
+    if name == "c4":
+        return ("C4 one_shot.rs: one new OneShot(100000) spawner per frame, lifetime 2.5 s (~15 M live)",
+                [], None, 152, (W.one_shot_spawner(100000, 2.5), base))
+    raise SystemExit(f"unknown workload {name}")
+
+
+class Scene:
+    """Drives either backend (Engine or OracleWorld: same method names) through the schedule."""
+
+    def __init__(self, backend, workload, rank):
+        self.b = backend
+        self.label, self.spawners, colliders, self.fill_frames, self.bursts = make_workload(workload, rank)
+        if colliders:
+            backend.set_colliders(colliders)
+        from bevy_firework_b200._native import frame_input
+
+        self._frame_input = frame_input
+        inputs = []
+        for key, sp, t, r in self.spawners:
+            ps, nt, es, ne = sp.pods()
+            backend.spawner_reset(key, ps, nt, es, ne, True)
+            inputs.append(frame_input(key, t, r))
+        from bevy_firework_b200 import _abi
+
+        self.inputs = (_abi.fw_spawner_frame_input * max(len(inputs), 1))(*inputs)
+        self.n_inputs = len(inputs)
+        self.frame_no = 0
+        self.live_bursts = []
+        self.updated = 0  # CPU arm: particles that entered the update so far
+
+    def step(self):
+        if self.bursts is not None:  # C4: new spawner each frame, retire the finished one
+            sp, base = self.bursts
+            key = base + self.frame_no
+            ps, nt, es, ne = sp.pods()
+            self.b.spawner_reset(key, ps, nt, es, ne, True)
+            self.live_bursts.append(key)
+            if len(self.live_bursts) > 151:  # lifetime 2.5 s: gone on update #151
+                self.b.spawner_remove(self.live_bursts.pop(0))
+            a = 0.37 * self.frame_no
+            inputs = [self._frame_input(key, (4.0 * np.cos(a), 1.0, 4.0 * np.sin(a)))]
+        else:
+            inputs = None
+        if isinstance(self.b, OracleBackendTag):
+            # spawn_particles ; update_particles, counting the particles that enter the update
+            self.b.spawn_only(DT, inputs if inputs is not None else self.inputs[: self.n_inputs])
+            self.updated += self.b.total_live()
+            self.b.update_only(DT)
+        elif inputs is not None:
+            self.b.frame(DT, inputs)
+        else:
+            self.b._check(self.b._L.fw_frame(self.b._ctx, DT, self.inputs, self.n_inputs))
+        self.frame_no += 1
+
+
+class OracleBackendTag:  # marker base so Scene knows which call convention to use
+    pass
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """NVML samples of SM clock and throttle reasons while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.01):
+        super().__init__(daemon=True)
+        self.period = period_s
+        self.samples, self.reasons = [], set()
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_mhz = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {"sm_mhz": (float(np.median(self.samples)) if self.samples else None),
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def run_cpu(workload: str, steps: int, warmup: int, threads: int):
+    """the reference's CPU path: the C oracle (reference-faithful AoS loop, task per spawner)."""
+    from oracle import oracle as O
+
+    class Backend(O.OracleWorld, OracleBackendTag):
+        pass
+
+    b = Backend(seed=W.SEED, n_threads=threads)
+    sc = Scene(b, workload, 0)
+    for _ in range(sc.fill_frames + warmup):
+        sc.step()
+    sc.updated = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sc.step()
+    dt = time.perf_counter() - t0
+    updated = sc.updated
+    live = b.total_live()
+    b.close()
+    return updated / dt, dt / steps * 1e3, live, sc.label
+
+
+# ------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--cpu-steps", type=int, default=8, help="timed frames of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extract", action="store_true", help="also time the full instance-row extract (D2H)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+
+    # -------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        v, ms, live, label = run_cpu(args.workload, args.steps, args.warmup, cores)
+        line = {
+            "impl": "reference", "metric": "particles updated/sec (fused step)", "value": v, "unit": "particles/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": label, "dt": "fl32(1/60)", "live_particles": live},
+            "cpu_baseline": {"value": v, "unit": "particles/s", "cores": cores, "kind": "port",
+                             "sample": f"full workload, {args.steps} frames after {args.warmup} warm-up frames; "
+                                       "C restatement of the reference loop (no Rust toolchain in the image), "
+                                       f"one task per spawner on {cores} threads, sequential spawn"},
+            "e2e": {"value": v, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # -------------------------------------------------------------- our arm (GPU)
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    from bevy_firework_b200._native import Engine
+
+    eng = Engine(device=local_rank, seed=W.SEED, profile=True)  # raises without the CUDA library
+    sc = Scene(eng, args.workload, rank)
+    for _ in range(sc.fill_frames):  # reach the stationary live count (lifetime/dt + 2 frames)
+        sc.step()
+    eng.sync()
+    live = eng.total_live()
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    sampler = ClockSampler(local_rank)
+    # ---- device-resident throughput: K steps, CUDA events on the launching stream
+    for _ in range(args.warmup):
+        sc.step()
+    barrier()
+    eng.profile_reset()
+    sampler.start()
+    eng.event_record(0)
+    for _ in range(args.steps):
+        sc.step()
+    eng.event_record(1)
+    ms = eng.event_elapsed_ms(0, 1)
+    barrier()
+    clocks = sampler.stop()
+    prof, n_prof = eng.profile_sum()
+    updated = int(prof.particles_updated)
+    assert n_prof == args.steps, (n_prof, args.steps)
+
+    # ---- end to end through the C ABI: host inputs in, per-frame results (counts, AABBs) out
+    keys = [k for k, *_ in sc.spawners]
+    eng.profile_reset()
+    barrier()
+    t0 = time.perf_counter()
+    eng.event_record(2)
+    e2e_steps = max(10, min(args.steps, 200))
+    for _ in range(e2e_steps):
+        sc.step()
+        k_, t_, counts = eng.counts_all()      # fw_sync + D2H of every stream's state
+        if keys:
+            eng.read_aabb(keys[0])             # served from the same snapshot
+    eng.event_record(3)
+    ms_e2e_dev = eng.event_elapsed_ms(2, 3)
+    ms_e2e_wall = (time.perf_counter() - t0) * 1e3
+    prof2, n2 = eng.profile_sum()
+    ms_e2e = max(ms_e2e_dev, ms_e2e_wall)
+    updated_e2e = int(prof2.particles_updated)
+    h2d = int(prof2.h2d_bytes // max(n2, 1))
+    d2h = int(prof2.d2h_bytes // max(n2, 1)) * 2  # async bound readback + the synchronous snapshot
+
+    extract = None
+    if args.extract:
+        cap = eng.total_live() + 4 * 512 * 400
+        host = torch.empty((cap, 16), dtype=torch.float32, pin_memory=True)
+        eng.extract_instances(host.data_ptr(), cap)
+        barrier()
+        t0 = time.perf_counter()
+        rows = 0
+        upd0 = eng.profile_sum()[0].particles_updated
+        for _ in range(10):
+            sc.step()
+            rows = eng.extract_instances(host.data_ptr(), cap)
+        dt_x = time.perf_counter() - t0
+        upd1 = eng.profile_sum()[0].particles_updated
+        extract = {"value": (upd1 - upd0) / dt_x, "unit": "particles/s", "d2h_bytes_per_step": rows * 64,
+                   "ms_per_step": dt_x / 10 * 1e3}
+
+    # ---- reduce over ranks: time = max, work = sum
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ww = torch.tensor([updated, updated_e2e, live, prof.kernel_launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+        ms_all, ms_e2e_all = tt.tolist()
+        updated_all, updated_e2e_all, live_all, launches_all = [int(x) for x in ww.tolist()]
+    else:
+        ms_all, ms_e2e_all, updated_all, updated_e2e_all, live_all, launches_all = ms, ms_e2e, updated, updated_e2e, live, prof.kernel_launches
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        upd_kernel_ms = prof.update_ms / args.steps
+        per_launch_particles = updated / args.steps
+        achieved = ALGO_BYTES_PER_PARTICLE * per_launch_particles / (upd_kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": "particles updated/sec (fused step)", "value": updated_all / (ms_all * 1e-3), "unit": "particles/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": sc.label, "dt": "fl32(1/60)", "live_particles": live_all, "seed": hex(W.SEED),
+                       "streams_per_gpu": len(sc.spawners) or 151, "parallelism": f"shard-by-spawner x{world}",
+                       "l2": "state per GPU (1.6 GB at C3) is larger than the 126 MB L2; no flush between steps",
+                       "fill_frames": sc.fill_frames},
+            "e2e": {"value": updated_e2e_all / (ms_e2e_all * 1e-3), "unit": "particles/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "what": "fw_frame with host input structs + fw_counts_all/fw_read_aabb (sync + D2H) every step"},
+            "gpu_launches": int(launches_all),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "fw::update_kernel<false,false>",
+                         "algorithmic_bytes_per_particle": ALGO_BYTES_PER_PARTICLE,
+                         "particles_per_launch": per_launch_particles, "kernel_ms": upd_kernel_ms,
+                         "peak_source": peak_src},
+            "kernel_ms": {"plan": prof.plan_ms / args.steps, "spawn": prof.spawn_ms / args.steps,
+                          "update": upd_kernel_ms, "frame": prof.total_ms / args.steps},
+            "clocks": clocks,
+        }
+        if extract:
+            line["e2e_extract"] = extract
+        if world == 1 and not args.no_cpu_baseline:
+            eng.close()
+            v, cms, clive, _ = run_cpu(args.workload, args.cpu_steps, 1, cores)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "particles/s", "cores": cores, "kind": "port",
+                "sample": f"full workload ({clive} live particles), {args.cpu_steps} timed frames after the fill "
+                          f"frames, {cms:.1f} ms/frame; C restatement of the reference loop (oracle/fw_oracle.c), "
+                          f"one task per spawner on {cores} threads, sequential spawn"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

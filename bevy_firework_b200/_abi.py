@@ -148,7 +148,8 @@ class fw_spawner_status(C.Structure):
 class fw_frame_profile(C.Structure):
     _fields_ = [("plan_ms", f32), ("spawn_ms", f32), ("update_ms", f32), ("total_ms", f32),
                 ("kernel_launches", u32), ("reserved", u32),
-                ("particles_updated", u64), ("particles_spawned", u64)]
+                ("particles_updated", u64), ("particles_spawned", u64),
+                ("h2d_bytes", u64), ("d2h_bytes", u64)]
 
 
 # numpy structured dtypes of the two row formats (for zero-copy readback)
@@ -202,6 +203,9 @@ EXPORTS = {
     "fw_profile_last": (C.c_int, [_ctx, P(fw_frame_profile)]),
     "fw_profile_sum": (C.c_int, [_ctx, P(fw_frame_profile), P(u32)]),
     "fw_profile_reset": (C.c_int, [_ctx]),
+    "fw_extract_instances": (C.c_int, [_ctx, C.c_void_p, u64, P(u64)]),
+    "fw_event_record": (C.c_int, [_ctx, u32]),
+    "fw_event_elapsed_ms": (C.c_int, [_ctx, u32, u32, P(f32)]),
     "fw_stream_handle": (C.c_void_p, [_ctx]),
 }
 

@@ -196,6 +196,19 @@ class Engine:
         self._check(self._L.fw_pack_instances_device(self._ctx, device_ptr, cap_rows, C.byref(n)))
         return int(n.value)
 
+    def extract_instances(self, host_ptr: int, cap_rows: int) -> int:
+        n = C.c_uint64()
+        self._check(self._L.fw_extract_instances(self._ctx, host_ptr, cap_rows, C.byref(n)))
+        return int(n.value)
+
+    def event_record(self, slot: int):
+        self._check(self._L.fw_event_record(self._ctx, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._check(self._L.fw_event_elapsed_ms(self._ctx, a, b, C.byref(ms)))
+        return float(ms.value)
+
     def profile_last(self) -> _abi.fw_frame_profile:
         p = _abi.fw_frame_profile()
         self._check(self._L.fw_profile_last(self._ctx, C.byref(p)))

@@ -78,6 +78,7 @@ struct FrameSlot {
     bool profiled = false;
     uint64_t particles_spawned = 0;
     uint32_t launches = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
 };
 
 } // namespace
@@ -115,6 +116,9 @@ struct fw_context {
     unsigned long long *d_pack = nullptr; // n_rows + per-slot offsets
     uint32_t pack_cap = 0;
     unsigned long long *h_pack = nullptr; // pinned
+    float4 *d_extract = nullptr;          // staging of fw_extract_instances
+    uint64_t extract_cap = 0;
+    cudaEvent_t user_events[16] = {};
 
     std::map<uint32_t, std::vector<void *>> block_cache; // capacity -> free device blocks
     FrameSlot ring[kRing];
@@ -310,9 +314,18 @@ uint32_t pick_variant(const fw_particle_settings &ps) {
 
 void fill_dev_settings(const fw_particle_settings &ps, DevParticleSettings &d) {
     memset(&d, 0, sizeof(d));
-    d.scale_curve = ps.scale_curve;
-    d.base_color = ps.base_color;
-    d.emissive_color = ps.emissive_color;
+    d.scale_curve.kind = ps.scale_curve.kind;
+    d.scale_curve.n = ps.scale_curve.n;
+    memcpy(d.scale_curve.times, ps.scale_curve.times, sizeof(d.scale_curve.times));
+    memcpy(d.scale_curve.values, ps.scale_curve.values, sizeof(d.scale_curve.values));
+    const fw_gradient *src[2] = {&ps.base_color, &ps.emissive_color};
+    DevGradient *dst[2] = {&d.base_color, &d.emissive_color};
+    for (int k = 0; k < 2; k++) {
+        dst[k]->kind = src[k]->kind;
+        dst[k]->n = src[k]->n;
+        memcpy(dst[k]->times, src[k]->times, sizeof(dst[k]->times));
+        memcpy(dst[k]->colors, src[k]->colors, sizeof(dst[k]->colors));
+    }
     memcpy(d.acceleration, ps.acceleration, sizeof(float) * 3);
     d.linear_drag = ps.linear_drag;
     memcpy(d.angular_acceleration, ps.angular_acceleration, sizeof(float) * 3);
@@ -484,6 +497,8 @@ void absorb_profile(fw_context *ctx, FrameSlot &fs) {
     cudaEventElapsedTime(&p.total_ms, fs.ev[0], fs.ev[3]);
     p.kernel_launches = fs.launches;
     p.particles_spawned = fs.particles_spawned;
+    p.h2d_bytes = fs.h2d_bytes;
+    p.d2h_bytes = fs.d2h_bytes;
     p.particles_updated = fs.plan_host ? fs.plan_host->total_update : 0;
     ctx->prof_last = p;
     ctx->prof_sum.plan_ms += p.plan_ms;
@@ -493,6 +508,8 @@ void absorb_profile(fw_context *ctx, FrameSlot &fs) {
     ctx->prof_sum.kernel_launches += p.kernel_launches;
     ctx->prof_sum.particles_spawned += p.particles_spawned;
     ctx->prof_sum.particles_updated += p.particles_updated;
+    ctx->prof_sum.h2d_bytes += p.h2d_bytes;
+    ctx->prof_sum.d2h_bytes += p.d2h_bytes;
     ctx->prof_frames++;
 }
 
@@ -638,6 +655,9 @@ int fw_destroy(fw_context *ctx) {
     cudaFree(ctx->d_lookback);
     cudaFree(ctx->d_plan);
     cudaFree(ctx->d_pack);
+    cudaFree(ctx->d_extract);
+    for (auto &ev : ctx->user_events)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -927,6 +947,8 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     fs.profiled = prof;
     fs.launches = launches;
     fs.particles_spawned = total_spawn;
+    fs.h2d_bytes = bytes;
+    fs.d2h_bytes = sizeof(StreamState) * (uint64_t)ctx->n_slots + sizeof(PlanOut);
     return FW_OK;
 }
 
@@ -1161,6 +1183,47 @@ int fw_pack_instances_device(fw_context *ctx, void *device_dst, uint64_t cap_row
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (n_rows) *n_rows = *ctx->h_pack;
     if (*ctx->h_pack > cap_rows) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_pack_instances_device: %llu rows, room for %llu", *ctx->h_pack, (unsigned long long)cap_rows);
+    return FW_OK;
+}
+
+int fw_extract_instances(fw_context *ctx, void *host_dst, uint64_t cap_rows, uint64_t *n_rows) {
+    ENTER(ctx);
+    if (!host_dst && cap_rows) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_extract_instances: null destination");
+    uint64_t bound = 0; // host-side upper bound of the live rows, no sync needed
+    for (auto &sp : ctx->spawners)
+        for (Stream &st : sp->streams) bound += std::min<uint64_t>(st.n_hi, st.block.capacity);
+    if (bound > ctx->extract_cap) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_extract) CU(ctx, cudaFree(ctx->d_extract));
+        ctx->d_extract = nullptr;
+        ctx->extract_cap = bound + bound / 8 + 1024;
+        CU(ctx, cudaMalloc((void **)&ctx->d_extract, ctx->extract_cap * 64));
+    }
+    uint64_t n = 0;
+    int rc = fw_pack_instances_device(ctx, ctx->d_extract, ctx->extract_cap, &n);
+    if (rc) return rc;
+    if (n_rows) *n_rows = n;
+    if (n > cap_rows) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_extract_instances: %llu rows, room for %llu", (unsigned long long)n, (unsigned long long)cap_rows);
+    if (n) {
+        CU(ctx, cudaMemcpyAsync(host_dst, ctx->d_extract, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return FW_OK;
+}
+
+int fw_event_record(fw_context *ctx, uint32_t slot) {
+    ENTER(ctx);
+    if (slot >= 16) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_event_record: slot %u out of range", slot);
+    if (!ctx->user_events[slot]) CU(ctx, cudaEventCreate(&ctx->user_events[slot]));
+    CU(ctx, cudaEventRecord(ctx->user_events[slot], ctx->stream));
+    return FW_OK;
+}
+int fw_event_elapsed_ms(fw_context *ctx, uint32_t a, uint32_t b, float *out_ms) {
+    ENTER(ctx);
+    if (a >= 16 || b >= 16 || !ctx->user_events[a] || !ctx->user_events[b] || !out_ms)
+        return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_event_elapsed_ms: markers not recorded");
+    CU(ctx, cudaEventSynchronize(ctx->user_events[b]));
+    CU(ctx, cudaEventElapsedTime(out_ms, ctx->user_events[a], ctx->user_events[b]));
     return FW_OK;
 }
 

@@ -37,10 +37,22 @@ enum Variant : uint32_t {
 
 // update-relevant part of fw_particle_settings; staged into shared memory once per tile with a
 // bulk async copy, so sizeof must be a multiple of 16.
+// device forms of fw_curve_f32 / fw_gradient with 16-byte aligned tables
+struct alignas(16) DevCurve {
+    float times[FW_MAX_KNOTS];
+    float values[FW_MAX_KNOTS];
+    uint32_t kind, n, pad[2];
+};
+struct alignas(16) DevGradient {
+    float4 colors[FW_MAX_KNOTS];
+    float times[FW_MAX_KNOTS];
+    uint32_t kind, n, pad[2];
+};
+
 struct alignas(16) DevParticleSettings {
-    fw_curve_f32 scale_curve;   // 136 B
-    fw_gradient base_color;     // 328 B
-    fw_gradient emissive_color; // 328 B
+    DevCurve scale_curve;       // 144 B
+    DevGradient base_color;     // 336 B
+    DevGradient emissive_color; // 336 B
     float acceleration[3];
     float linear_drag;
     float angular_acceleration[3];

@@ -155,7 +155,7 @@ __device__ __forceinline__ Interp uneven_interp(const float *times, uint32_t n, 
     return r;
 }
 // FireworkCurve<f32>::sample_clamped (reference src/core.rs:603)
-__device__ __forceinline__ float sample_curve(const fw_curve_f32 &c, float t) {
+__device__ __forceinline__ float sample_curve(const DevCurve &c, float t) {
     if (c.kind == FW_CURVE_CONSTANT) return c.values[0];
     t = clamp01(t);
     Interp it = (c.kind == FW_CURVE_EVEN) ? even_interp(c.n, t) : uneven_interp(c.times, c.n, t);
@@ -166,8 +166,8 @@ __device__ __forceinline__ float sample_curve(const fw_curve_f32 &c, float t) {
 }
 // FireworkGradient<LinearRgba>::sample_clamped (reference src/core.rs:460-461,653,655);
 // bevy_color Mix: a*(1-s) + b*s per channel
-__device__ __forceinline__ float4 sample_gradient(const fw_gradient &g, float t) {
-    const float4 *colors = reinterpret_cast<const float4 *>(&g.colors[0][0]);
+__device__ __forceinline__ float4 sample_gradient(const DevGradient &g, float t) {
+    const float4 *colors = g.colors;
     if (g.kind == FW_CURVE_CONSTANT) return colors[0];
     t = clamp01(t);
     Interp it = (g.kind == FW_CURVE_EVEN) ? even_interp(g.n, t) : uneven_interp(g.times, g.n, t);

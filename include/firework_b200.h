@@ -232,6 +232,8 @@ typedef struct fw_frame_profile {
     uint32_t reserved;
     uint64_t particles_updated; /* live particles entering the update of that frame */
     uint64_t particles_spawned;
+    uint64_t h2d_bytes; /* per-frame parameter block copied host -> device */
+    uint64_t d2h_bytes; /* per-frame state readback copied device -> host */
 } fw_frame_profile;
 
 const char *fw_last_global_error(void);
@@ -305,6 +307,16 @@ int fw_total_live(fw_context *ctx, uint64_t *out);
 int fw_profile_last(fw_context *ctx, fw_frame_profile *out);
 int fw_profile_sum(fw_context *ctx, fw_frame_profile *out, uint32_t *n_frames);
 int fw_profile_reset(fw_context *ctx);
+
+/* render extract: the live ParticleInstance rows of every stream (same order as
+ * fw_pack_instances_device) copied into ONE caller-owned HOST buffer (pinned memory makes it a
+ * single DMA). Synchronises. */
+int fw_extract_instances(fw_context *ctx, void *host_dst, uint64_t cap_rows, uint64_t *n_rows);
+
+/* CUDA-event stopwatch on the context's stream: record marker `slot` (0..15) now; elapsed
+ * milliseconds between two recorded markers (synchronises on the later one). */
+int fw_event_record(fw_context *ctx, uint32_t slot);
+int fw_event_elapsed_ms(fw_context *ctx, uint32_t slot_begin, uint32_t slot_end, float *out_ms);
 
 /* the stream every launch of the context goes to (cudaStream_t) */
 void *fw_stream_handle(fw_context *ctx);

@@ -213,7 +213,7 @@ def test_one_shot_bursts_c4_reduced(engine, oracle):
             assert engine.total_live() == w.total_live()
             assert_rows_match(engine.read_particles(live[0], 0), w.read_particles(live[0], 0),
                               exact=("age", "lifetime", "initial_scale", "base_color", "emissive_color"))
-    assert len(live) == 31  # lifetime 0.5 s -> removed on update #31
+    assert len(live) == 29  # lifetime 0.5 s: the f32 age sum reaches 0.5 on update #30
 
 
 def test_random_lifetime_compaction(engine, oracle):
