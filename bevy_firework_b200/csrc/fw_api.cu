@@ -107,7 +107,9 @@ struct fw_context {
     fw_emission_settings *d_emitters = nullptr;
     fw_collider *d_colliders = nullptr;
     uint32_t n_colliders = 0;
-    TileEntry *d_tiles = nullptr;
+    uint32_t *d_tile_prefix = nullptr; // kNumVariants x (slots_cap + 1)
+    uint8_t *d_stage = nullptr;        // staging of ParticleData rows (host mirror reads/writes)
+    size_t stage_bytes = 0;
     unsigned long long *d_lookback = nullptr;
     uint32_t tiles_cap = 0;
     uint64_t tiles_needed = 0; // sum over streams of ceil(capacity / kTile)
@@ -210,14 +212,13 @@ inline uint32_t round_capacity(uint64_t want) {
     if (r > 0xFFFFFF00ull) r = 0xFFFFFF00ull;
     return (uint32_t)r;
 }
-inline size_t block_bytes(uint32_t cap) { return (size_t)cap * 100u; }
-inline void block_arrays(const Block &b, StreamDesc &d) {
-    uint8_t *p = (uint8_t *)b.base;
-    d.rows = (float4 *)p;
-    d.s0 = (float4 *)(p + (size_t)b.capacity * 64u);
-    d.s1 = (float4 *)(p + (size_t)b.capacity * 80u);
-    d.s2 = (float *)(p + (size_t)b.capacity * 96u);
+inline size_t block_bytes(uint32_t cap) { return (size_t)cap * kBytesPerSlot; }
+inline StreamDesc block_desc(const Block &b, uint32_t variant) {
+    StreamDesc d{};
+    d.base = (uint8_t *)b.base;
     d.capacity = b.capacity;
+    d.variant = variant;
+    return d;
 }
 
 int alloc_block(fw_context *ctx, uint32_t capacity, Block &out) {
@@ -270,6 +271,9 @@ int ensure_slots(fw_context *ctx, uint32_t need) {
     if ((rc = grow_device_array(ctx, ctx->d_descs, ctx->slots_cap, ncap))) return rc;
     if ((rc = grow_device_array(ctx, ctx->d_states, ctx->slots_cap, ncap))) return rc;
     if ((rc = grow_device_array(ctx, ctx->d_settings, ctx->slots_cap, ncap))) return rc;
+    if (ctx->d_tile_prefix) CU(ctx, cudaFree(ctx->d_tile_prefix));
+    ctx->d_tile_prefix = nullptr;
+    CU(ctx, cudaMalloc((void **)&ctx->d_tile_prefix, sizeof(uint32_t) * (size_t)kNumVariants * (ncap + 1)));
     ctx->h_descs.resize(ncap);
     ctx->slot_owner.resize(ncap, nullptr);
     ctx->slots_cap = ncap;
@@ -291,11 +295,8 @@ int ensure_tiles(fw_context *ctx) {
     while (ncap < need) ncap *= 2;
     if (ncap > 0xFFFFFFFFull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "tile table too large");
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->d_tiles) CU(ctx, cudaFree(ctx->d_tiles));
     if (ctx->d_lookback) CU(ctx, cudaFree(ctx->d_lookback));
-    ctx->d_tiles = nullptr;
     ctx->d_lookback = nullptr;
-    CU(ctx, cudaMalloc((void **)&ctx->d_tiles, sizeof(TileEntry) * ncap));
     CU(ctx, cudaMalloc((void **)&ctx->d_lookback, sizeof(unsigned long long) * ncap));
     CU(ctx, cudaMemsetAsync(ctx->d_lookback, 0, sizeof(unsigned long long) * ncap, ctx->stream));
     ctx->tiles_cap = (uint32_t)ncap;
@@ -384,10 +385,7 @@ void free_spawner_resources(fw_context *ctx, Spawner &sp) {
 }
 
 int upload_desc(fw_context *ctx, const Stream &st) {
-    StreamDesc d{};
-    block_arrays(st.block, d);
-    d.settings_idx = st.slot;
-    d.variant = st.variant;
+    const StreamDesc d = block_desc(st.block, st.variant);
     ctx->h_descs[st.slot] = d;
     CU(ctx, cudaMemcpyAsync(ctx->d_descs + st.slot, &d, sizeof(d), cudaMemcpyHostToDevice, ctx->stream));
     return FW_OK;
@@ -440,20 +438,8 @@ int grow_stream(fw_context *ctx, Stream &st, uint64_t need) {
     Block nb;
     int rc = alloc_block(ctx, ncap, nb);
     if (rc) return rc;
-    StreamDesc od{}, nd{};
-    block_arrays(st.block, od);
-    block_arrays(nb, nd);
-    const uint32_t seg1 = std::min(live, st.block.capacity - first), seg2 = live - seg1;
-    auto copy = [&](void *dst, const void *src, size_t elem) -> cudaError_t {
-        cudaError_t e = cudaSuccess;
-        if (seg1) e = cudaMemcpyAsync(dst, (const uint8_t *)src + (size_t)first * elem, (size_t)seg1 * elem, cudaMemcpyDeviceToDevice, ctx->stream);
-        if (e == cudaSuccess && seg2) e = cudaMemcpyAsync((uint8_t *)dst + (size_t)seg1 * elem, src, (size_t)seg2 * elem, cudaMemcpyDeviceToDevice, ctx->stream);
-        return e;
-    };
-    CU(ctx, copy(nd.rows, od.rows, 64));
-    CU(ctx, copy(nd.s0, od.s0, 16));
-    CU(ctx, copy(nd.s1, od.s1, 16));
-    CU(ctx, copy(nd.s2, od.s2, 4));
+    // unwrap the ring into the start of the new block
+    CU(ctx, launch_ring_copy(block_desc(st.block, st.variant), first, live, block_desc(nb, st.variant), ctx->stream));
     StreamState ns = s;
     ns.head = 0;
     ns.count = live;
@@ -529,33 +515,23 @@ Spawner *find(fw_context *ctx, uint32_t key) {
     return it == ctx->by_key.end() ? nullptr : it->second;
 }
 
-// stream rows -> host arrays (ring unwrapped), after a sync
-int read_stream_arrays(fw_context *ctx, const Stream &st, std::vector<float> &rows, std::vector<float> &s0,
-                       std::vector<float> &s1, std::vector<float> &s2, uint32_t &live) {
-    int rc = refresh_exact(ctx);
-    if (rc) return rc;
+// device staging buffer for ParticleData / ParticleInstance rows of one stream
+int ensure_stage(fw_context *ctx, size_t bytes) {
+    if (bytes <= ctx->stage_bytes) return FW_OK;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_stage) CU(ctx, cudaFree(ctx->d_stage));
+    ctx->d_stage = nullptr;
+    ctx->stage_bytes = 0;
+    const size_t nb = bytes + bytes / 4 + 4096;
+    CU(ctx, cudaMalloc((void **)&ctx->d_stage, nb));
+    ctx->stage_bytes = nb;
+    return FW_OK;
+}
+// first live slot and live count of a stream from the exact snapshot
+inline void live_range(const fw_context *ctx, const Stream &st, uint32_t &first, uint32_t &live) {
     const StreamState s = ctx->snapshot[st.slot];
     live = s.count - s.dead;
-    const uint32_t cap = st.block.capacity;
-    const uint32_t first = (s.head + (is_fifo(st.variant) ? s.dead : 0u)) % std::max(1u, cap);
-    rows.resize((size_t)live * 16);
-    s0.resize((size_t)live * 4);
-    s1.resize((size_t)live * 4);
-    s2.resize(live);
-    if (!live) return FW_OK;
-    StreamDesc d{};
-    block_arrays(st.block, d);
-    const uint32_t seg1 = std::min(live, cap - first), seg2 = live - seg1;
-    auto copy = [&](void *dst, const void *src, size_t elem) -> cudaError_t {
-        cudaError_t e = cudaMemcpy(dst, (const uint8_t *)src + (size_t)first * elem, (size_t)seg1 * elem, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess && seg2) e = cudaMemcpy((uint8_t *)dst + (size_t)seg1 * elem, src, (size_t)seg2 * elem, cudaMemcpyDeviceToHost);
-        return e;
-    };
-    CU(ctx, copy(rows.data(), d.rows, 64));
-    CU(ctx, copy(s0.data(), d.s0, 16));
-    CU(ctx, copy(s1.data(), d.s1, 16));
-    CU(ctx, copy(s2.data(), d.s2, 4));
-    return FW_OK;
+    first = (s.head + (is_fifo(st.variant) ? s.dead : 0u)) % std::max(1u, st.block.capacity);
 }
 
 inline float dec_f32(uint32_t u) {
@@ -651,7 +627,8 @@ int fw_destroy(fw_context *ctx) {
     cudaFree(ctx->d_settings);
     cudaFree(ctx->d_emitters);
     cudaFree(ctx->d_colliders);
-    cudaFree(ctx->d_tiles);
+    cudaFree(ctx->d_tile_prefix);
+    cudaFree(ctx->d_stage);
     cudaFree(ctx->d_lookback);
     cudaFree(ctx->d_plan);
     cudaFree(ctx->d_pack);
@@ -909,8 +886,9 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     t.emitters = ctx->d_emitters;
     t.colliders = ctx->d_colliders;
     t.n_colliders = ctx->n_colliders;
-    t.tiles = ctx->d_tiles;
-    t.tiles_capacity = ctx->tiles_cap;
+    t.tile_prefix = ctx->d_tile_prefix;
+    t.slots_cap = ctx->slots_cap;
+    t.lookback_capacity = ctx->tiles_cap;
     t.plan = ctx->d_plan;
     t.lookback = ctx->d_lookback;
     t.seed = ctx->seed;
@@ -923,7 +901,10 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     const bool prof = (ctx->flags & FW_FLAG_PROFILE) != 0;
     uint32_t launches = 0;
     if (prof) CU(ctx, cudaEventRecord(fs.ev[0], ctx->stream));
-    CU(ctx, launch_plan(t, f, ctx->stream));
+    uint32_t variant_mask = 0;
+    for (uint32_t v = 0; v < kNumVariants; v++)
+        if (ctx->variant_streams[v]) variant_mask |= 1u << v;
+    CU(ctx, launch_plan(t, f, variant_mask, ctx->stream));
     launches++;
     if (prof) CU(ctx, cudaEventRecord(fs.ev[1], ctx->stream));
     if (total_spawn) {
@@ -1039,27 +1020,18 @@ int fw_read_particles(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_
     Spawner *sp = find(ctx, key);
     if (!sp || type >= sp->streams.size()) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_read_particles: unknown spawner %u / type %u", key, type);
     const Stream &st = sp->streams[type];
-    std::vector<float> rows, s0, s1, s2;
-    uint32_t live = 0;
-    int rc = read_stream_arrays(ctx, st, rows, s0, s1, s2, live);
+    int rc = refresh_exact(ctx);
     if (rc) return rc;
+    uint32_t first, live;
+    live_range(ctx, st, first, live);
     if (n) *n = live;
     if (live > cap || (live && !out)) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_read_particles: %u particles, room for %llu", live, (unsigned long long)cap);
-    for (uint32_t i = 0; i < live; i++) {
-        fw_particle_data &p = out[i];
-        const float *r = &rows[(size_t)i * 16];
-        memcpy(p.position, r, 12);
-        p.scale = r[3];
-        memcpy(p.rotation, r + 4, 16);
-        memcpy(p.base_color, r + 8, 16);
-        memcpy(p.emissive_color, r + 12, 16);
-        memcpy(p.velocity, &s0[(size_t)i * 4], 12);
-        p.age = s0[(size_t)i * 4 + 3];
-        memcpy(p.angular_velocity, &s1[(size_t)i * 4], 12);
-        p.lifetime = s1[(size_t)i * 4 + 3];
-        p.initial_scale = s2[i];
-        p.pbr = st.ps.pbr; // src/core.rs:462: a copy of the type's setting
-    }
+    if (!live) return FW_OK;
+    if ((rc = ensure_stage(ctx, (size_t)live * sizeof(fw_particle_data)))) return rc;
+    // pbr is a copy of the type's setting (src/core.rs:462)
+    CU(ctx, launch_gather_particles(block_desc(st.block, st.variant), first, live, st.ps.pbr, (fw_particle_data *)ctx->d_stage, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out, ctx->d_stage, (size_t)live * sizeof(fw_particle_data), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return FW_OK;
 }
 
@@ -1078,33 +1050,16 @@ int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_pa
         if ((rc = grow_stream(ctx, st, n))) return rc;
         if ((rc = ensure_tiles(ctx))) return rc;
     }
-    std::vector<float> rows((size_t)n * 16), s0((size_t)n * 4), s1((size_t)n * 4), s2(n);
-    for (uint64_t i = 0; i < n; i++) {
-        const fw_particle_data &p = in[i];
-        float *r = &rows[(size_t)i * 16];
-        memcpy(r, p.position, 12);
-        r[3] = p.scale;
-        memcpy(r + 4, p.rotation, 16);
-        memcpy(r + 8, p.base_color, 16);
-        memcpy(r + 12, p.emissive_color, 16);
-        memcpy(&s0[(size_t)i * 4], p.velocity, 12);
-        s0[(size_t)i * 4 + 3] = p.age;
-        memcpy(&s1[(size_t)i * 4], p.angular_velocity, 12);
-        s1[(size_t)i * 4 + 3] = p.lifetime;
-        s2[i] = p.initial_scale;
-    }
-    StreamDesc d{};
-    block_arrays(st.block, d);
     if (n) {
-        CU(ctx, cudaMemcpy(d.rows, rows.data(), (size_t)n * 64, cudaMemcpyHostToDevice));
-        CU(ctx, cudaMemcpy(d.s0, s0.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
-        CU(ctx, cudaMemcpy(d.s1, s1.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
-        CU(ctx, cudaMemcpy(d.s2, s2.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+        if ((rc = ensure_stage(ctx, (size_t)n * sizeof(fw_particle_data)))) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->d_stage, in, (size_t)n * sizeof(fw_particle_data), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, launch_scatter_particles(block_desc(st.block, st.variant), (uint32_t)n, (const fw_particle_data *)ctx->d_stage, ctx->stream));
     }
     StreamState ns{};
     ns.count = (uint32_t)n;
     ns.aabb_min[0] = ns.aabb_min[1] = ns.aabb_min[2] = 0xFFFFFFFFu;
-    CU(ctx, cudaMemcpy(ctx->d_states + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpyAsync(ctx->d_states + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     st.n_hi = n;
     st.born_frame = ctx->frame_no + 1;
     return FW_OK;
@@ -1117,18 +1072,20 @@ int fw_read_instances(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_
     const Stream &st = sp->streams[type];
     int rc = refresh_exact(ctx);
     if (rc) return rc;
-    const StreamState s = ctx->snapshot[st.slot];
-    const uint32_t live = s.count - s.dead;
+    uint32_t first, live;
+    live_range(ctx, st, first, live);
     if (n) *n = live;
     if (live > cap || (live && !out)) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_read_instances: %u rows, room for %llu", live, (unsigned long long)cap);
     if (!live) return FW_OK;
-    const uint32_t capn = st.block.capacity;
-    const uint32_t first = (s.head + (is_fifo(st.variant) ? s.dead : 0u)) % capn;
-    const uint32_t seg1 = std::min(live, capn - first), seg2 = live - seg1;
-    StreamDesc d{};
-    block_arrays(st.block, d);
-    CU(ctx, cudaMemcpy(out, (const uint8_t *)d.rows + (size_t)first * 64, (size_t)seg1 * 64, cudaMemcpyDeviceToHost));
-    if (seg2) CU(ctx, cudaMemcpy((uint8_t *)out + (size_t)seg1 * 64, d.rows, (size_t)seg2 * 64, cudaMemcpyDeviceToHost));
+    // rows of this one stream: [n_rows, offset] words then the rows
+    const size_t hdr = 64;
+    if ((rc = ensure_stage(ctx, hdr + (size_t)live * 64))) return rc;
+    DeviceTables t{};
+    t.descs = ctx->d_descs;
+    t.states = ctx->d_states;
+    CU(ctx, launch_pack_instances(t, st.slot, st.slot + 1, (float4 *)(ctx->d_stage + hdr), live, (unsigned long long *)ctx->d_stage, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out, ctx->d_stage + hdr, (size_t)live * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return FW_OK;
 }
 
@@ -1178,7 +1135,7 @@ int fw_pack_instances_device(fw_context *ctx, void *device_dst, uint64_t cap_row
     DeviceTables t{};
     t.descs = ctx->d_descs;
     t.states = ctx->d_states;
-    CU(ctx, launch_pack_instances(t, ctx->n_slots, (float4 *)device_dst, cap_rows, ctx->d_pack, ctx->stream));
+    CU(ctx, launch_pack_instances(t, 0, ctx->n_slots, (float4 *)device_dst, cap_rows, ctx->d_pack, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->h_pack, ctx->d_pack, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (n_rows) *n_rows = *ctx->h_pack;

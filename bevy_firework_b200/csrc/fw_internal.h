@@ -1,16 +1,27 @@
 // fw_internal.h -- structures shared by the host side (fw_api.cu) and the kernels
 // (fw_kernels.cu) of libfirework_b200.so. Not part of the public ABI.
 //
-// Device data layout (one *stream* = one (spawner, particle type) vector
-// `data.particles[i]`, reference src/core.rs:274):
+// Device data layout. One *stream* = one (spawner, particle type) vector
+// `data.particles[i]` (reference src/core.rs:274). A stream owns one device block of
+// `capacity` particle slots holding eight structure-of-arrays packs, laid out so that the
+// update kernel moves exactly the algorithmic bytes of the reference's per-particle step
+// (64 B read + 92 B written) with 16/8/4-byte fully coalesced accesses:
 //
-//   rows : float4[4*capacity]  the 64-byte ParticleInstance row of reference
-//                              src/render.rs:95-103, AoS: [pos.xyz,scale][rot][base][emissive].
-//                              It IS the live state for position/scale/rotation and at the same
-//                              time the vertex-instance buffer a renderer consumes.
-//   s0   : float4[capacity]    velocity.xyz, age
-//   s1   : float4[capacity]    angular_velocity.xyz, lifetime
-//   s2   : float [capacity]    initial_scale
+//   pack  offset      type    contents                       update reads  update writes
+//   m0    0           float4  position.xyz, age                   16            16
+//   m1    16*cap      float4  rotation (x,y,z,w)                  16            16
+//   m2    32*cap      float4  velocity.xyz, angular_velocity.x    16            16
+//   m3    48*cap      float2  angular_velocity.y, .z               8             8
+//   k     56*cap      float2  lifetime, initial_scale              8             -  (constants)
+//   o0    64*cap      float4  base_color                           -            16
+//   o1    80*cap      float4  emissive_color                       -            16
+//   o2    96*cap      float   scale                                -             4
+//                                                         total   64            92   = 156 B
+//
+// (An earlier layout kept the 64-byte ParticleInstance row of reference src/render.rs:95-103
+// resident as AoS; ncu showed DRAM fetching the whole 64-byte row to read its 32-byte state
+// half: +0.32 GB per 10 M particles, profiles/r1_a_*. Rows are now assembled by the
+// pack/extract kernel, which every render hand-off needs anyway.)
 //
 // Each stream is a ring: logical particle i (the reference's Vec index) lives in slot
 // (head + i) mod capacity. Order inside the ring == the reference's Vec order (survivors keep
@@ -23,20 +34,19 @@
 
 namespace fw {
 
-constexpr int kTile = 256;          // particles per update tile == threads per CTA
+constexpr int kTile = 256; // particles per update tile == threads per CTA
 constexpr int kUpdateThreads = 256;
+constexpr uint32_t kBytesPerSlot = 100;
 
-// variants of the update kernel (one tile table each)
+// variants of the update kernel
 enum Variant : uint32_t {
-    kFifo = 0,          // constant lifetime, no destroy-on-collision: deaths are a prefix
-    kCompact = 1,       // anything else: in-place stable compaction (decoupled look-back)
+    kFifo = 0,    // constant lifetime, no destroy-on-collision: deaths are a prefix of the Vec
+    kCompact = 1, // anything else: in-place stable compaction (decoupled look-back)
     kFifoCollide = 2,
     kCompactCollide = 3,
     kNumVariants = 4
 };
 
-// update-relevant part of fw_particle_settings; staged into shared memory once per tile with a
-// bulk async copy, so sizeof must be a multiple of 16.
 // device forms of fw_curve_f32 / fw_gradient with 16-byte aligned tables
 struct alignas(16) DevCurve {
     float times[FW_MAX_KNOTS];
@@ -49,6 +59,8 @@ struct alignas(16) DevGradient {
     uint32_t kind, n, pad[2];
 };
 
+// per-stream settings; staged into shared memory once per tile with a bulk async copy (TMA
+// unit), so sizeof must be a multiple of 16.
 struct alignas(16) DevParticleSettings {
     DevCurve scale_curve;       // 144 B
     DevGradient base_color;     // 336 B
@@ -66,15 +78,31 @@ struct alignas(16) DevParticleSettings {
 static_assert(sizeof(DevParticleSettings) % 16 == 0, "bulk copy needs a 16-byte multiple");
 
 struct StreamDesc { // written by the host when a stream is created / grown / removed
-    float4 *rows;
-    float4 *s0;
-    float4 *s1;
-    float *s2;
-    uint32_t capacity; // 0 = slot unused
-    uint32_t settings_idx;
+    uint8_t *base;     // device block of capacity * kBytesPerSlot bytes, 256-byte aligned
+    uint32_t capacity; // multiple of 256; 0 = slot unused
     uint32_t variant;
-    uint32_t pad;
 };
+
+// typed views of a stream block
+struct StreamArrays {
+    float4 *m0, *m1, *m2;
+    float2 *m3, *k;
+    float4 *o0, *o1;
+    float *o2;
+};
+__host__ __device__ inline StreamArrays stream_arrays(uint8_t *base, uint32_t cap) {
+    StreamArrays a;
+    const size_t c = cap;
+    a.m0 = (float4 *)(base);
+    a.m1 = (float4 *)(base + 16 * c);
+    a.m2 = (float4 *)(base + 32 * c);
+    a.m3 = (float2 *)(base + 48 * c);
+    a.k = (float2 *)(base + 56 * c);
+    a.o0 = (float4 *)(base + 64 * c);
+    a.o1 = (float4 *)(base + 80 * c);
+    a.o2 = (float *)(base + 96 * c);
+    return a;
+}
 
 struct StreamState { // mutated by kernels
     uint32_t head;
@@ -83,25 +111,20 @@ struct StreamState { // mutated by kernels
     uint32_t spawn_base; // logical index of this frame's first spawned particle
     uint32_t aabb_min[3]; // order-preserving uint encoding of float
     uint32_t aabb_max[3];
-    uint32_t overflow;   // spawns dropped because the ring was full (host grows before that)
+    uint32_t overflow; // spawns dropped because the ring was full (the host grows before that)
     uint32_t pad;
-};
-
-struct TileEntry {
-    uint32_t stream;
-    uint32_t tile; // tile index inside the stream
 };
 
 struct SpawnCmd { // one per (emitter, frame) with count > 0
     uint32_t stream;
-    uint32_t emitter_idx;  // index into the device fw_emission_settings array
-    uint32_t input_idx;    // index into the per-frame SpawnerInput array
+    uint32_t emitter_idx;   // index into the device fw_emission_settings array
+    uint32_t input_idx;     // index into the per-frame SpawnerInput array
     uint32_t count;
-    uint32_t first;        // exclusive prefix of count over the commands of the frame
-    uint32_t dst_off;      // offset inside the block appended to the stream this frame
-    uint32_t spawner_key;  // RNG protocol
+    uint32_t first;         // exclusive prefix of count over the commands of the frame
+    uint32_t dst_off;       // offset inside the block appended to the stream this frame
+    uint32_t spawner_key;   // RNG protocol
     uint32_t emitter_local; // emitter index inside its spawner (RNG protocol)
-    uint64_t serial_base;  // first particle serial of this command
+    uint64_t serial_base;   // first particle serial of this command
 };
 
 struct SpawnerInput {
@@ -114,7 +137,7 @@ struct SpawnerInput {
 
 struct FrameHeader {
     float dt;
-    uint32_t n_slots;     // stream slots to scan
+    uint32_t n_slots; // stream slots to scan
     uint32_t n_cmds;
     uint32_t total_spawn;
     uint32_t epoch;
@@ -123,7 +146,7 @@ struct FrameHeader {
 
 struct PlanOut { // device, written by the plan kernel
     uint32_t n_tiles[kNumVariants];
-    uint32_t tile_base[kNumVariants]; // start of each variant inside the tile table
+    uint32_t tile_base[kNumVariants]; // start of each variant inside the look-back array
     uint32_t error_flags;
     uint32_t total_update; // particles entering the update this frame
     uint32_t pad[2];
@@ -132,12 +155,14 @@ struct PlanOut { // device, written by the plan kernel
 struct DeviceTables {
     const StreamDesc *descs;
     StreamState *states;
-    const DevParticleSettings *settings;
+    const DevParticleSettings *settings; // indexed by stream slot
     const fw_emission_settings *emitters;
     const fw_collider *colliders;
     uint32_t n_colliders;
-    TileEntry *tiles;
-    uint32_t tiles_capacity;
+    // tile_prefix[v * slots_cap + s] = number of update tiles of variant v in slots < s
+    uint32_t *tile_prefix;
+    uint32_t slots_cap;
+    uint32_t lookback_capacity;
     PlanOut *plan;
     unsigned long long *lookback; // one status word per tile (compact variants)
     uint64_t seed;
@@ -151,13 +176,18 @@ struct FrameDeviceInputs {
 };
 
 // launchers (fw_kernels.cu)
-cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, cudaStream_t s);
-cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t total_spawn,
-                         cudaStream_t s);
-cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant,
-                          int grid, cudaStream_t s);
+cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant_mask, cudaStream_t s);
+cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t total_spawn, cudaStream_t s);
+cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, cudaStream_t s);
 cudaError_t update_grid_size(int device, int *grids /*[kNumVariants]*/);
-cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t n_slots, float4 *dst,
-                                  uint64_t cap_rows, unsigned long long *n_rows, cudaStream_t s);
+// live ParticleInstance rows of the streams [slot_begin, slot_end) -> contiguous 64-byte rows
+cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, float4 *dst,
+                                  uint64_t cap_rows, unsigned long long *n_rows_and_offsets, cudaStream_t s);
+// one stream <-> fw_particle_data rows (host mirror / fw_write_particles)
+cudaError_t launch_gather_particles(const StreamDesc &d, uint32_t first, uint32_t n, uint32_t pbr,
+                                    fw_particle_data *dst, cudaStream_t s);
+cudaError_t launch_scatter_particles(const StreamDesc &d, uint32_t n, const fw_particle_data *src, cudaStream_t s);
+// ring -> linear copy into a bigger block (growth)
+cudaError_t launch_ring_copy(const StreamDesc &src, uint32_t first, uint32_t n, const StreamDesc &dst, cudaStream_t s);
 
 } // namespace fw

@@ -1,15 +1,19 @@
 // fw_kernels.cu -- sm_100a kernels of the particle path.
 //
 //   plan_kernel    applies last frame's deaths to every ring (head/count), appends this
-//                  frame's spawn counts, and builds the per-variant tile tables
+//                  frame's spawn counts, and builds the per-variant tile prefix table
 //   spawn_kernel   reference src/core.rs:437-469 + src/emission_shape.rs:18-39, one thread per
 //                  new particle, Philox4x32-10 counter-based draws
-//   update_kernel  reference src/core.rs:591-658 (+ :744-800 when COLLIDE), fused with the
-//                  ParticleInstance row conversion (src/render.rs:105-115), death handling
-//                  and the per-stream AABB reduction (src/render.rs:677-703)
-//   pack_kernel    gathers the live instance rows of all streams into one contiguous buffer
+//   update_kernel  reference src/core.rs:591-658 (+ :744-800 when COLLIDE), fused with death
+//                  handling (FIFO ring advance or in-place stable compaction) and the
+//                  per-stream AABB reduction (src/render.rs:677-703)
+//   pack kernels   assemble the 64-byte ParticleInstance rows (src/render.rs:95-115) of the
+//                  live particles into one contiguous buffer (render extract / all-gather)
+//   gather/scatter ParticleData rows of one stream <-> the SoA packs (host mirror)
 //
 // Built with -fmad=false (see fw_math.cuh).
+#include <algorithm>
+
 #include "fw_math.cuh"
 
 namespace fw {
@@ -45,11 +49,12 @@ __device__ __forceinline__ uint32_t block_inclusive_scan(uint32_t v, uint32_t *w
 }
 
 constexpr uint32_t kErrOverflow = 1u;
-constexpr uint32_t kErrTileTable = 2u;
+constexpr uint32_t kErrLookback = 2u;
 
-__global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceInputs f) {
+__global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant_mask) {
     __shared__ uint32_t warp_sums[32];
     const uint32_t n_slots = f.header->n_slots;
+    const uint32_t stride = t.slots_cap + 1u;
     uint32_t my_total = 0;
     for (uint32_t s = threadIdx.x; s < n_slots; s += blockDim.x) {
         const StreamDesc d = t.descs[s];
@@ -77,22 +82,25 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
     uint32_t base_total = 0;
     for (uint32_t v = 0; v < kNumVariants; v++) {
         uint32_t carry = 0;
-        for (uint32_t chunk = 0; chunk < n_slots; chunk += blockDim.x) {
-            const uint32_t s = chunk + threadIdx.x;
-            uint32_t tiles = 0;
-            if (s < n_slots) {
-                const StreamDesc d = t.descs[s];
-                if (d.capacity != 0u && d.variant == v) tiles = (t.states[s].count + kTile - 1u) / kTile;
+        if (variant_mask & (1u << v)) {
+            uint32_t *prefix = t.tile_prefix + (size_t)v * stride;
+            for (uint32_t chunk = 0; chunk < n_slots; chunk += blockDim.x) {
+                const uint32_t s = chunk + threadIdx.x;
+                uint32_t tiles = 0;
+                if (s < n_slots) {
+                    const StreamDesc d = t.descs[s];
+                    if (d.capacity != 0u && d.variant == v) tiles = (t.states[s].count + kTile - 1u) / kTile;
+                }
+                uint32_t total;
+                const uint32_t incl = block_inclusive_scan(tiles, warp_sums, total);
+                if (s < n_slots) prefix[s] = carry + incl - tiles;
+                carry += total;
             }
-            uint32_t total;
-            const uint32_t incl = block_inclusive_scan(tiles, warp_sums, total);
-            uint32_t at = base_total + carry + incl - tiles;
-            if (at + tiles > t.tiles_capacity) {
-                if (tiles) atomicOr(&t.plan->error_flags, kErrTileTable);
-            } else {
-                for (uint32_t j = 0; j < tiles; j++) t.tiles[at + j] = TileEntry{s, j};
+            if (threadIdx.x == 0) {
+                prefix[n_slots] = carry; // sentinel: total tiles of the variant
+                if ((v == kCompact || v == kCompactCollide) && base_total + carry > t.lookback_capacity)
+                    atomicOr(&t.plan->error_flags, kErrLookback);
             }
-            carry += total;
         }
         if (threadIdx.x == 0) {
             t.plan->tile_base[v] = base_total;
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(256) spawn_kernel(DeviceTables t, FrameDeviceI
     const uint32_t slot = wrap(st.head + logical, d.capacity);
 
     const fw_emission_settings &es = t.emitters[cmd.emitter_idx];
-    const DevParticleSettings &ps = t.settings[d.settings_idx];
+    const DevParticleSettings &ps = t.settings[cmd.stream];
     const SpawnerInput in = f.inputs[cmd.input_idx];
 
     // draws 0..11 in the reference's draw order (src/core.rs:438-466)
@@ -180,17 +188,16 @@ __global__ void __launch_bounds__(256) spawn_kernel(DeviceTables t, FrameDeviceI
     const V3 position = v3(in.translation[0], in.translation[1], in.translation[2]) + spawn_offset;
     const float lifetime = u_life * (ps.lifetime.max - ps.lifetime.min) + ps.lifetime.min;
     const V3 av = rand_vec3(es.initial_angular_velocity, u_ang_angle, u_ang_radius, u_ang_mag);
-    const float4 base = sample_gradient(ps.base_color, 0.0f);
-    const float4 emissive = sample_gradient(ps.emissive_color, 0.0f);
 
-    float4 *row = d.rows + (size_t)slot * 4u;
-    row[0] = make_float4(position.x, position.y, position.z, initial_scale);
-    row[1] = make_float4(es.initial_rotation[0], es.initial_rotation[1], es.initial_rotation[2], es.initial_rotation[3]);
-    row[2] = base;
-    row[3] = emissive;
-    d.s0[slot] = make_float4(velocity.x, velocity.y, velocity.z, 0.0f);
-    d.s1[slot] = make_float4(av.x, av.y, av.z, lifetime);
-    d.s2[slot] = initial_scale;
+    const StreamArrays a = stream_arrays(d.base, d.capacity);
+    a.m0[slot] = make_float4(position.x, position.y, position.z, 0.0f); // age = 0
+    a.m1[slot] = make_float4(es.initial_rotation[0], es.initial_rotation[1], es.initial_rotation[2], es.initial_rotation[3]);
+    a.m2[slot] = make_float4(velocity.x, velocity.y, velocity.z, av.x);
+    a.m3[slot] = make_float2(av.y, av.z);
+    a.k[slot] = make_float2(lifetime, initial_scale);
+    a.o0[slot] = sample_gradient(ps.base_color, 0.0f);     // :460
+    a.o1[slot] = sample_gradient(ps.emissive_color, 0.0f); // :461
+    a.o2[slot] = initial_scale;                            // scale: initial_scale (:457)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -200,7 +207,7 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_load_settings(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -230,119 +237,117 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
     return v;
 }
 
+struct TileRef {
+    uint32_t stream;
+    uint32_t tile; // tile index inside the stream
+};
+// stream owning update tile `tile` of a variant: last s with prefix[s] <= tile (prefix[n] > tile)
+__device__ __forceinline__ TileRef find_tile(const uint32_t *__restrict__ prefix, uint32_t n_slots, uint32_t tile) {
+    uint32_t lo = 0, hi = n_slots;
+    while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (prefix[mid] <= tile) lo = mid; else hi = mid;
+    }
+    return TileRef{lo, tile - prefix[lo]};
+}
+
 struct alignas(16) UpdateSmem {
     DevParticleSettings settings[2];
-    float4 rows[kUpdateThreads / 32][32 * 4]; // per-warp 2 KB staging for the AoS row transposes
     uint64_t bar[2];
+    TileRef ref[2];
     uint32_t warp_alive[kUpdateThreads / 32];
     uint32_t excl_dead; // dead particles of the stream before this tile (compact variants)
 };
 
 // The fused per-frame update. One CTA processes whole tiles of 256 consecutive particles of one
 // stream; persistent grid, tile = blockIdx.x + k*gridDim.x in increasing order (required by the
-// look-back of the compact variants: a tile only ever waits on lower-numbered tiles).
+// look-back of the compact variants: a tile only ever waits on lower-numbered tiles, and every
+// CTA of the grid is resident). Thread 0 looks up the next tile's stream and prefetches its
+// settings block with a bulk async copy while the CTA works on the current tile.
 template <bool COMPACT, bool COLLIDE>
 __global__ void __launch_bounds__(kUpdateThreads) update_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant) {
     __shared__ UpdateSmem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t n_tiles = t.plan->n_tiles[variant];
-    const uint32_t tile_base = t.plan->tile_base[variant];
     if (blockIdx.x >= n_tiles) return;
+    const uint32_t tile_base = t.plan->tile_base[variant];
+    const uint32_t n_slots = f.header->n_slots;
+    const uint32_t *prefix = t.tile_prefix + (size_t)variant * (t.slots_cap + 1u);
     const float dt = f.header->dt;
     const uint32_t epoch = f.header->epoch;
 
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
+        const TileRef r = find_tile(prefix, n_slots, blockIdx.x);
+        sm.ref[0] = r;
+        bulk_load(&sm.settings[0], &t.settings[r.stream], sizeof(DevParticleSettings), &sm.bar[0]);
     }
     __syncthreads();
-    // prefetch the settings of the first tile
-    if (tid == 0) {
-        const TileEntry e = t.tiles[tile_base + blockIdx.x];
-        bulk_load_settings(&sm.settings[0], &t.settings[t.descs[e.stream].settings_idx], sizeof(DevParticleSettings), &sm.bar[0]);
-    }
-    float4 *wrows = sm.rows[warp];
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
         const uint32_t buf = it & 1u;
-        const TileEntry e = t.tiles[tile_base + tile];
+        const TileRef e = sm.ref[buf];
         const StreamDesc d = t.descs[e.stream];
         StreamState *stp = &t.states[e.stream];
         const uint32_t head = stp->head, n_update = stp->count;
-        // prefetch the next tile's settings into the other buffer (all threads left it at the
-        // __syncthreads that closed the previous iteration)
-        if (tid == 0 && tile + gridDim.x < n_tiles) {
-            const TileEntry en = t.tiles[tile_base + tile + gridDim.x];
-            bulk_load_settings(&sm.settings[buf ^ 1u], &t.settings[t.descs[en.stream].settings_idx], sizeof(DevParticleSettings), &sm.bar[buf ^ 1u]);
-        }
+        const StreamArrays a = stream_arrays(d.base, d.capacity);
         const uint32_t tile_first = e.tile * kTile;
-        const uint32_t warp_first = tile_first + warp * 32u;
-        const uint32_t i = warp_first + lane;
+        const uint32_t i = tile_first + tid;
         const bool valid = i < n_update;
         const uint32_t slot = wrap(head + (valid ? i : 0u), d.capacity);
 
-        // ---- loads: 5 independent 16-byte (one 4-byte) requests per thread in flight
-        float4 S0 = make_float4(0.f, 0.f, 0.f, 0.f), S1 = make_float4(0.f, 0.f, 0.f, 1.f);
-        float iscale = 0.f;
+        // ---- loads: 64 B per particle, five independent coalesced requests per thread
+        float4 M0 = make_float4(0.f, 0.f, 0.f, 0.f), M1 = M0, M2 = M0;
+        float2 M3 = make_float2(0.f, 0.f), K = make_float2(1.f, 0.f);
         if (valid) {
-            S0 = d.s0[slot];
-            S1 = d.s1[slot];
-            iscale = d.s2[slot];
+            M0 = a.m0[slot];
+            M1 = a.m1[slot];
+            M2 = a.m2[slot];
+            M3 = a.m3[slot];
+            K = a.k[slot];
         }
-        // rows: the warp's 32 rows are 2 KB contiguous (mod ring wrap); only bytes 0..31 of each
-        // row (position/scale, rotation) are state. Lane q loads 16-byte chunk q of the 64
-        // input chunks, fully coalesced, and they are transposed through shared memory.
-        float4 in0 = make_float4(0.f, 0.f, 0.f, 0.f), in1 = in0;
-        {
-            const uint32_t p0 = lane >> 1, c = lane & 1u;
-            const uint32_t ia = warp_first + p0, ib = warp_first + 16u + p0;
-            if (ia < n_update) in0 = d.rows[(size_t)wrap(head + ia, d.capacity) * 4u + c];
-            if (ib < n_update) in1 = d.rows[(size_t)wrap(head + ib, d.capacity) * 4u + c];
-            // 2-chunk layout, 16-byte unit index = 2p + (c ^ ((p>>2)&1)): conflict-free both ways
-            wrows[2u * p0 + (c ^ ((p0 >> 2) & 1u))] = in0;
-            const uint32_t p1 = 16u + p0;
-            wrows[2u * p1 + (c ^ ((p1 >> 2) & 1u))] = in1;
+        // next tile: stream lookup + settings prefetch into the other buffer (every thread left
+        // that buffer at the __syncthreads closing the previous iteration)
+        if (tid == 0 && tile + gridDim.x < n_tiles) {
+            const TileRef r = find_tile(prefix, n_slots, tile + gridDim.x);
+            sm.ref[buf ^ 1u] = r;
+            bulk_load(&sm.settings[buf ^ 1u], &t.settings[r.stream], sizeof(DevParticleSettings), &sm.bar[buf ^ 1u]);
         }
-        __syncwarp();
-        const uint32_t sw2 = (lane >> 2) & 1u;
-        const float4 P0 = wrows[2u * lane + (0u ^ sw2)];
-        const float4 P1 = wrows[2u * lane + (1u ^ sw2)];
-        __syncwarp();
-
         mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
         const DevParticleSettings &ps = sm.settings[buf];
 
         // ---- reference src/core.rs:591-658, same order
-        const float lifetime = S1.w;
-        const float age = S0.w + dt;                 // :594
-        bool alive = valid && !(age >= lifetime);    // :596-599
-        float4 o0 = P0, o1 = P1, o2, o3, oS0 = S0, oS1 = S1;
-        o2 = o3 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float lifetime = K.x, iscale = K.y;
+        const float age = M0.w + dt;              // :594
+        bool alive = valid && !(age >= lifetime); // :596-599
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+        float scale = 0.f;
         if (alive) {
-            const float age_percent = age / lifetime;                        // :601
-            const float scale = iscale * sample_curve(ps.scale_curve, age_percent); // :602-605
-            V3 pos = v3(P0.x, P0.y, P0.z), vel = v3(S0.x, S0.y, S0.z);
+            const float age_percent = age / lifetime;                       // :601
+            scale = iscale * sample_curve(ps.scale_curve, age_percent);     // :602-605
+            V3 pos = v3(M0.x, M0.y, M0.z), vel = v3(M2.x, M2.y, M2.z);
             bool should_destroy = false;
             if (COLLIDE) {
                 particle_collision(t.colliders, t.n_colliders, ps.collision, pos, vel, dt, should_destroy); // :608-617
             } else {
-                pos = pos + vel * dt;                                        // :619-623
+                pos = pos + vel * dt;                                       // :619-623
             }
             if (should_destroy) {
-                alive = false;                                               // :636-639
+                alive = false;                                              // :636-639
             } else {
                 const V3 acc = v3(ps.acceleration[0], ps.acceleration[1], ps.acceleration[2]);
-                vel = vel + (acc - vel * ps.linear_drag) * dt;               // :641-643
-                V3 av = v3(S1.x, S1.y, S1.z);
-                const Q4 rot = qmul(q_from_scaled_axis(av * dt), Q4{P1.x, P1.y, P1.z, P1.w}); // :645-647
+                vel = vel + (acc - vel * ps.linear_drag) * dt;              // :641-643
+                V3 av = v3(M2.w, M3.x, M3.y);
+                const Q4 rot = qmul(q_from_scaled_axis(av * dt), Q4{M1.x, M1.y, M1.z, M1.w}); // :645-647
                 const V3 aacc = v3(ps.angular_acceleration[0], ps.angular_acceleration[1], ps.angular_acceleration[2]);
-                av = av + (aacc - av * ps.angular_drag) * dt;                // :648-650
-                o0 = make_float4(pos.x, pos.y, pos.z, scale);
-                o1 = make_float4(rot.x, rot.y, rot.z, rot.w);
-                o2 = sample_gradient(ps.base_color, age_percent);            // :652-653
-                o3 = sample_gradient(ps.emissive_color, age_percent);        // :654-655
-                oS0 = make_float4(vel.x, vel.y, vel.z, age);
-                oS1 = make_float4(av.x, av.y, av.z, lifetime);
+                av = av + (aacc - av * ps.angular_drag) * dt;               // :648-650
+                c0 = sample_gradient(ps.base_color, age_percent);           // :652-653
+                c1 = sample_gradient(ps.emissive_color, age_percent);       // :654-655
+                M0 = make_float4(pos.x, pos.y, pos.z, age);
+                M1 = make_float4(rot.x, rot.y, rot.z, rot.w);
+                M2 = make_float4(vel.x, vel.y, vel.z, av.x);
+                M3 = make_float2(av.y, av.z);
             }
         }
         const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
@@ -352,37 +357,36 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(DeviceTables t, 
         // ---- per-stream AABB of position -/+ scale (reference src/render.rs:681-692)
         {
             uint32_t mn[3], mx[3];
-            mn[0] = alive ? enc_f32(o0.x - o0.w) : 0xFFFFFFFFu;
-            mn[1] = alive ? enc_f32(o0.y - o0.w) : 0xFFFFFFFFu;
-            mn[2] = alive ? enc_f32(o0.z - o0.w) : 0xFFFFFFFFu;
-            mx[0] = alive ? enc_f32(o0.x + o0.w) : 0u;
-            mx[1] = alive ? enc_f32(o0.y + o0.w) : 0u;
-            mx[2] = alive ? enc_f32(o0.z + o0.w) : 0u;
+            mn[0] = alive ? enc_f32(M0.x - scale) : 0xFFFFFFFFu;
+            mn[1] = alive ? enc_f32(M0.y - scale) : 0xFFFFFFFFu;
+            mn[2] = alive ? enc_f32(M0.z - scale) : 0xFFFFFFFFu;
+            mx[0] = alive ? enc_f32(M0.x + scale) : 0u;
+            mx[1] = alive ? enc_f32(M0.y + scale) : 0u;
+            mx[2] = alive ? enc_f32(M0.z + scale) : 0u;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
                 mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
             }
             if (lane < 3u) {
-                const uint32_t a = lane == 0 ? mn[0] : (lane == 1 ? mn[1] : mn[2]);
-                const uint32_t b = lane == 0 ? mx[0] : (lane == 1 ? mx[1] : mx[2]);
-                if (a < stp->aabb_min[lane]) atomicMin(&stp->aabb_min[lane], a);
-                if (b > stp->aabb_max[lane]) atomicMax(&stp->aabb_max[lane], b);
+                const uint32_t lo = lane == 0 ? mn[0] : (lane == 1 ? mn[1] : mn[2]);
+                const uint32_t hi = lane == 0 ? mx[0] : (lane == 1 ? mx[1] : mx[2]);
+                if (lo < stp->aabb_min[lane]) atomicMin(&stp->aabb_min[lane], lo);
+                if (hi > stp->aabb_max[lane]) atomicMax(&stp->aabb_max[lane], hi);
             }
         }
 
-        // ---- destination of the survivors
-        uint32_t dst_first; // logical index the warp's first stored row goes to
-        uint32_t my_rank;   // row position of this lane inside the warp's stored block
+        // ---- destination slot of a survivor
+        uint32_t dslot = slot;
         if (COMPACT) {
             if (lane == 0) sm.warp_alive[warp] = n_alive_w;
             __syncthreads(); // every load of this tile has been consumed by now
             uint32_t before = 0, tile_alive = 0;
 #pragma unroll
             for (uint32_t w = 0; w < kUpdateThreads / 32; w++) {
-                const uint32_t a = sm.warp_alive[w];
-                if (w < warp) before += a;
-                tile_alive += a;
+                const uint32_t n = sm.warp_alive[w];
+                if (w < warp) before += n;
+                tile_alive += n;
             }
             if (tid == 0) {
                 const uint32_t tile_valid = min(n_update - tile_first, (uint32_t)kTile);
@@ -396,7 +400,7 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(DeviceTables t, 
                     const unsigned long long *p = status - 1;
                     for (uint32_t back = 0; back < e.tile;) {
                         const unsigned long long w = ld_acquire(p);
-                        if ((w >> 34) != (unsigned long long)epoch || ((w >> 32) & 3ull) == 0ull) continue; // not published yet
+                        if ((w >> 34) != (unsigned long long)epoch || ((w >> 32) & 3ull) == 0ull) continue; // not yet published
                         excl += (uint32_t)w;
                         if (((w >> 32) & 3ull) == kFlagPrefix) break;
                         back++;
@@ -408,77 +412,127 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(DeviceTables t, 
                 if (tile_first + kTile >= n_update) stp->dead = excl + tile_dead; // last tile of the stream
             }
             __syncthreads();
-            dst_first = tile_first - sm.excl_dead + before;
-            my_rank = __popc(alive_mask & ((1u << lane) - 1u));
+            const uint32_t rank = before + __popc(alive_mask & ((1u << lane) - 1u));
+            dslot = wrap(head + tile_first - sm.excl_dead + rank, d.capacity);
         } else {
-            dst_first = warp_first;
-            my_rank = lane;
             const uint32_t n_dead_w = __popc(valid_mask & ~alive_mask);
             if (lane == 0 && n_dead_w) atomicAdd(&stp->dead, n_dead_w);
         }
 
-        // ---- stores. s0/s1 (and s2 when particles move) go straight from the owning lane;
-        // rows are transposed back through shared memory so each store instruction writes
-        // whole 64-byte rows.
+        // ---- stores: 92 B per survivor (100 B when a compacting stream moves its constants)
         if (alive) {
-            const uint32_t dslot = wrap(head + dst_first + my_rank, d.capacity);
-            d.s0[dslot] = oS0;
-            d.s1[dslot] = oS1;
-            if (COMPACT) d.s2[dslot] = iscale;
-            // 4-chunk layout, 16-byte unit index = 4r + (c ^ ((r>>1)&3)): conflict-free both ways
-            const uint32_t sw4 = (my_rank >> 1) & 3u;
-            wrows[4u * my_rank + (0u ^ sw4)] = o0;
-            wrows[4u * my_rank + (1u ^ sw4)] = o1;
-            wrows[4u * my_rank + (2u ^ sw4)] = o2;
-            wrows[4u * my_rank + (3u ^ sw4)] = o3;
+            a.m0[dslot] = M0;
+            a.m1[dslot] = M1;
+            a.m2[dslot] = M2;
+            a.m3[dslot] = M3;
+            if (COMPACT) a.k[dslot] = K;
+            a.o0[dslot] = c0;
+            a.o1[dslot] = c1;
+            a.o2[dslot] = scale;
         }
-        __syncwarp();
-#pragma unroll
-        for (uint32_t j = 0; j < 4u; j++) {
-            const uint32_t q = j * 32u + lane, r = q >> 2, c = q & 3u;
-            const bool on = COMPACT ? (r < n_alive_w) : ((alive_mask >> r) & 1u);
-            if (on) {
-                const float4 v = wrows[4u * r + (c ^ ((r >> 1) & 3u))];
-                d.rows[(size_t)wrap(head + dst_first + r, d.capacity) * 4u + c] = v;
-            }
-        }
-        __syncthreads(); // settings buffer + staging reuse
+        __syncthreads(); // settings / tile-ref buffers are reused by the next iterations
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// pack: live instance rows of every stream, creation order, Vec order inside a stream
-__global__ void __launch_bounds__(256) pack_prefix_kernel(DeviceTables t, uint32_t n_slots, unsigned long long *offsets, unsigned long long *n_rows) {
-    // single thread-block serial prefix over streams (n_slots is small)
+// pack: live ParticleInstance rows of the streams [slot_begin, slot_end), creation order, Vec
+// order inside a stream. out[0] = total rows, out[1 + k] = first row of stream slot_begin + k.
+__global__ void pack_prefix_kernel(DeviceTables t, uint32_t slot_begin, uint32_t slot_end, unsigned long long *out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long acc = 0;
-        for (uint32_t s = 0; s < n_slots; s++) {
-            offsets[s] = acc;
+        for (uint32_t s = slot_begin; s < slot_end; s++) {
+            out[1 + (s - slot_begin)] = acc;
             if (t.descs[s].capacity) acc += t.states[s].count - t.states[s].dead;
         }
-        *n_rows = acc;
+        out[0] = acc;
     }
 }
-__global__ void __launch_bounds__(256) pack_copy_kernel(DeviceTables t, uint32_t n_slots, const unsigned long long *offsets, float4 *dst, uint64_t cap_rows) {
-    const uint32_t s = blockIdx.y;
-    if (s >= n_slots) return;
+__global__ void __launch_bounds__(256) pack_copy_kernel(DeviceTables t, uint32_t slot_begin, uint32_t slot_end,
+                                                        const unsigned long long *offsets, float4 *dst, uint64_t cap_rows) {
+    const uint32_t s = slot_begin + blockIdx.y;
+    if (s >= slot_end) return;
     const StreamDesc d = t.descs[s];
     if (d.capacity == 0u) return;
     const StreamState st = t.states[s];
     const bool fifo = (d.variant == kFifo || d.variant == kFifoCollide);
     const uint32_t live = st.count - st.dead;
     const uint32_t first = wrap(st.head + (fifo ? st.dead : 0u), d.capacity);
-    const unsigned long long off = offsets[s];
+    const unsigned long long off = offsets[1 + blockIdx.y];
+    const StreamArrays a = stream_arrays(d.base, d.capacity);
+    // one 16-byte chunk of a row per thread: fully coalesced 64-byte row writes
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < (uint64_t)live * 4u; q += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t r = (uint32_t)(q >> 2), c = (uint32_t)(q & 3u);
         if (off + r >= cap_rows) return;
-        dst[(off + r) * 4u + c] = d.rows[(size_t)wrap(first + r, d.capacity) * 4u + c];
+        const uint32_t slot = wrap(first + r, d.capacity);
+        float4 v;
+        if (c == 0u) {
+            v = a.m0[slot];
+            v.w = a.o2[slot]; // position.xyz, scale
+        } else if (c == 1u) {
+            v = a.m1[slot];
+        } else if (c == 2u) {
+            v = a.o0[slot];
+        } else {
+            v = a.o1[slot];
+        }
+        dst[(off + r) * 4u + c] = v;
+    }
+}
+
+// ParticleData rows of one stream (host mirror, tests)
+__global__ void __launch_bounds__(256) gather_particles_kernel(StreamDesc d, uint32_t first, uint32_t n, uint32_t pbr, fw_particle_data *dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const StreamArrays a = stream_arrays(d.base, d.capacity);
+    const uint32_t slot = wrap(first + i, d.capacity);
+    const float4 m0 = a.m0[slot], m1 = a.m1[slot], m2 = a.m2[slot], o0 = a.o0[slot], o1 = a.o1[slot];
+    const float2 m3 = a.m3[slot], k = a.k[slot];
+    fw_particle_data p;
+    p.position[0] = m0.x; p.position[1] = m0.y; p.position[2] = m0.z;
+    p.velocity[0] = m2.x; p.velocity[1] = m2.y; p.velocity[2] = m2.z;
+    p.rotation[0] = m1.x; p.rotation[1] = m1.y; p.rotation[2] = m1.z; p.rotation[3] = m1.w;
+    p.angular_velocity[0] = m2.w; p.angular_velocity[1] = m3.x; p.angular_velocity[2] = m3.y;
+    p.initial_scale = k.y;
+    p.scale = a.o2[slot];
+    p.age = m0.w;
+    p.lifetime = k.x;
+    p.base_color[0] = o0.x; p.base_color[1] = o0.y; p.base_color[2] = o0.z; p.base_color[3] = o0.w;
+    p.emissive_color[0] = o1.x; p.emissive_color[1] = o1.y; p.emissive_color[2] = o1.z; p.emissive_color[3] = o1.w;
+    p.pbr = pbr;
+    dst[i] = p;
+}
+__global__ void __launch_bounds__(256) scatter_particles_kernel(StreamDesc d, uint32_t n, const fw_particle_data *src) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const StreamArrays a = stream_arrays(d.base, d.capacity);
+    const fw_particle_data p = src[i];
+    a.m0[i] = make_float4(p.position[0], p.position[1], p.position[2], p.age);
+    a.m1[i] = make_float4(p.rotation[0], p.rotation[1], p.rotation[2], p.rotation[3]);
+    a.m2[i] = make_float4(p.velocity[0], p.velocity[1], p.velocity[2], p.angular_velocity[0]);
+    a.m3[i] = make_float2(p.angular_velocity[1], p.angular_velocity[2]);
+    a.k[i] = make_float2(p.lifetime, p.initial_scale);
+    a.o0[i] = make_float4(p.base_color[0], p.base_color[1], p.base_color[2], p.base_color[3]);
+    a.o1[i] = make_float4(p.emissive_color[0], p.emissive_color[1], p.emissive_color[2], p.emissive_color[3]);
+    a.o2[i] = p.scale;
+}
+__global__ void __launch_bounds__(256) ring_copy_kernel(StreamDesc src, uint32_t first, uint32_t n, StreamDesc dst) {
+    const StreamArrays a = stream_arrays(src.base, src.capacity), b = stream_arrays(dst.base, dst.capacity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t s = wrap(first + i, src.capacity);
+        b.m0[i] = a.m0[s];
+        b.m1[i] = a.m1[s];
+        b.m2[i] = a.m2[s];
+        b.m3[i] = a.m3[s];
+        b.k[i] = a.k[s];
+        b.o0[i] = a.o0[s];
+        b.o1[i] = a.o1[s];
+        b.o2[i] = a.o2[s];
     }
 }
 
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, cudaStream_t s) {
-    plan_kernel<<<1, 1024, 0, s>>>(t, f);
+cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant_mask, cudaStream_t s) {
+    plan_kernel<<<1, 1024, 0, s>>>(t, f, variant_mask);
     return cudaGetLastError();
 }
 cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t total_spawn, cudaStream_t s) {
@@ -509,17 +563,37 @@ cudaError_t update_grid_size(int device, int *grids) {
     if (e != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kCompactCollide], update_kernel<true, true>, kUpdateThreads, 0);
     if (e != cudaSuccess) return e;
+    // persistent grids: every CTA must be resident (the look-back of the compact variants
+    // spins on lower-numbered tiles)
     for (int v = 0; v < (int)kNumVariants; v++) grids[v] = sms * (occ[v] > 0 ? occ[v] : 1);
     return cudaSuccess;
 }
-cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t n_slots, float4 *dst, uint64_t cap_rows, unsigned long long *n_rows, cudaStream_t s) {
-    // offsets scratch lives right behind n_rows (the host allocates n_slots + 1 words)
-    unsigned long long *offsets = n_rows + 1;
-    pack_prefix_kernel<<<1, 32, 0, s>>>(t, n_slots, offsets, n_rows);
-    if (n_slots) {
-        dim3 grid(64, n_slots);
-        pack_copy_kernel<<<grid, 256, 0, s>>>(t, n_slots, offsets, dst, cap_rows);
+cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, float4 *dst,
+                                  uint64_t cap_rows, unsigned long long *out, cudaStream_t s) {
+    pack_prefix_kernel<<<1, 32, 0, s>>>(t, slot_begin, slot_end, out);
+    if (slot_end > slot_begin) {
+        const uint32_t n = slot_end - slot_begin;
+        for (uint32_t y0 = 0; y0 < n; y0 += 32768u) { // gridDim.y limit is 65535
+            dim3 grid(n == 1 ? 1184 : 16, std::min(32768u, n - y0));
+            pack_copy_kernel<<<grid, 256, 0, s>>>(t, slot_begin + y0, slot_end, out + y0, dst, cap_rows);
+        }
     }
+    return cudaGetLastError();
+}
+cudaError_t launch_gather_particles(const StreamDesc &d, uint32_t first, uint32_t n, uint32_t pbr, fw_particle_data *dst, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    gather_particles_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(d, first, n, pbr, dst);
+    return cudaGetLastError();
+}
+cudaError_t launch_scatter_particles(const StreamDesc &d, uint32_t n, const fw_particle_data *src, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    scatter_particles_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(d, n, src);
+    return cudaGetLastError();
+}
+cudaError_t launch_ring_copy(const StreamDesc &src, uint32_t first, uint32_t n, const StreamDesc &dst, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t blocks = std::min<uint32_t>((n + 255u) / 256u, 148u * 8u);
+    ring_copy_kernel<<<blocks, 256, 0, s>>>(src, first, n, dst);
     return cudaGetLastError();
 }
 
