@@ -28,6 +28,7 @@ FW_SHAPE_POINT, FW_SHAPE_SPHERE, FW_SHAPE_CIRCLE = 0, 1, 2
 FW_TRANSFORM_GLOBAL, FW_TRANSFORM_LOCAL = 0, 1
 FW_COLLIDER_CUBOID, FW_COLLIDER_SPHERE = 0, 1
 FW_FLAG_PROFILE = 1
+FW_FLAG_NO_GRAPHS = 2
 
 f32 = C.c_float
 u32 = C.c_uint32

@@ -33,7 +33,8 @@ def load_library(build_if_missing: bool = True):
         if not build_if_missing:
             raise FileNotFoundError(LIB_PATH)
         build_native()
-    L = C.CDLL(LIB_PATH)
+    # FW_B200_LIB: a differently tuned build of the SAME library (kernel tuning experiments)
+    L = C.CDLL(os.environ.get("FW_B200_LIB") or LIB_PATH)
     for name, (res, args) in _abi.EXPORTS.items():
         fn = getattr(L, name)  # AttributeError if the library lacks a declared symbol
         fn.restype = res
@@ -71,14 +72,14 @@ class Engine:
     """One ``fw_context``: all particle state of one GPU."""
 
     def __init__(self, device: int = 0, seed: int = 0x00F12E00, profile: bool = False,
-                 external_stream: Optional[int] = None):
+                 external_stream: Optional[int] = None, graphs: bool = True):
         self._L = load_library()
         cfg = _abi.fw_config()
         cfg.abi_version = _abi.FW_ABI_VERSION
         cfg.device = device
         cfg.seed = seed
         cfg.external_stream = external_stream
-        cfg.flags = _abi.FW_FLAG_PROFILE if profile else 0
+        cfg.flags = (_abi.FW_FLAG_PROFILE if profile else 0) | (0 if graphs else _abi.FW_FLAG_NO_GRAPHS)
         self._ctx = C.c_void_p()
         rc = self._L.fw_create(C.byref(cfg), C.byref(self._ctx))
         if rc != _abi.FW_OK:

@@ -26,6 +26,7 @@ namespace {
 thread_local std::string g_global_error;
 
 constexpr uint32_t kRing = 4; // frames in flight (pinned parameter blocks + state readbacks)
+constexpr uint32_t kGraphWarmFrames = 8; // frames of unchanged topology before frames are replayed as graphs
 
 struct Emitter {
     fw_emission_settings es;
@@ -79,6 +80,10 @@ struct FrameSlot {
     uint64_t particles_spawned = 0;
     uint32_t launches = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
+    // the frame as an instantiated CUDA graph (valid while the topology version matches)
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_version = 0;
+    uint32_t graph_launches = 0;
 };
 
 } // namespace
@@ -125,6 +130,12 @@ struct fw_context {
     std::map<uint32_t, std::vector<void *>> block_cache; // capacity -> free device blocks
     FrameSlot ring[kRing];
     uint64_t frame_no = 0; // frames submitted so far; epoch of the next frame = frame_no + 1
+    // topology = everything a captured frame graph bakes in (table pointers, slot / emitter /
+    // spawner counts, active variants, colliders). Any change bumps the version.
+    uint64_t topo_version = 1;
+    uint32_t topo_stable_frames = 0;
+    uint32_t live_emitters = 0;
+    bool use_graphs = true;
     int grids[kNumVariants] = {0, 0, 0, 0};
     uint32_t variant_streams[kNumVariants] = {0, 0, 0, 0};
 
@@ -147,6 +158,11 @@ int fail(fw_context *ctx, int code, const char *fmt, ...) {
     if (ctx) ctx->error = buf;
     g_global_error = buf;
     return code;
+}
+
+inline void topo_changed(fw_context *ctx) {
+    ctx->topo_version++;
+    ctx->topo_stable_frames = 0;
 }
 
 #define CU(ctx, call)                                                                              \
@@ -277,6 +293,7 @@ int ensure_slots(fw_context *ctx, uint32_t need) {
     ctx->h_descs.resize(ncap);
     ctx->slot_owner.resize(ncap, nullptr);
     ctx->slots_cap = ncap;
+    topo_changed(ctx);
     return FW_OK;
 }
 int ensure_emitters(fw_context *ctx, uint32_t need) {
@@ -286,6 +303,7 @@ int ensure_emitters(fw_context *ctx, uint32_t need) {
     int rc = grow_device_array(ctx, ctx->d_emitters, ctx->emitters_cap, ncap);
     if (rc) return rc;
     ctx->emitters_cap = ncap;
+    topo_changed(ctx);
     return FW_OK;
 }
 int ensure_tiles(fw_context *ctx) {
@@ -300,6 +318,7 @@ int ensure_tiles(fw_context *ctx) {
     CU(ctx, cudaMalloc((void **)&ctx->d_lookback, sizeof(unsigned long long) * ncap));
     CU(ctx, cudaMemsetAsync(ctx->d_lookback, 0, sizeof(unsigned long long) * ncap, ctx->stream));
     ctx->tiles_cap = (uint32_t)ncap;
+    topo_changed(ctx);
     return FW_OK;
 }
 
@@ -378,6 +397,8 @@ void free_stream(fw_context *ctx, Stream &st) {
     ctx->free_slots.push_back(st.slot);
 }
 void free_spawner_resources(fw_context *ctx, Spawner &sp) {
+    topo_changed(ctx);
+    ctx->live_emitters -= (uint32_t)sp.emitters.size();
     for (Stream &st : sp.streams) free_stream(ctx, st);
     for (Emitter &e : sp.emitters) ctx->free_emitters.push_back(e.dev_idx);
     sp.streams.clear();
@@ -463,12 +484,14 @@ int ensure_frame_slot(fw_context *ctx, FrameSlot &fs, size_t bytes) {
         CU(ctx, cudaMallocHost((void **)&fs.host, nb));
         CU(ctx, cudaMalloc((void **)&fs.dev, nb));
         fs.bytes = nb;
+        fs.graph_version = 0;
     }
     if (fs.states_slots < ctx->slots_cap) {
         if (fs.states_host) CU(ctx, cudaFreeHost(fs.states_host));
         fs.states_host = nullptr;
         CU(ctx, cudaMallocHost((void **)&fs.states_host, sizeof(StreamState) * ctx->slots_cap));
         fs.states_slots = ctx->slots_cap;
+        fs.graph_version = 0;
     }
     return FW_OK;
 }
@@ -579,6 +602,7 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
     ctx->device = cfg->device;
     ctx->seed = cfg->seed;
     ctx->flags = cfg->flags;
+    ctx->use_graphs = (cfg->flags & FW_FLAG_NO_GRAPHS) == 0;
     CU(nullptr, cudaSetDevice(cfg->device));
     if (cfg->external_stream) {
         ctx->stream = (cudaStream_t)cfg->external_stream;
@@ -618,6 +642,7 @@ int fw_destroy(fw_context *ctx) {
         if (fs.dev) cudaFree(fs.dev);
         if (fs.states_host) cudaFreeHost(fs.states_host);
         if (fs.plan_host) cudaFreeHost(fs.plan_host);
+        if (fs.graph_exec) cudaGraphExecDestroy(fs.graph_exec);
         if (fs.done) cudaEventDestroy(fs.done);
         for (auto &ev : fs.ev)
             if (ev) cudaEventDestroy(ev);
@@ -674,6 +699,8 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
         free_spawner_resources(ctx, *sp); // data.particles = vec![Vec::new(); n]  (src/core.rs:360)
     }
     sp->initialized = true; // :361-363
+    topo_changed(ctx);
+    ctx->live_emitters += n_emitters;
     sp->emitters.resize(n_emitters);
     for (uint32_t i = 0; i < n_emitters; i++) { // :347-359
         Emitter &e = sp->emitters[i];
@@ -751,6 +778,7 @@ int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) 
     if (ctx->d_colliders) CU(ctx, cudaFree(ctx->d_colliders));
     ctx->d_colliders = nullptr;
     ctx->n_colliders = n;
+    topo_changed(ctx);
     if (n) {
         CU(ctx, cudaMalloc((void **)&ctx->d_colliders, sizeof(fw_collider) * n));
         CU(ctx, cudaMemcpy(ctx->d_colliders, colliders, sizeof(fw_collider) * n, cudaMemcpyHostToDevice));
@@ -857,12 +885,16 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     for (uint32_t s = 0; s < ctx->n_slots; s++)
         if (fs.spawn_per_slot[s]) ctx->slot_owner[s]->n_hi += fs.spawn_per_slot[s];
 
-    // ---- parameter block of the frame: header | spawn_per_slot | cmds | inputs
+    // ---- parameter block of the frame: header | spawn_per_slot | cmds | inputs. Its layout
+    // depends only on the topology (stream slots, emitters, spawners), so that a frame is a fixed
+    // sequence of nodes that can be replayed as one CUDA graph.
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t cmds_cap = std::max<size_t>(1, ctx->live_emitters);
+    const size_t inputs_cap = std::max<size_t>(1, ctx->spawners.size());
     const size_t off_spawn = align16(sizeof(FrameHeader));
     const size_t off_cmds = align16(off_spawn + sizeof(uint32_t) * std::max(1u, ctx->n_slots));
-    const size_t off_inputs = align16(off_cmds + sizeof(SpawnCmd) * std::max<size_t>(1, cmds.size()));
-    const size_t bytes = align16(off_inputs + sizeof(SpawnerInput) * std::max<size_t>(1, sinputs.size()));
+    const size_t off_inputs = align16(off_cmds + sizeof(SpawnCmd) * cmds_cap);
+    const size_t bytes = align16(off_inputs + sizeof(SpawnerInput) * inputs_cap);
     {
         int rc = ensure_frame_slot(ctx, fs, bytes);
         if (rc) return rc;
@@ -877,7 +909,6 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     if (ctx->n_slots) memcpy(fs.host + off_spawn, fs.spawn_per_slot.data(), sizeof(uint32_t) * ctx->n_slots);
     if (!cmds.empty()) memcpy(fs.host + off_cmds, cmds.data(), sizeof(SpawnCmd) * cmds.size());
     if (!sinputs.empty()) memcpy(fs.host + off_inputs, sinputs.data(), sizeof(SpawnerInput) * sinputs.size());
-    CU(ctx, cudaMemcpyAsync(fs.dev, fs.host, bytes, cudaMemcpyHostToDevice, ctx->stream));
 
     DeviceTables t{};
     t.descs = ctx->d_descs;
@@ -899,28 +930,66 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     f.inputs = (const SpawnerInput *)(fs.dev + off_inputs);
 
     const bool prof = (ctx->flags & FW_FLAG_PROFILE) != 0;
-    uint32_t launches = 0;
-    if (prof) CU(ctx, cudaEventRecord(fs.ev[0], ctx->stream));
     uint32_t variant_mask = 0;
     for (uint32_t v = 0; v < kNumVariants; v++)
         if (ctx->variant_streams[v]) variant_mask |= 1u << v;
-    CU(ctx, launch_plan(t, f, variant_mask, ctx->stream));
-    launches++;
-    if (prof) CU(ctx, cudaEventRecord(fs.ev[1], ctx->stream));
-    if (total_spawn) {
-        CU(ctx, launch_spawn(t, f, (uint32_t)total_spawn, ctx->stream));
+    uint32_t launches = 0;
+    // the device work of one frame; `replay` = being captured into a graph, so nothing may
+    // depend on this particular frame's counts
+    auto enqueue = [&](bool replay) -> int {
+        launches = 0;
+        CU(ctx, cudaMemcpyAsync(fs.dev, fs.host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (prof) CU(ctx, cudaEventRecord(fs.ev[0], ctx->stream));
+        CU(ctx, launch_plan(t, f, variant_mask, ctx->stream));
         launches++;
+        if (prof) CU(ctx, cudaEventRecord(fs.ev[1], ctx->stream));
+        if (replay || total_spawn) {
+            CU(ctx, launch_spawn(t, f, replay ? 0xFFFFFFFFu : (uint32_t)total_spawn, ctx->stream));
+            launches++;
+        }
+        if (prof) CU(ctx, cudaEventRecord(fs.ev[2], ctx->stream));
+        for (uint32_t v = 0; v < kNumVariants; v++) {
+            if (!ctx->variant_streams[v]) continue;
+            CU(ctx, launch_update(t, f, v, ctx->grids[v], ctx->stream));
+            launches++;
+        }
+        if (prof) CU(ctx, cudaEventRecord(fs.ev[3], ctx->stream));
+        // asynchronous readback of the stream states (bounds for the next frames) + plan output
+        if (ctx->n_slots) CU(ctx, cudaMemcpyAsync(fs.states_host, ctx->d_states, sizeof(StreamState) * ctx->n_slots, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(fs.plan_host, ctx->d_plan, sizeof(PlanOut), cudaMemcpyDeviceToHost, ctx->stream));
+        return FW_OK;
+    };
+    ctx->topo_stable_frames++;
+    if (ctx->use_graphs && ctx->topo_stable_frames > kGraphWarmFrames) {
+        if (!fs.graph_exec || fs.graph_version != ctx->topo_version) {
+            if (fs.graph_exec) cudaGraphExecDestroy(fs.graph_exec);
+            fs.graph_exec = nullptr;
+            CU(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue(true);
+            cudaGraph_t g = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+            if (rc != FW_OK || e != cudaSuccess) {
+                if (g) cudaGraphDestroy(g);
+                (void)cudaGetLastError();
+                ctx->use_graphs = false;
+                return fail(ctx, FW_ERR_CUDA, "frame graph capture failed: %s", e != cudaSuccess ? cudaGetErrorString(e) : ctx->error.c_str());
+            }
+            const cudaError_t ei = cudaGraphInstantiate(&fs.graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ei != cudaSuccess) {
+                fs.graph_exec = nullptr;
+                ctx->use_graphs = false;
+                return fail(ctx, FW_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+            }
+            fs.graph_version = ctx->topo_version;
+            fs.graph_launches = launches;
+        }
+        launches = fs.graph_launches;
+        CU(ctx, cudaGraphLaunch(fs.graph_exec, ctx->stream));
+    } else {
+        int rc = enqueue(false);
+        if (rc) return rc;
     }
-    if (prof) CU(ctx, cudaEventRecord(fs.ev[2], ctx->stream));
-    for (uint32_t v = 0; v < kNumVariants; v++) {
-        if (!ctx->variant_streams[v]) continue;
-        CU(ctx, launch_update(t, f, v, ctx->grids[v], ctx->stream));
-        launches++;
-    }
-    if (prof) CU(ctx, cudaEventRecord(fs.ev[3], ctx->stream));
-    // asynchronous readback of the stream states (bounds for the next frames) + plan output
-    if (ctx->n_slots) CU(ctx, cudaMemcpyAsync(fs.states_host, ctx->d_states, sizeof(StreamState) * ctx->n_slots, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(fs.plan_host, ctx->d_plan, sizeof(PlanOut), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaEventRecord(fs.done, ctx->stream));
     ctx->frame_no++;
     fs.in_flight = true;

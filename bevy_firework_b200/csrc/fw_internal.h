@@ -34,8 +34,11 @@
 
 namespace fw {
 
-constexpr int kTile = 256; // particles per update tile == threads per CTA
-constexpr int kUpdateThreads = 256;
+#ifndef FW_TILE
+#define FW_TILE 256
+#endif
+constexpr int kTile = FW_TILE; // particles per update tile == threads per CTA
+constexpr int kUpdateThreads = FW_TILE;
 constexpr uint32_t kBytesPerSlot = 100;
 
 // variants of the update kernel

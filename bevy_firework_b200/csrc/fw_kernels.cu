@@ -16,7 +16,38 @@
 
 #include "fw_math.cuh"
 
+// tuning knobs (see profiles/r1_tuning.md for the measurements behind the defaults)
+#ifndef FW_MINB
+// minimum resident CTAs per SM asked of ptxas for the streaming update kernels: 5 x 256 threads
+// = 40 warps/SM at <= 48 registers, no spills. Measured on C3 (10 M particles): 4 CTAs/SM
+// 0.320 ms, 5 CTAs/SM 0.261 ms, 6 CTAs/SM (40 regs, spills) 0.275 ms.
+#define FW_MINB 5
+#endif
+#ifndef FW_MINB_COLLIDE
+#define FW_MINB_COLLIDE 3 // the collision variants are compute-bound and need ~80 registers
+#endif
+#ifndef FW_CS
+#define FW_CS 0 // 1: streaming (evict-first) cache hints on the particle packs
+#endif
+
 namespace fw {
+
+template <typename T>
+__device__ __forceinline__ T ld_pack(const T *p) {
+#if FW_CS
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <typename T>
+__device__ __forceinline__ void st_pack(T *p, T v) {
+#if FW_CS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 __device__ __forceinline__ uint32_t wrap(uint32_t x, uint32_t cap) { return x >= cap ? x - cap : x; }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
@@ -114,11 +145,8 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
 }
 
 // ------------------------------------------------------------------------------------------
-// spawn: one thread per new particle
-__global__ void __launch_bounds__(256) spawn_kernel(DeviceTables t, FrameDeviceInputs f) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t total = f.header->total_spawn;
-    if (g >= total) return;
+// spawn: one thread per new particle (g = index of the particle among this frame's spawns)
+__device__ __forceinline__ void spawn_one(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t g) {
     // command of this particle: last c with cmds[c].first <= g
     uint32_t lo = 0, hi = f.header->n_cmds;
     while (hi - lo > 1u) {
@@ -199,6 +227,12 @@ __global__ void __launch_bounds__(256) spawn_kernel(DeviceTables t, FrameDeviceI
     a.o1[slot] = sample_gradient(ps.emissive_color, 0.0f); // :461
     a.o2[slot] = initial_scale;                            // scale: initial_scale (:457)
 }
+// grid-stride so the launch configuration is frame-independent (CUDA-graph friendly): the
+// number of new particles is read from the frame header on the device
+__global__ void __launch_bounds__(256) spawn_kernel(DeviceTables t, FrameDeviceInputs f) {
+    const uint32_t total = f.header->total_spawn;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) spawn_one(t, f, g);
+}
 
 // ------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk async copy (TMA unit; SASS UBLKCP) for the per-stream settings block
@@ -265,7 +299,7 @@ struct alignas(16) UpdateSmem {
 // CTA of the grid is resident). Thread 0 looks up the next tile's stream and prefetches its
 // settings block with a bulk async copy while the CTA works on the current tile.
 template <bool COMPACT, bool COLLIDE>
-__global__ void __launch_bounds__(kUpdateThreads) update_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant) {
+__global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : FW_MINB) update_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant) {
     __shared__ UpdateSmem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t n_tiles = t.plan->n_tiles[variant];
@@ -301,11 +335,11 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(DeviceTables t, 
         float4 M0 = make_float4(0.f, 0.f, 0.f, 0.f), M1 = M0, M2 = M0;
         float2 M3 = make_float2(0.f, 0.f), K = make_float2(1.f, 0.f);
         if (valid) {
-            M0 = a.m0[slot];
-            M1 = a.m1[slot];
-            M2 = a.m2[slot];
-            M3 = a.m3[slot];
-            K = a.k[slot];
+            M0 = ld_pack(a.m0 + slot);
+            M1 = ld_pack(a.m1 + slot);
+            M2 = ld_pack(a.m2 + slot);
+            M3 = ld_pack(a.m3 + slot);
+            K = ld_pack(a.k + slot);
         }
         // next tile: stream lookup + settings prefetch into the other buffer (every thread left
         // that buffer at the __syncthreads closing the previous iteration)
@@ -421,14 +455,14 @@ __global__ void __launch_bounds__(kUpdateThreads) update_kernel(DeviceTables t, 
 
         // ---- stores: 92 B per survivor (100 B when a compacting stream moves its constants)
         if (alive) {
-            a.m0[dslot] = M0;
-            a.m1[dslot] = M1;
-            a.m2[dslot] = M2;
-            a.m3[dslot] = M3;
-            if (COMPACT) a.k[dslot] = K;
-            a.o0[dslot] = c0;
-            a.o1[dslot] = c1;
-            a.o2[dslot] = scale;
+            st_pack(a.m0 + dslot, M0);
+            st_pack(a.m1 + dslot, M1);
+            st_pack(a.m2 + dslot, M2);
+            st_pack(a.m3 + dslot, M3);
+            if (COMPACT) st_pack(a.k + dslot, K);
+            st_pack(a.o0 + dslot, c0);
+            st_pack(a.o1 + dslot, c1);
+            st_pack(a.o2 + dslot, scale);
         }
         __syncthreads(); // settings / tile-ref buffers are reused by the next iterations
     }
@@ -536,8 +570,12 @@ cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint3
     return cudaGetLastError();
 }
 cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t total_spawn, cudaStream_t s) {
+    // total_spawn == 0xFFFFFFFF: "unknown at launch time" (graph replay): a fixed grid that
+    // covers any count by striding; otherwise just enough CTAs
     if (total_spawn == 0) return cudaSuccess;
-    spawn_kernel<<<(total_spawn + 255u) / 256u, 256, 0, s>>>(t, f);
+    const uint32_t fixed = 148u * 8u;
+    const uint32_t blocks = total_spawn == 0xFFFFFFFFu ? fixed : std::min(fixed, (total_spawn + 255u) / 256u);
+    spawn_kernel<<<blocks, 256, 0, s>>>(t, f);
     return cudaGetLastError();
 }
 cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, cudaStream_t s) {

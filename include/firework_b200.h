@@ -211,7 +211,8 @@ typedef struct fw_config {
     uint32_t reserved;
 } fw_config;
 
-#define FW_FLAG_PROFILE 1u /* record CUDA events around every kernel of a frame */
+#define FW_FLAG_PROFILE 1u   /* record CUDA events around every kernel of a frame */
+#define FW_FLAG_NO_GRAPHS 2u /* always launch kernel by kernel (never replay frames as CUDA graphs) */
 
 typedef struct fw_context fw_context;
 
