@@ -148,7 +148,7 @@ class fw_spawner_status(C.Structure):
 
 class fw_frame_profile(C.Structure):
     _fields_ = [("plan_ms", f32), ("spawn_ms", f32), ("update_ms", f32), ("total_ms", f32),
-                ("kernel_launches", u32), ("reserved", u32),
+                ("kernel_launches", u32), ("timed_frames", u32),
                 ("particles_updated", u64), ("particles_spawned", u64),
                 ("h2d_bytes", u64), ("d2h_bytes", u64)]
 
@@ -201,6 +201,7 @@ EXPORTS = {
     "fw_read_aabb": (C.c_int, [_ctx, u32, P(f32 * 3), P(f32 * 3), P(u32)]),
     "fw_pack_instances_device": (C.c_int, [_ctx, C.c_void_p, u64, P(u64)]),
     "fw_total_live": (C.c_int, [_ctx, P(u64)]),
+    "fw_set_profiling": (C.c_int, [_ctx, u32]),
     "fw_profile_last": (C.c_int, [_ctx, P(fw_frame_profile)]),
     "fw_profile_sum": (C.c_int, [_ctx, P(fw_frame_profile), P(u32)]),
     "fw_profile_reset": (C.c_int, [_ctx]),

@@ -210,6 +210,9 @@ class Engine:
         self._check(self._L.fw_event_elapsed_ms(self._ctx, a, b, C.byref(ms)))
         return float(ms.value)
 
+    def set_profiling(self, on: bool):
+        self._check(self._L.fw_set_profiling(self._ctx, 1 if on else 0))
+
     def profile_last(self) -> _abi.fw_frame_profile:
         p = _abi.fw_frame_profile()
         self._check(self._L.fw_profile_last(self._ctx, C.byref(p)))

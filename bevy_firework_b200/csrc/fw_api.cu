@@ -76,7 +76,8 @@ struct FrameSlot {
     std::vector<uint32_t> spawn_per_slot; // host copy, for the n_hi bound
     // profiling
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool profiled = false;
+    bool profiled = false;        // events ev[0..3] were recorded around the kernels
+    bool pending_account = false; // not yet added to the profile sums
     uint64_t particles_spawned = 0;
     uint32_t launches = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
@@ -143,6 +144,8 @@ struct fw_context {
     fw_frame_profile prof_last{};
     fw_frame_profile prof_sum{};
     uint32_t prof_frames = 0;
+    uint32_t prof_timed_frames = 0;
+    bool profiling = false; // timed frames are launched kernel by kernel (events inside a graph do not time)
     // last exact state snapshot (valid after refresh_exact)
     std::vector<StreamState> snapshot;
 };
@@ -496,14 +499,20 @@ int ensure_frame_slot(fw_context *ctx, FrameSlot &fs, size_t bytes) {
     return FW_OK;
 }
 
+// account one completed frame: counts always, kernel times when it was a timed frame
 void absorb_profile(fw_context *ctx, FrameSlot &fs) {
-    if (!fs.profiled) return;
-    fs.profiled = false;
+    if (!fs.pending_account) return;
+    fs.pending_account = false;
     fw_frame_profile p{};
-    cudaEventElapsedTime(&p.plan_ms, fs.ev[0], fs.ev[1]);
-    cudaEventElapsedTime(&p.spawn_ms, fs.ev[1], fs.ev[2]);
-    cudaEventElapsedTime(&p.update_ms, fs.ev[2], fs.ev[3]);
-    cudaEventElapsedTime(&p.total_ms, fs.ev[0], fs.ev[3]);
+    if (fs.profiled) {
+        cudaEventElapsedTime(&p.plan_ms, fs.ev[0], fs.ev[1]);
+        cudaEventElapsedTime(&p.spawn_ms, fs.ev[1], fs.ev[2]);
+        cudaEventElapsedTime(&p.update_ms, fs.ev[2], fs.ev[3]);
+        cudaEventElapsedTime(&p.total_ms, fs.ev[0], fs.ev[3]);
+        ctx->prof_timed_frames++;
+        p.timed_frames = 1;
+    }
+    fs.profiled = false;
     p.kernel_launches = fs.launches;
     p.particles_spawned = fs.particles_spawned;
     p.h2d_bytes = fs.h2d_bytes;
@@ -519,6 +528,7 @@ void absorb_profile(fw_context *ctx, FrameSlot &fs) {
     ctx->prof_sum.particles_updated += p.particles_updated;
     ctx->prof_sum.h2d_bytes += p.h2d_bytes;
     ctx->prof_sum.d2h_bytes += p.d2h_bytes;
+    ctx->prof_sum.timed_frames = ctx->prof_timed_frames;
     ctx->prof_frames++;
 }
 
@@ -603,6 +613,7 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
     ctx->seed = cfg->seed;
     ctx->flags = cfg->flags;
     ctx->use_graphs = (cfg->flags & FW_FLAG_NO_GRAPHS) == 0;
+    ctx->profiling = (cfg->flags & FW_FLAG_PROFILE) != 0;
     CU(nullptr, cudaSetDevice(cfg->device));
     if (cfg->external_stream) {
         ctx->stream = (cudaStream_t)cfg->external_stream;
@@ -929,7 +940,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     f.cmds = (const SpawnCmd *)(fs.dev + off_cmds);
     f.inputs = (const SpawnerInput *)(fs.dev + off_inputs);
 
-    const bool prof = (ctx->flags & FW_FLAG_PROFILE) != 0;
+    const bool prof = ctx->profiling;
     uint32_t variant_mask = 0;
     for (uint32_t v = 0; v < kNumVariants; v++)
         if (ctx->variant_streams[v]) variant_mask |= 1u << v;
@@ -960,7 +971,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
         return FW_OK;
     };
     ctx->topo_stable_frames++;
-    if (ctx->use_graphs && ctx->topo_stable_frames > kGraphWarmFrames) {
+    if (ctx->use_graphs && !prof && ctx->topo_stable_frames > kGraphWarmFrames) {
         if (!fs.graph_exec || fs.graph_version != ctx->topo_version) {
             if (fs.graph_exec) cudaGraphExecDestroy(fs.graph_exec);
             fs.graph_exec = nullptr;
@@ -995,6 +1006,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     fs.in_flight = true;
     fs.frame = ctx->frame_no;
     fs.profiled = prof;
+    fs.pending_account = true;
     fs.launches = launches;
     fs.particles_spawned = total_spawn;
     fs.h2d_bytes = bytes;
@@ -1253,9 +1265,14 @@ int fw_event_elapsed_ms(fw_context *ctx, uint32_t a, uint32_t b, float *out_ms) 
     return FW_OK;
 }
 
+int fw_set_profiling(fw_context *ctx, uint32_t on) {
+    ENTER(ctx);
+    ctx->profiling = on != 0;
+    return FW_OK;
+}
+
 int fw_profile_last(fw_context *ctx, fw_frame_profile *out) {
     ENTER(ctx);
-    if (!(ctx->flags & FW_FLAG_PROFILE)) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "context was created without FW_FLAG_PROFILE");
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     // absorb in submission order
     for (uint32_t k = 0; k < kRing; k++) absorb_profile(ctx, ctx->ring[(ctx->frame_no + k) % kRing]);
@@ -1271,13 +1288,12 @@ int fw_profile_sum(fw_context *ctx, fw_frame_profile *out, uint32_t *n_frames) {
 }
 int fw_profile_reset(fw_context *ctx) {
     ENTER(ctx);
-    if (ctx->flags & FW_FLAG_PROFILE) {
-        int rc = fw_profile_last(ctx, nullptr);
-        if (rc) return rc;
-    }
+    int rc = fw_profile_last(ctx, nullptr);
+    if (rc) return rc;
     memset(&ctx->prof_sum, 0, sizeof(ctx->prof_sum));
     memset(&ctx->prof_last, 0, sizeof(ctx->prof_last));
     ctx->prof_frames = 0;
+    ctx->prof_timed_frames = 0;
     return FW_OK;
 }
 

@@ -230,7 +230,7 @@ typedef struct fw_frame_profile {
     float update_ms;
     float total_ms;
     uint32_t kernel_launches;
-    uint32_t reserved;
+    uint32_t timed_frames; /* frames whose kernel times are in *_ms (profiling was on) */
     uint64_t particles_updated; /* live particles entering the update of that frame */
     uint64_t particles_spawned;
     uint64_t h2d_bytes; /* per-frame parameter block copied host -> device */
@@ -305,6 +305,11 @@ int fw_total_live(fw_context *ctx, uint64_t *out);
 
 /* profile of the most recent frame (FW_FLAG_PROFILE; synchronises) and the running sums since
  * the last fw_profile_reset */
+/* Frame accounting. Counts (particles, launches, bytes) are accumulated for every frame;
+ * kernel times only for frames submitted while profiling is on (FW_FLAG_PROFILE at creation or
+ * fw_set_profiling): those frames are launched kernel by kernel with CUDA events around each
+ * kernel, all other frames may be replayed as CUDA graphs. */
+int fw_set_profiling(fw_context *ctx, uint32_t on);
 int fw_profile_last(fw_context *ctx, fw_frame_profile *out);
 int fw_profile_sum(fw_context *ctx, fw_frame_profile *out, uint32_t *n_frames);
 int fw_profile_reset(fw_context *ctx);
