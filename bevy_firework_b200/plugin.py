@@ -178,7 +178,7 @@ class App:
         eng = self.engine
         # propagate_particle_spawner_modifier (src/core.rs:690-703)
         for eid, e in list(self._entities.items()):
-            if e.modifier is not None and e.spawner is None:
+            if e.modifier is not None:
                 for child in self._descendants(eid):
                     if self._entities[child].spawner is not None:
                         self._entities[child].modifier = e.modifier
