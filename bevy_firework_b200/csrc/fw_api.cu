@@ -112,6 +112,7 @@ struct fw_context {
     std::vector<uint32_t> free_emitters;
     fw_emission_settings *d_emitters = nullptr;
     fw_collider *d_colliders = nullptr;
+    float4 *d_collider_bounds = nullptr;
     uint32_t n_colliders = 0;
     uint32_t *d_tile_prefix = nullptr; // kNumVariants x (slots_cap + 1)
     uint8_t *d_stage = nullptr;        // staging of ParticleData rows (host mirror reads/writes)
@@ -663,6 +664,7 @@ int fw_destroy(fw_context *ctx) {
     cudaFree(ctx->d_settings);
     cudaFree(ctx->d_emitters);
     cudaFree(ctx->d_colliders);
+    cudaFree(ctx->d_collider_bounds);
     cudaFree(ctx->d_tile_prefix);
     cudaFree(ctx->d_stage);
     cudaFree(ctx->d_lookback);
@@ -790,9 +792,35 @@ int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) 
     ctx->d_colliders = nullptr;
     ctx->n_colliders = n;
     topo_changed(ctx);
+    if (ctx->d_collider_bounds) CU(ctx, cudaFree(ctx->d_collider_bounds));
+    ctx->d_collider_bounds = nullptr;
     if (n) {
         CU(ctx, cudaMalloc((void **)&ctx->d_colliders, sizeof(fw_collider) * n));
         CU(ctx, cudaMemcpy(ctx->d_colliders, colliders, sizeof(fw_collider) * n, cudaMemcpyHostToDevice));
+        // broad-phase bounds: world AABB of every collider, inflated well beyond fp32 rounding
+        std::vector<float4> bounds(2 * (size_t)n);
+        for (uint32_t i = 0; i < n; i++) {
+            const fw_collider &c = colliders[i];
+            const double x = c.rotation[0], y = c.rotation[1], z = c.rotation[2], w = c.rotation[3];
+            const double R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)},
+                                    {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
+                                    {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
+            float lo[3], hi[3];
+            for (int a = 0; a < 3; a++) {
+                double ext = c.kind == FW_COLLIDER_SPHERE
+                                 ? std::fabs((double)c.half_extents[0])
+                                 : std::fabs(R[a][0] * c.half_extents[0]) + std::fabs(R[a][1] * c.half_extents[1]) + std::fabs(R[a][2] * c.half_extents[2]);
+                const double margin = 1e-3 + 1e-3 * (std::fabs((double)c.translation[a]) + ext);
+                lo[a] = (float)(c.translation[a] - ext - margin);
+                hi[a] = (float)(c.translation[a] + ext + margin);
+            }
+            float layers_bits;
+            memcpy(&layers_bits, &c.layers, 4);
+            bounds[2 * i] = make_float4(lo[0], lo[1], lo[2], layers_bits);
+            bounds[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+        }
+        CU(ctx, cudaMalloc((void **)&ctx->d_collider_bounds, sizeof(float4) * bounds.size()));
+        CU(ctx, cudaMemcpy(ctx->d_collider_bounds, bounds.data(), sizeof(float4) * bounds.size(), cudaMemcpyHostToDevice));
     }
     return FW_OK;
 }
@@ -927,6 +955,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     t.settings = ctx->d_settings;
     t.emitters = ctx->d_emitters;
     t.colliders = ctx->d_colliders;
+    t.collider_bounds = ctx->d_collider_bounds;
     t.n_colliders = ctx->n_colliders;
     t.tile_prefix = ctx->d_tile_prefix;
     t.slots_cap = ctx->slots_cap;

@@ -161,6 +161,7 @@ struct DeviceTables {
     const DevParticleSettings *settings; // indexed by stream slot
     const fw_emission_settings *emitters;
     const fw_collider *colliders;
+    const float4 *collider_bounds; // 2 per collider: inflated world AABB min (+ layers bits), max
     uint32_t n_colliders;
     // tile_prefix[v * slots_cap + s] = number of update tiles of variant v in slots < s
     uint32_t *tile_prefix;

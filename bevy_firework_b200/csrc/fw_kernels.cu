@@ -146,13 +146,20 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
 
 // ------------------------------------------------------------------------------------------
 // spawn: one thread per new particle (g = index of the particle among this frame's spawns)
-__device__ __forceinline__ void spawn_one(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t g) {
-    // command of this particle: last c with cmds[c].first <= g
+__device__ __forceinline__ uint32_t find_cmd(const FrameDeviceInputs &f, uint32_t g) {
+    // last c with cmds[c].first <= g
     uint32_t lo = 0, hi = f.header->n_cmds;
     while (hi - lo > 1u) {
         const uint32_t mid = (lo + hi) >> 1;
         if (f.cmds[mid].first <= g) lo = mid; else hi = mid;
     }
+    return lo;
+}
+__device__ __forceinline__ void spawn_one(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t g, uint32_t c_hint) {
+    // command of this particle: the CTA's first particle belongs to c_hint; walk forward
+    uint32_t lo = c_hint;
+    const uint32_t n_cmds = f.header->n_cmds;
+    while (lo + 1u < n_cmds && f.cmds[lo + 1u].first <= g) lo++;
     const SpawnCmd cmd = f.cmds[lo];
     const uint32_t j = g - cmd.first;
     const StreamDesc d = t.descs[cmd.stream];
@@ -230,8 +237,16 @@ __device__ __forceinline__ void spawn_one(const DeviceTables &t, const FrameDevi
 // grid-stride so the launch configuration is frame-independent (CUDA-graph friendly): the
 // number of new particles is read from the frame header on the device
 __global__ void __launch_bounds__(256) spawn_kernel(DeviceTables t, FrameDeviceInputs f) {
+    __shared__ uint32_t s_cmd;
     const uint32_t total = f.header->total_spawn;
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) spawn_one(t, f, g);
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        // one binary search per CTA chunk (a chunk of 256 particles spans very few commands)
+        if (threadIdx.x == 0) s_cmd = find_cmd(f, base);
+        __syncthreads();
+        const uint32_t g = base + threadIdx.x;
+        if (g < total) spawn_one(t, f, g, s_cmd);
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -363,7 +378,7 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : FW
             V3 pos = v3(M0.x, M0.y, M0.z), vel = v3(M2.x, M2.y, M2.z);
             bool should_destroy = false;
             if (COLLIDE) {
-                particle_collision(t.colliders, t.n_colliders, ps.collision, pos, vel, dt, should_destroy); // :608-617
+                particle_collision(t.colliders, t.collider_bounds, t.n_colliders, ps.collision, pos, vel, dt, should_destroy); // :608-617
             } else {
                 pos = pos + vel * dt;                                       // :619-623
             }

@@ -281,15 +281,25 @@ __device__ __forceinline__ bool ray_ball_local(float radius, V3 o, V3 d, float m
     normal = n;
     return true;
 }
-__device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ colliders, uint32_t n,
-                                         uint32_t filter_mask, V3 o, V3 d, float max_distance,
+// Broad phase: bounds[2i] = (world AABB min.xyz, layers bits), bounds[2i+1] = (max.xyz, -),
+// inflated on the host by far more than any fp32 rounding of the exact test, so a collider is
+// skipped only when the exact test below could not report a hit within max_distance: the result
+// is identical to testing every collider (the CPU oracle does exactly that). NaN never culls.
+__device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ colliders, const float4 *__restrict__ bounds,
+                                         uint32_t n, uint32_t filter_mask, V3 o, V3 d, float max_distance,
                                          float &distance, V3 &normal) {
     bool found = false;
     float best = 0.0f;
     V3 best_n = v3(0.0f, 0.0f, 0.0f);
+    const V3 e = o + d * max_distance;
+    const V3 slo = v3(fminf(o.x, e.x), fminf(o.y, e.y), fminf(o.z, e.z));
+    const V3 shi = v3(fmaxf(o.x, e.x), fmaxf(o.y, e.y), fmaxf(o.z, e.z));
+    const bool cull_ok = isfinite(e.x) && isfinite(e.y) && isfinite(e.z) && isfinite(o.x) && isfinite(o.y) && isfinite(o.z);
     for (uint32_t i = 0; i < n; i++) {
+        const float4 blo = __ldg(bounds + 2u * i), bhi = __ldg(bounds + 2u * i + 1u);
+        if ((__float_as_uint(blo.w) & filter_mask) == 0u) continue;
+        if (cull_ok && (shi.x < blo.x || slo.x > bhi.x || shi.y < blo.y || slo.y > bhi.y || shi.z < blo.z || slo.z > bhi.z)) continue;
         const fw_collider &c = colliders[i];
-        if ((c.layers & filter_mask) == 0u) continue;
         Q4 rot{c.rotation[0], c.rotation[1], c.rotation[2], c.rotation[3]};
         Q4 inv = qconj(rot);
         V3 tr = v3(c.translation[0], c.translation[1], c.translation[2]);
@@ -312,8 +322,8 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
 }
 
 // reference src/core.rs:744-800 particle_collision
-__device__ __forceinline__ void particle_collision(const fw_collider *__restrict__ colliders, uint32_t n_colliders,
-                                                   const fw_collision_settings &cs, V3 &pos, V3 &vel,
+__device__ __forceinline__ void particle_collision(const fw_collider *__restrict__ colliders, const float4 *__restrict__ bounds,
+                                                   uint32_t n_colliders, const fw_collision_settings &cs, V3 &pos, V3 &vel,
                                                    float delta, bool &should_destroy) {
     const float orig_delta = delta;
     int n_steps = 0;
@@ -323,7 +333,7 @@ __device__ __forceinline__ void particle_collision(const fw_collider *__restrict
         V3 dir = (isfinite(len) && len > 0.0f) ? vel / len : v3(0.0f, 1.0f, 0.0f);
         float distance;
         V3 hit_normal;
-        if (cast_ray(colliders, n_colliders, cs.filter_mask, pos, dir, length(vel) * delta, distance, hit_normal)) {
+        if (cast_ray(colliders, bounds, n_colliders, cs.filter_mask, pos, dir, length(vel) * delta, distance, hit_normal)) {
             if (distance == 0.0f) {
                 V3 normal = hit_normal;
                 if (is_zero(normal)) {
