@@ -162,16 +162,14 @@ class Engine:
         self._check(self._L.fw_spawner_mark_finished_notified(self._ctx, key))
 
     def _read_rows(self, fn, dtype, key, type_):
-        # size from the exact count, then the rows
-        cnt = self.counts(key)[type_] if fn is not self._L.fw_read_destroyed else 0
+        # first call sizes the buffer (FW_ERR_BUFFER_TOO_SMALL still reports the count)
         n = C.c_uint64()
-        if fn is self._L.fw_read_destroyed:
-            rc = fn(self._ctx, key, type_, None, 0, C.byref(n))
-            if rc not in (_abi.FW_OK, _abi.FW_ERR_BUFFER_TOO_SMALL):
-                self._check(rc)
-            cnt = n.value
-        out = np.zeros(cnt, dtype=dtype)
-        self._check(fn(self._ctx, key, type_, out.ctypes.data if cnt else None, cnt, C.byref(n)))
+        rc = fn(self._ctx, key, type_, None, 0, C.byref(n))
+        if rc not in (_abi.FW_OK, _abi.FW_ERR_BUFFER_TOO_SMALL):
+            self._check(rc)
+        out = np.zeros(n.value, dtype=dtype)
+        if n.value:
+            self._check(fn(self._ctx, key, type_, out.ctypes.data, n.value, C.byref(n)))
         return out[: n.value]
 
     def read_particles(self, key, type_=0) -> np.ndarray:

@@ -34,19 +34,24 @@ struct Emitter {
     float time_passed_in_cycle = 0.f;
     bool enabled = true;
     bool emits_on_other_particles = false;
-    uint64_t serial = 0;   // particles spawned since reset (RNG protocol)
-    uint32_t dev_idx = 0;  // index into the device emitter array
+    uint64_t serial = 0;   // particles spawned since reset (RNG protocol; Global emitters)
+    uint32_t dev_idx = 0;  // index into the device emitter array (and nested_serial)
+    uint32_t lea_index = 0; // Nested: which last_emitted_age array of the target stream
 };
 
-struct Block { // one device allocation holding the four arrays of a stream
+struct Block { // one device allocation holding the packs of a stream
     void *base = nullptr;
     uint32_t capacity = 0;
+    uint32_t n_lea = 0;
 };
 
 struct Stream {
     uint32_t slot = 0;
     uint32_t type = 0;
     Block block;
+    Block destroyed; // particles destroyed by the last update (capture_destroyed types only)
+    uint32_t n_lea = 0;     // nested emitters targeting this type
+    bool injected = false;  // state was written by the host: nested emitters may catch up at once
     uint32_t variant = kFifo;
     uint64_t n_hi = 0;        // host-side upper bound of the live count
     uint64_t born_frame = 0;  // readbacks of older frames do not describe this stream
@@ -73,7 +78,7 @@ struct FrameSlot {
     cudaEvent_t done = nullptr;
     bool in_flight = false;
     uint64_t frame = 0;
-    std::vector<uint32_t> spawn_per_slot; // host copy, for the n_hi bound
+    std::vector<uint32_t> spawn_per_slot; // host copy (all phases summed), for the n_hi bound
     // profiling
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool profiled = false;        // events ev[0..3] were recorded around the kernels
@@ -111,6 +116,7 @@ struct fw_context {
     uint32_t emitters_cap = 0, n_emitters = 0;
     std::vector<uint32_t> free_emitters;
     fw_emission_settings *d_emitters = nullptr;
+    std::vector<fw_emission_settings> h_emitters; // host copy, indexed like d_emitters
     fw_collider *d_colliders = nullptr;
     float4 *d_collider_bounds = nullptr;
     uint32_t n_colliders = 0;
@@ -129,7 +135,7 @@ struct fw_context {
     uint64_t extract_cap = 0;
     cudaEvent_t user_events[16] = {};
 
-    std::map<uint32_t, std::vector<void *>> block_cache; // capacity -> free device blocks
+    std::map<size_t, std::vector<void *>> block_cache; // bytes -> free device blocks
     FrameSlot ring[kRing];
     uint64_t frame_no = 0; // frames submitted so far; epoch of the next frame = frame_no + 1
     // topology = everything a captured frame graph bakes in (table pointers, slot / emitter /
@@ -137,7 +143,15 @@ struct fw_context {
     uint64_t topo_version = 1;
     uint32_t topo_stable_frames = 0;
     uint32_t live_emitters = 0;
+    uint32_t live_nested = 0; // nested emitters over all spawners
+    uint32_t n_phases = 1;    // 1 + max nested emitters per spawner
     bool use_graphs = true;
+    // nested emission scratch
+    uint32_t *d_nested_scratch = nullptr;
+    uint64_t nested_scratch_cap = 0;
+    unsigned long long *d_nested_serial = nullptr; // per device emitter
+    NestedOut *d_nested_out = nullptr;
+    uint32_t nested_out_cap = 0;
     int grids[kNumVariants] = {0, 0, 0, 0};
     uint32_t variant_streams[kNumVariants] = {0, 0, 0, 0};
 
@@ -232,41 +246,46 @@ inline uint32_t round_capacity(uint64_t want) {
     if (r > 0xFFFFFF00ull) r = 0xFFFFFF00ull;
     return (uint32_t)r;
 }
-inline size_t block_bytes(uint32_t cap) { return (size_t)cap * kBytesPerSlot; }
-inline StreamDesc block_desc(const Block &b, uint32_t variant) {
+inline size_t block_bytes(uint32_t cap, uint32_t n_lea) { return (size_t)cap * (kBytesPerSlot + 4u * n_lea); }
+inline StreamDesc block_desc(const Block &b, uint32_t variant, const Block *destroyed = nullptr) {
     StreamDesc d{};
     d.base = (uint8_t *)b.base;
+    d.destroyed_base = destroyed ? (uint8_t *)destroyed->base : nullptr;
     d.capacity = b.capacity;
     d.variant = variant;
+    d.n_lea = b.n_lea;
     return d;
 }
 
-int alloc_block(fw_context *ctx, uint32_t capacity, Block &out) {
-    auto it = ctx->block_cache.find(capacity);
+int alloc_block(fw_context *ctx, uint32_t capacity, uint32_t n_lea, Block &out) {
+    const size_t bytes = block_bytes(capacity, n_lea);
+    auto it = ctx->block_cache.find(bytes);
     if (it != ctx->block_cache.end() && !it->second.empty()) {
         out.base = it->second.back();
         it->second.pop_back();
         out.capacity = capacity;
+        out.n_lea = n_lea;
         return FW_OK;
     }
     void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, block_bytes(capacity));
+    cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) {
         // drop the cache and retry once
         for (auto &kv : ctx->block_cache)
             for (void *q : kv.second) cudaFree(q);
         ctx->block_cache.clear();
         (void)cudaGetLastError();
-        e = cudaMalloc(&p, block_bytes(capacity));
+        e = cudaMalloc(&p, bytes);
     }
     if (e != cudaSuccess) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "cudaMalloc of a %u-particle stream failed: %s", capacity, cudaGetErrorString(e));
     out.base = p;
     out.capacity = capacity;
+    out.n_lea = n_lea;
     return FW_OK;
 }
 void release_block(fw_context *ctx, Block &b) {
     // all work is ordered on one CUDA stream, so a cached block can be handed out again at once
-    if (b.base) ctx->block_cache[b.capacity].push_back(b.base);
+    if (b.base) ctx->block_cache[block_bytes(b.capacity, b.n_lea)].push_back(b.base);
     b.base = nullptr;
     b.capacity = 0;
 }
@@ -306,6 +325,8 @@ int ensure_emitters(fw_context *ctx, uint32_t need) {
     while (ncap < need) ncap *= 2;
     int rc = grow_device_array(ctx, ctx->d_emitters, ctx->emitters_cap, ncap);
     if (rc) return rc;
+    if ((rc = grow_device_array(ctx, ctx->d_nested_serial, ctx->emitters_cap, ncap))) return rc;
+    ctx->h_emitters.resize(ncap);
     ctx->emitters_cap = ncap;
     topo_changed(ctx);
     return FW_OK;
@@ -394,6 +415,7 @@ void free_stream(fw_context *ctx, Stream &st) {
     ctx->tiles_needed -= (st.block.capacity + kTile - 1) / kTile;
     ctx->variant_streams[st.variant]--;
     release_block(ctx, st.block);
+    release_block(ctx, st.destroyed);
     StreamDesc zero{};
     ctx->h_descs[st.slot] = zero;
     cudaMemcpyAsync(ctx->d_descs + st.slot, &zero, sizeof(zero), cudaMemcpyHostToDevice, ctx->stream);
@@ -410,7 +432,7 @@ void free_spawner_resources(fw_context *ctx, Spawner &sp) {
 }
 
 int upload_desc(fw_context *ctx, const Stream &st) {
-    const StreamDesc d = block_desc(st.block, st.variant);
+    const StreamDesc d = block_desc(st.block, st.variant, st.destroyed.base ? &st.destroyed : nullptr);
     ctx->h_descs[st.slot] = d;
     CU(ctx, cudaMemcpyAsync(ctx->d_descs + st.slot, &d, sizeof(d), cudaMemcpyHostToDevice, ctx->stream));
     return FW_OK;
@@ -461,8 +483,12 @@ int grow_stream(fw_context *ctx, Stream &st, uint64_t need) {
     const uint32_t ncap = round_capacity(std::max<uint64_t>(need + need / 4, (uint64_t)st.block.capacity * 2));
     if ((uint64_t)ncap < need) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "stream would exceed 2^32 particles");
     Block nb;
-    int rc = alloc_block(ctx, ncap, nb);
+    int rc = alloc_block(ctx, ncap, st.n_lea, nb);
     if (rc) return rc;
+    if (st.destroyed.base) { // same capacity; its content only lives until the next frame
+        release_block(ctx, st.destroyed);
+        if ((rc = alloc_block(ctx, ncap, st.n_lea, st.destroyed))) return rc;
+    }
     // unwrap the ring into the start of the new block
     CU(ctx, launch_ring_copy(block_desc(st.block, st.variant), first, live, block_desc(nb, st.variant), ctx->stream));
     StreamState ns = s;
@@ -542,6 +568,19 @@ bool spawner_active(const Spawner &sp, bool any_particles) {
         else enabled |= e.enabled;
     }
     return enabled;
+}
+
+// topology summary of the nested emitters: total and the number of phases a frame needs
+void recount_nested(fw_context *ctx) {
+    uint32_t total = 0, max_per = 0;
+    for (auto &sp : ctx->spawners) {
+        uint32_t n = 0;
+        for (const Emitter &e : sp->emitters) n += e.emits_on_other_particles ? 1u : 0u;
+        total += n;
+        max_per = std::max(max_per, n);
+    }
+    ctx->live_nested = total;
+    ctx->n_phases = 1 + max_per;
 }
 
 Spawner *find(fw_context *ctx, uint32_t key) {
@@ -645,8 +684,10 @@ int fw_destroy(fw_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &sp : ctx->spawners)
-        for (Stream &st : sp->streams)
+        for (Stream &st : sp->streams) {
             if (st.block.base) cudaFree(st.block.base);
+            if (st.destroyed.base) cudaFree(st.destroyed.base);
+        }
     for (auto &kv : ctx->block_cache)
         for (void *p : kv.second) cudaFree(p);
     for (FrameSlot &fs : ctx->ring) {
@@ -666,6 +707,9 @@ int fw_destroy(fw_context *ctx) {
     cudaFree(ctx->d_colliders);
     cudaFree(ctx->d_collider_bounds);
     cudaFree(ctx->d_tile_prefix);
+    cudaFree(ctx->d_nested_scratch);
+    cudaFree(ctx->d_nested_serial);
+    cudaFree(ctx->d_nested_out);
     cudaFree(ctx->d_stage);
     cudaFree(ctx->d_lookback);
     cudaFree(ctx->d_plan);
@@ -695,8 +739,20 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
         if (es[i].particle_index >= n_types) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "emitter %u: particle_index %u out of range", i, es[i].particle_index);
         if (es[i].pacing_kind > FW_PACING_COUNT_OVER_DURATION) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "emitter %u: unknown pacing", i);
         if (es[i].shape_kind > FW_SHAPE_CIRCLE) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "emitter %u: unknown shape", i);
-        if (es[i].mode == FW_MODE_NESTED) return fail(ctx, FW_ERR_UNSUPPORTED, "emitter %u: EmissionMode::Nested is not implemented yet", i);
         if (es[i].mode > FW_MODE_NESTED) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "emitter %u: unknown emission mode", i);
+        if (es[i].mode == FW_MODE_NESTED && es[i].target_particle_type >= n_types)
+            return fail(ctx, FW_ERR_INVALID_ARGUMENT, "emitter %u: target_particle_type %u out of range", i, es[i].target_particle_type);
+    }
+    {
+        uint32_t n_nested = 0;
+        std::vector<uint32_t> lea_per_type(n_types, 0);
+        for (uint32_t i = 0; i < n_emitters; i++)
+            if (es[i].mode == FW_MODE_NESTED) {
+                n_nested++;
+                if (++lea_per_type[es[i].target_particle_type] > kMaxLea)
+                    return fail(ctx, FW_ERR_UNSUPPORTED, "more than %u nested emitters target particle type %u", kMaxLea, es[i].target_particle_type);
+            }
+        if (n_nested + 1 > kMaxPhases) return fail(ctx, FW_ERR_UNSUPPORTED, "more than %u nested emitters in one spawner", kMaxPhases - 1);
     }
     Spawner *sp = find(ctx, key);
     if (!sp) {
@@ -723,6 +779,10 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
         e.enabled = starts_enabled != 0;
         e.emits_on_other_particles = es[i].mode == FW_MODE_NESTED;
         e.serial = 0;
+        e.lea_index = 0;
+        if (e.emits_on_other_particles)
+            for (uint32_t k = 0; k < i; k++)
+                if (es[k].mode == FW_MODE_NESTED && es[k].target_particle_type == es[i].target_particle_type) e.lea_index++;
         if (!ctx->free_emitters.empty()) {
             e.dev_idx = ctx->free_emitters.back();
             ctx->free_emitters.pop_back();
@@ -732,6 +792,8 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
             e.dev_idx = ctx->n_emitters++;
         }
         CU(ctx, cudaMemcpyAsync(ctx->d_emitters + e.dev_idx, &es[i], sizeof(fw_emission_settings), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemsetAsync(ctx->d_nested_serial + e.dev_idx, 0, sizeof(unsigned long long), ctx->stream));
+        ctx->h_emitters[e.dev_idx] = es[i];
     }
     sp->streams.resize(n_types);
     for (uint32_t t = 0; t < n_types; t++) {
@@ -741,6 +803,10 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
         st.variant = pick_variant(ps[t]);
         st.n_hi = 0;
         st.born_frame = ctx->frame_no + 1;
+        st.injected = false;
+        st.n_lea = 0;
+        for (uint32_t i = 0; i < n_emitters; i++)
+            if (es[i].mode == FW_MODE_NESTED && es[i].target_particle_type == t) st.n_lea++;
     }
     for (uint32_t t = 0; t < n_types; t++) {
         Stream &st = sp->streams[t];
@@ -752,8 +818,9 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
             if (rc) return rc;
             st.slot = ctx->n_slots++;
         }
-        int rc = alloc_block(ctx, round_capacity(estimate_capacity(*sp, t)), st.block);
+        int rc = alloc_block(ctx, round_capacity(estimate_capacity(*sp, t)), st.n_lea, st.block);
         if (rc) return rc;
+        if (ps[t].capture_destroyed && (rc = alloc_block(ctx, st.block.capacity, st.n_lea, st.destroyed))) return rc;
         ctx->tiles_needed += (st.block.capacity + kTile - 1) / kTile;
         ctx->variant_streams[st.variant]++;
         ctx->slot_owner[st.slot] = &st;
@@ -765,6 +832,7 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
     }
     sp->finished_notified = false;
     sp->manual_queued_count = 0;
+    recount_nested(ctx);
     return ensure_tiles(ctx);
 }
 
@@ -779,6 +847,7 @@ int fw_spawner_remove(fw_context *ctx, uint32_t key) {
             ctx->spawners.erase(ctx->spawners.begin() + (long)i);
             break;
         }
+    recount_nested(ctx);
     return FW_OK;
 }
 
@@ -850,17 +919,46 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     }
     absorb_profile(ctx, fs);
 
-    // ---- spawn_particles, host part (reference src/core.rs:377-428)
-    std::vector<SpawnCmd> cmds;
+    // ---- spawn_particles, host part (reference src/core.rs:377-428). The emitters of a spawner
+    // are walked in order; its k-th Nested emitter closes phase k (see PhaseInfo).
+    const uint32_t n_phases = ctx->n_phases;
+    const uint32_t n_slots = ctx->n_slots;
+    std::vector<SpawnCmd> cmds[kMaxPhases];
+    std::vector<NestedCmd> nested[kMaxPhases];
+    std::vector<uint32_t> spawn_per_slot((size_t)n_phases * std::max(1u, n_slots), 0u); // [phase][slot]
+    uint64_t phase_total[kMaxPhases] = {0};
     std::vector<SpawnerInput> sinputs;
-    fs.spawn_per_slot.assign(ctx->n_slots, 0u);
-    uint64_t total_spawn = 0;
     for (auto &spp : ctx->spawners) {
         Spawner &sp = *spp;
-        if (!spawner_active(sp, true)) continue; // :378
+        if (!spawner_active(sp, true)) continue; // :378 (a nested emitter without parents emits nothing anyway)
         int input_idx = -1;
+        auto need_input = [&]() {
+            if (input_idx < 0) {
+                input_idx = (int)sinputs.size();
+                sinputs.push_back(sp.input);
+            }
+            return (uint32_t)input_idx;
+        };
+        uint32_t phase = 0;
         for (uint32_t i = 0; i < sp.emitters.size(); i++) { // :386
             Emitter &e = sp.emitters[i];
+            if (e.emits_on_other_particles) { // EmissionMode::Nested (:471-546)
+                const uint32_t my_phase = phase++;
+                if (!e.enabled) continue;                                        // :388-390
+                if (e.es.pacing_kind != FW_PACING_COUNT_OVER_DURATION) continue; // :474-485 (warn_once! + skip)
+                Stream &parent = sp.streams[e.es.target_particle_type];
+                Stream &child = sp.streams[e.es.particle_index];
+                NestedCmd c{};
+                c.parent_stream = parent.slot;
+                c.child_stream = child.slot;
+                c.emitter_idx = e.dev_idx;
+                c.emitter_local = i;
+                c.spawner_key = sp.key;
+                c.lea_index = e.lea_index;
+                c.input_idx = need_input();
+                nested[my_phase].push_back(c);
+                continue;
+            }
             if (!e.enabled) continue; // :388-390
             uint64_t n = 0;
             if (e.es.pacing_kind == FW_PACING_ONE_SHOT) { // :397-400
@@ -879,61 +977,113 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
             if (n == 0) continue;
             Stream &st = sp.streams[e.es.particle_index];
             if (n > 0xFFFFFF00ull - st.n_hi) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "spawner %u would exceed 2^32 particles in one stream", sp.key);
-            if (input_idx < 0) {
-                input_idx = (int)sinputs.size();
-                sinputs.push_back(sp.input);
-            }
+            uint32_t &slot_spawn = spawn_per_slot[(size_t)phase * n_slots + st.slot];
             SpawnCmd c{};
             c.stream = st.slot;
             c.emitter_idx = e.dev_idx;
-            c.input_idx = (uint32_t)input_idx;
+            c.input_idx = need_input();
             c.count = (uint32_t)n;
-            c.first = (uint32_t)total_spawn;
-            c.dst_off = fs.spawn_per_slot[st.slot];
+            c.first = (uint32_t)phase_total[phase];
+            c.dst_off = slot_spawn;
             c.spawner_key = sp.key;
             c.emitter_local = i;
             c.serial_base = e.serial;
-            cmds.push_back(c);
+            cmds[phase].push_back(c);
             e.serial += n;
-            fs.spawn_per_slot[st.slot] += (uint32_t)n;
-            total_spawn += n;
-            if (total_spawn > 0xFFFFFF00ull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "more than 2^32 particles spawned in one frame");
+            slot_spawn += (uint32_t)n;
+            phase_total[phase] += n;
+            if (phase_total[phase] > 0xFFFFFF00ull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "more than 2^32 particles spawned in one frame");
         }
     }
-    // ---- capacity: grow a ring before it could overflow (bounds first, exact state on demand)
-    bool exact = false;
-    for (const SpawnCmd &c : cmds) {
-        Stream *st = ctx->slot_owner[c.stream];
-        const uint64_t need = st->n_hi + fs.spawn_per_slot[c.stream];
-        if (need <= st->block.capacity) continue;
-        if (!exact) {
-            int rc = refresh_exact(ctx);
-            if (rc) return rc;
-            exact = true;
+    // ---- capacity planning: a ring is grown before it could overflow. Global spawn counts are
+    // exact; what a Nested emitter will emit is only known on the device, so its child stream is
+    // charged an upper bound (parents x per-parent cap; the count kernel enforces the cap and
+    // raises an error flag if the reference would have emitted more). Bounds first, the exact
+    // device state only if a bound does not fit.
+    std::vector<uint64_t> add(std::max(1u, n_slots));
+    auto plan_bounds = [&]() {
+        std::fill(add.begin(), add.end(), 0);
+        uint64_t scratch = 0;
+        for (uint32_t p = 0; p < n_phases; p++) {
+            for (uint32_t s = 0; s < n_slots; s++) add[s] += spawn_per_slot[(size_t)p * n_slots + s];
+            for (NestedCmd &c : nested[p]) {
+                const Stream *parent = ctx->slot_owner[c.parent_stream];
+                const fw_emission_settings &es = ctx->h_emitters[c.emitter_idx];
+                const float life_min = std::fmin(parent->ps.lifetime.min, parent->ps.lifetime.max);
+                const double span = std::fmax((double)es.offset_end - (double)es.offset_start, 1e-9);
+                double per = life_min > 0.f ? std::floor((double)es.count * ((double)dt / life_min) / span) * 2.0 + 4.0
+                                            : std::ceil((double)es.count) + 4.0;
+                if (parent->injected) per = std::fmax(per, std::ceil((double)es.count) + 4.0);
+                per = std::fmin(std::fmax(per, 1.0), 1048576.0);
+                c.per_parent_cap = (uint32_t)per;
+                const uint64_t parents = std::min<uint64_t>(parent->n_hi + add[c.parent_stream], 0xFFFFFF00ull);
+                c.scratch_off = (uint32_t)scratch;
+                scratch += parents + 1;
+                add[c.child_stream] += parents * c.per_parent_cap;
+            }
         }
-        const uint64_t need2 = st->n_hi + fs.spawn_per_slot[c.stream];
-        if (need2 > st->block.capacity) {
-            int rc = grow_stream(ctx, *st, need2);
-            if (rc) return rc;
+        return scratch;
+    };
+    uint64_t scratch_need = plan_bounds();
+    auto any_overflow = [&]() {
+        for (uint32_t s = 0; s < n_slots; s++)
+            if (add[s] && ctx->slot_owner[s] && ctx->slot_owner[s]->n_hi + add[s] > ctx->slot_owner[s]->block.capacity) return true;
+        return false;
+    };
+    if (any_overflow()) {
+        int rc = refresh_exact(ctx);
+        if (rc) return rc;
+        scratch_need = plan_bounds();
+        for (uint32_t s = 0; s < n_slots; s++) {
+            Stream *st = ctx->slot_owner[s];
+            if (!st || !add[s]) continue;
+            const uint64_t need = st->n_hi + add[s];
+            if (need > 0xFFFFFF00ull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "a stream would exceed 2^32 particles");
+            if (need > st->block.capacity && (rc = grow_stream(ctx, *st, need))) return rc;
         }
+    }
+    if (scratch_need > 0xFFFFFF00ull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "nested emission scratch too large");
+    if (scratch_need > ctx->nested_scratch_cap) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_nested_scratch) CU(ctx, cudaFree(ctx->d_nested_scratch));
+        ctx->d_nested_scratch = nullptr;
+        ctx->nested_scratch_cap = scratch_need + scratch_need / 2 + 4096;
+        CU(ctx, cudaMalloc((void **)&ctx->d_nested_scratch, sizeof(uint32_t) * ctx->nested_scratch_cap));
+        topo_changed(ctx);
+    }
+    if (ctx->live_nested > ctx->nested_out_cap) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_nested_out) CU(ctx, cudaFree(ctx->d_nested_out));
+        ctx->d_nested_out = nullptr;
+        ctx->nested_out_cap = std::max(64u, ctx->live_nested * 2);
+        CU(ctx, cudaMalloc((void **)&ctx->d_nested_out, sizeof(NestedOut) * ctx->nested_out_cap));
+        topo_changed(ctx);
     }
     {
         int rc = ensure_tiles(ctx);
         if (rc) return rc;
     }
-    for (uint32_t s = 0; s < ctx->n_slots; s++)
-        if (fs.spawn_per_slot[s]) ctx->slot_owner[s]->n_hi += fs.spawn_per_slot[s];
+    fs.spawn_per_slot.assign(n_slots, 0u);
+    for (uint32_t s = 0; s < n_slots; s++)
+        if (add[s] && ctx->slot_owner[s]) {
+            ctx->slot_owner[s]->n_hi += add[s];
+            fs.spawn_per_slot[s] = (uint32_t)std::min<uint64_t>(add[s], 0xFFFFFFFFull);
+        }
+    for (uint32_t s = 0; s < n_slots; s++)
+        if (ctx->slot_owner[s]) ctx->slot_owner[s]->injected = false;
 
-    // ---- parameter block of the frame: header | spawn_per_slot | cmds | inputs. Its layout
-    // depends only on the topology (stream slots, emitters, spawners), so that a frame is a fixed
-    // sequence of nodes that can be replayed as one CUDA graph.
+    // ---- parameter block of the frame: header | spawn_per_slot[phase][slot] | cmds | inputs |
+    // nested cmds. Its layout depends only on the topology (stream slots, emitters, spawners,
+    // phases), so that a frame is a fixed sequence of nodes that can be replayed as one CUDA graph.
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t cmds_cap = std::max<size_t>(1, ctx->live_emitters);
     const size_t inputs_cap = std::max<size_t>(1, ctx->spawners.size());
+    const size_t nested_cap = std::max<size_t>(1, ctx->live_nested);
     const size_t off_spawn = align16(sizeof(FrameHeader));
-    const size_t off_cmds = align16(off_spawn + sizeof(uint32_t) * std::max(1u, ctx->n_slots));
+    const size_t off_cmds = align16(off_spawn + sizeof(uint32_t) * n_phases * std::max(1u, n_slots));
     const size_t off_inputs = align16(off_cmds + sizeof(SpawnCmd) * cmds_cap);
-    const size_t bytes = align16(off_inputs + sizeof(SpawnerInput) * inputs_cap);
+    const size_t off_nested = align16(off_inputs + sizeof(SpawnerInput) * inputs_cap);
+    const size_t bytes = align16(off_nested + sizeof(NestedCmd) * nested_cap);
     {
         int rc = ensure_frame_slot(ctx, fs, bytes);
         if (rc) return rc;
@@ -941,12 +1091,29 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     FrameHeader *h = (FrameHeader *)fs.host;
     memset(h, 0, sizeof(*h));
     h->dt = dt;
-    h->n_slots = ctx->n_slots;
-    h->n_cmds = (uint32_t)cmds.size();
-    h->total_spawn = (uint32_t)total_spawn;
+    h->n_slots = n_slots;
+    h->n_phases = n_phases;
     h->epoch = (uint32_t)((ctx->frame_no + 1) & 0x3FFFFFFFu);
-    if (ctx->n_slots) memcpy(fs.host + off_spawn, fs.spawn_per_slot.data(), sizeof(uint32_t) * ctx->n_slots);
-    if (!cmds.empty()) memcpy(fs.host + off_cmds, cmds.data(), sizeof(SpawnCmd) * cmds.size());
+    uint64_t total_spawn = 0;
+    {
+        SpawnCmd *hc = (SpawnCmd *)(fs.host + off_cmds);
+        NestedCmd *hn = (NestedCmd *)(fs.host + off_nested);
+        uint32_t nc = 0, nn = 0;
+        for (uint32_t p = 0; p < n_phases; p++) {
+            PhaseInfo &ph = h->phase[p];
+            ph.cmd_begin = nc;
+            for (const SpawnCmd &c : cmds[p]) hc[nc++] = c;
+            ph.cmd_end = nc;
+            ph.total_spawn = (uint32_t)phase_total[p];
+            ph.nested_begin = nn;
+            for (const NestedCmd &c : nested[p]) hn[nn++] = c;
+            ph.nested_end = nn;
+            total_spawn += phase_total[p];
+        }
+        h->n_cmds = nc;
+        h->n_nested = nn;
+    }
+    if (n_slots) memcpy(fs.host + off_spawn, spawn_per_slot.data(), sizeof(uint32_t) * n_phases * n_slots);
     if (!sinputs.empty()) memcpy(fs.host + off_inputs, sinputs.data(), sizeof(SpawnerInput) * sinputs.size());
 
     DeviceTables t{};
@@ -963,16 +1130,28 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     t.plan = ctx->d_plan;
     t.lookback = ctx->d_lookback;
     t.seed = ctx->seed;
+    t.nested_scratch = ctx->d_nested_scratch;
+    t.nested_serial = ctx->d_nested_serial;
+    t.nested_out = ctx->d_nested_out;
     FrameDeviceInputs f{};
     f.header = (const FrameHeader *)fs.dev;
     f.spawn_per_slot = (const uint32_t *)(fs.dev + off_spawn);
     f.cmds = (const SpawnCmd *)(fs.dev + off_cmds);
     f.inputs = (const SpawnerInput *)(fs.dev + off_inputs);
+    f.nested = (const NestedCmd *)(fs.dev + off_nested);
 
     const bool prof = ctx->profiling;
     uint32_t variant_mask = 0;
     for (uint32_t v = 0; v < kNumVariants; v++)
         if (ctx->variant_streams[v]) variant_mask |= 1u << v;
+    // nested emitters per phase is a property of the topology (enabled or not), so a replayed
+    // graph launches the nested kernels of every phase that could have commands
+    uint32_t nested_slots[kMaxPhases] = {0};
+    for (auto &spp : ctx->spawners) {
+        uint32_t p = 0;
+        for (const Emitter &e : spp->emitters)
+            if (e.emits_on_other_particles) nested_slots[p++]++;
+    }
     uint32_t launches = 0;
     // the device work of one frame; `replay` = being captured into a graph, so nothing may
     // depend on this particular frame's counts
@@ -980,11 +1159,27 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
         launches = 0;
         CU(ctx, cudaMemcpyAsync(fs.dev, fs.host, bytes, cudaMemcpyHostToDevice, ctx->stream));
         if (prof) CU(ctx, cudaEventRecord(fs.ev[0], ctx->stream));
-        CU(ctx, launch_plan(t, f, variant_mask, ctx->stream));
+        const bool single = n_phases == 1;
+        CU(ctx, launch_plan(t, f, variant_mask, kPlanDeaths | kPlanAppend | (single ? kPlanTiles : 0u), 0, ctx->stream));
         launches++;
         if (prof) CU(ctx, cudaEventRecord(fs.ev[1], ctx->stream));
-        if (replay || total_spawn) {
-            CU(ctx, launch_spawn(t, f, replay ? 0xFFFFFFFFu : (uint32_t)total_spawn, ctx->stream));
+        for (uint32_t p = 0; p < n_phases; p++) {
+            if (p > 0 && (replay || phase_total[p])) {
+                CU(ctx, launch_plan(t, f, variant_mask, kPlanAppend, p, ctx->stream));
+                launches++;
+            }
+            if (replay || phase_total[p]) {
+                CU(ctx, launch_spawn(t, f, p, replay ? 0xFFFFFFFFu : (uint32_t)phase_total[p], ctx->stream));
+                launches++;
+            }
+            const uint32_t nn = replay ? nested_slots[p] : (uint32_t)nested[p].size();
+            if (nn) {
+                CU(ctx, launch_nested(t, f, p, nn, ctx->stream));
+                launches += 3;
+            }
+        }
+        if (!single) {
+            CU(ctx, launch_plan(t, f, variant_mask, kPlanTiles, 0, ctx->stream));
             launches++;
         }
         if (prof) CU(ctx, cudaEventRecord(fs.ev[2], ctx->stream));
@@ -1139,7 +1334,7 @@ int fw_read_particles(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_
     if (!live) return FW_OK;
     if ((rc = ensure_stage(ctx, (size_t)live * sizeof(fw_particle_data)))) return rc;
     // pbr is a copy of the type's setting (src/core.rs:462)
-    CU(ctx, launch_gather_particles(block_desc(st.block, st.variant), first, live, st.ps.pbr, (fw_particle_data *)ctx->d_stage, ctx->stream));
+    CU(ctx, launch_gather_particles((uint8_t *)st.block.base, st.block.capacity, first, live, st.ps.pbr, (fw_particle_data *)ctx->d_stage, ctx->stream));
     CU(ctx, cudaMemcpyAsync(out, ctx->d_stage, (size_t)live * sizeof(fw_particle_data), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return FW_OK;
@@ -1160,6 +1355,21 @@ int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_pa
         if ((rc = grow_stream(ctx, st, n))) return rc;
         if ((rc = ensure_tiles(ctx))) return rc;
     }
+    // The FIFO variant relies on "deaths are a prefix of the Vec": every lifetime equals the
+    // type's constant lifetime and ages do not increase along the Vec. Host-written state that
+    // breaks this moves the stream to the compacting variant for good.
+    if (is_fifo(st.variant)) {
+        bool ok = true;
+        for (uint64_t i = 0; i < n && ok; i++)
+            ok = in[i].lifetime == st.ps.lifetime.min && (i == 0 || !(in[i].age > in[i - 1].age));
+        if (!ok) {
+            ctx->variant_streams[st.variant]--;
+            st.variant = st.variant == kFifoCollide ? kCompactCollide : kCompact;
+            ctx->variant_streams[st.variant]++;
+            topo_changed(ctx);
+            if ((rc = upload_desc(ctx, st))) return rc;
+        }
+    }
     if (n) {
         if ((rc = ensure_stage(ctx, (size_t)n * sizeof(fw_particle_data)))) return rc;
         CU(ctx, cudaMemcpyAsync(ctx->d_stage, in, (size_t)n * sizeof(fw_particle_data), cudaMemcpyHostToDevice, ctx->stream));
@@ -1172,6 +1382,7 @@ int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_pa
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     st.n_hi = n;
     st.born_frame = ctx->frame_no + 1;
+    st.injected = true;
     return FW_OK;
 }
 
@@ -1199,12 +1410,24 @@ int fw_read_instances(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_
     return FW_OK;
 }
 
-int fw_read_destroyed(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_data *, uint64_t, uint64_t *n) {
+int fw_read_destroyed(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_data *out, uint64_t cap, uint64_t *n) {
     ENTER(ctx);
     Spawner *sp = find(ctx, key);
     if (!sp || type >= sp->streams.size()) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_read_destroyed: unknown spawner %u / type %u", key, type);
+    const Stream &st = sp->streams[type];
     if (n) *n = 0;
-    return fail(ctx, FW_ERR_UNSUPPORTED, "fw_read_destroyed: the destroyed-particle stream is not implemented yet");
+    if (!st.destroyed.base) return FW_OK; // no handler registered: nothing is kept (src/core.rs:660-663)
+    int rc = refresh_exact(ctx);
+    if (rc) return rc;
+    const uint32_t dead = ctx->snapshot[st.slot].dead; // deaths of the last update, in Vec order
+    if (n) *n = dead;
+    if (dead > cap || (dead && !out)) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_read_destroyed: %u particles, room for %llu", dead, (unsigned long long)cap);
+    if (!dead) return FW_OK;
+    if ((rc = ensure_stage(ctx, (size_t)dead * sizeof(fw_particle_data)))) return rc;
+    CU(ctx, launch_gather_particles((uint8_t *)st.destroyed.base, st.destroyed.capacity, 0, dead, st.ps.pbr, (fw_particle_data *)ctx->d_stage, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out, ctx->d_stage, (size_t)dead * sizeof(fw_particle_data), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return FW_OK;
 }
 
 int fw_read_aabb(fw_context *ctx, uint32_t key, float out_min[3], float out_max[3], uint32_t *empty) {

@@ -80,11 +80,24 @@ struct alignas(16) DevParticleSettings {
 };
 static_assert(sizeof(DevParticleSettings) % 16 == 0, "bulk copy needs a 16-byte multiple");
 
+constexpr uint32_t kMaxLea = 4;    // nested emitters that may target one particle type
+constexpr uint32_t kMaxPhases = 8; // 1 + nested emitters per spawner
+
 struct StreamDesc { // written by the host when a stream is created / grown / removed
-    uint8_t *base;     // device block of capacity * kBytesPerSlot bytes, 256-byte aligned
-    uint32_t capacity; // multiple of 256; 0 = slot unused
+    uint8_t *base;           // device block of capacity * (100 + 4*n_lea) bytes, 256-byte aligned
+    uint8_t *destroyed_base; // same layout, holds the particles destroyed by the last update
+                             // (only for types with a particles_destroyed handler), else null
+    uint32_t capacity;       // multiple of 256; 0 = slot unused
     uint32_t variant;
+    uint32_t n_lea;          // last_emitted_age arrays (one per nested emitter targeting this type)
+    uint32_t pad;
 };
+// ParticleData.last_emitted_age[i] of reference src/core.rs:320, kept only for the emitters that
+// read it (nested emitters whose target is this particle type): float[capacity] each, behind
+// the eight packs
+__host__ __device__ inline float *lea_array(uint8_t *base, uint32_t cap, uint32_t j) {
+    return (float *)(base + (size_t)cap * (kBytesPerSlot + 4u * j));
+}
 
 // typed views of a stream block
 struct StreamArrays {
@@ -138,13 +151,44 @@ struct SpawnerInput {
     float modifier_speed;
 };
 
+// One nested emitter instance of a frame (reference src/core.rs:471-546)
+struct NestedCmd {
+    uint32_t parent_stream;  // particles[target_particle_type]
+    uint32_t child_stream;   // particles[particle_index]
+    uint32_t emitter_idx;    // device emission settings index; also indexes nested_serial
+    uint32_t emitter_local;  // RNG protocol
+    uint32_t spawner_key;    // RNG protocol
+    uint32_t lea_index;      // which last_emitted_age array of the parent stream
+    uint32_t input_idx;      // SpawnerInput of the spawner (EffectModifier)
+    uint32_t scratch_off;    // this command's per-parent counts inside nested_scratch
+    uint32_t per_parent_cap; // the host's capacity planning assumed at most this many per parent
+    uint32_t pad[3];
+};
+struct NestedOut { // device, per nested command of the frame
+    uint32_t total;      // children emitted
+    uint32_t spawn_base; // logical index of the first child in the child stream
+    uint64_t serial_base;
+};
+
+// The reference walks a spawner's emitters in order, and Global and Nested emitters may feed
+// the same particle type, so a frame is split into phases: phase p = the Global emitters that
+// sit between the (p-1)-th and the p-th Nested emitter of their spawner, followed by the p-th
+// Nested emitter of every spawner. Frames without nested emitters have exactly one phase.
+struct PhaseInfo {
+    uint32_t cmd_begin, cmd_end; // SpawnCmd range
+    uint32_t total_spawn;        // particles of the Global commands of the phase
+    uint32_t nested_begin, nested_end;
+    uint32_t pad[3];
+};
 struct FrameHeader {
     float dt;
     uint32_t n_slots; // stream slots to scan
     uint32_t n_cmds;
-    uint32_t total_spawn;
+    uint32_t n_phases;
     uint32_t epoch;
-    uint32_t pad[3];
+    uint32_t n_nested;
+    uint32_t pad[2];
+    PhaseInfo phase[kMaxPhases];
 };
 
 struct PlanOut { // device, written by the plan kernel
@@ -170,25 +214,37 @@ struct DeviceTables {
     PlanOut *plan;
     unsigned long long *lookback; // one status word per tile (compact variants)
     uint64_t seed;
+    // nested emission
+    uint32_t *nested_scratch;          // per-parent emission counts -> exclusive offsets
+    unsigned long long *nested_serial; // per device emitter: particles spawned so far
+    NestedOut *nested_out;             // per nested command of the frame
 };
 
 struct FrameDeviceInputs {
     const FrameHeader *header;
-    const uint32_t *spawn_per_slot;
+    const uint32_t *spawn_per_slot; // [n_phases][n_slots]
     const SpawnCmd *cmds;
     const SpawnerInput *inputs;
+    const NestedCmd *nested;
 };
 
 // launchers (fw_kernels.cu)
-cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant_mask, cudaStream_t s);
-cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t total_spawn, cudaStream_t s);
+// plan: what = bit 0 apply last frame's deaths, bit 1 append the Global spawns of `phase`,
+// bit 2 build the tile prefix tables
+constexpr uint32_t kPlanDeaths = 1u, kPlanAppend = 2u, kPlanTiles = 4u;
+cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant_mask, uint32_t what,
+                        uint32_t phase, cudaStream_t s);
+// total_spawn: particles of the phase, or 0xFFFFFFFF = unknown at launch time (graph replay)
+cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, cudaStream_t s);
+// the nested emitters of a phase: count per parent, scan + append, spawn the children
+cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t n_cmds, cudaStream_t s);
 cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, cudaStream_t s);
 cudaError_t update_grid_size(int device, int *grids /*[kNumVariants]*/);
 // live ParticleInstance rows of the streams [slot_begin, slot_end) -> contiguous 64-byte rows
 cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, float4 *dst,
                                   uint64_t cap_rows, unsigned long long *n_rows_and_offsets, cudaStream_t s);
 // one stream <-> fw_particle_data rows (host mirror / fw_write_particles)
-cudaError_t launch_gather_particles(const StreamDesc &d, uint32_t first, uint32_t n, uint32_t pbr,
+cudaError_t launch_gather_particles(uint8_t *base, uint32_t capacity, uint32_t first, uint32_t n, uint32_t pbr,
                                     fw_particle_data *dst, cudaStream_t s);
 cudaError_t launch_scatter_particles(const StreamDesc &d, uint32_t n, const fw_particle_data *src, cudaStream_t s);
 // ring -> linear copy into a bigger block (growth)

@@ -1,15 +1,16 @@
 // fw_kernels.cu -- sm_100a kernels of the particle path.
 //
-//   plan_kernel    applies last frame's deaths to every ring (head/count), appends this
-//                  frame's spawn counts, and builds the per-variant tile prefix table
-//   spawn_kernel   reference src/core.rs:437-469 + src/emission_shape.rs:18-39, one thread per
-//                  new particle, Philox4x32-10 counter-based draws
-//   update_kernel  reference src/core.rs:591-658 (+ :744-800 when COLLIDE), fused with death
-//                  handling (FIFO ring advance or in-place stable compaction) and the
-//                  per-stream AABB reduction (src/render.rs:677-703)
-//   pack kernels   assemble the 64-byte ParticleInstance rows (src/render.rs:95-115) of the
-//                  live particles into one contiguous buffer (render extract / all-gather)
-//   gather/scatter ParticleData rows of one stream <-> the SoA packs (host mirror)
+//   plan_kernel     applies last frame's deaths to every ring (head/count), appends a phase's
+//                   Global spawn counts, builds the per-variant tile prefix tables
+//   spawn_kernel    reference src/core.rs:437-469 + src/emission_shape.rs:18-39, one thread per
+//                   new particle, Philox4x32-10 counter-based draws
+//   nested_*        reference src/core.rs:471-546: per-parent emission counts, scan, children
+//   update_kernel   reference src/core.rs:591-658 (+ :744-800 when COLLIDE), fused with death
+//                   handling (FIFO ring advance or in-place stable compaction), the destroyed-
+//                   particle stream (:588,597,637) and the per-stream AABB (src/render.rs:677-703)
+//   pack kernels    assemble the 64-byte ParticleInstance rows (src/render.rs:95-115) of the
+//                   live particles into one contiguous buffer (render extract / all-gather)
+//   gather/scatter  ParticleData rows of one stream <-> the SoA packs (host mirror)
 //
 // Built with -fmad=false (see fw_math.cuh).
 #include <algorithm>
@@ -22,6 +23,9 @@
 // = 40 warps/SM at <= 48 registers, no spills. Measured on C3 (10 M particles): 4 CTAs/SM
 // 0.320 ms, 5 CTAs/SM 0.261 ms, 6 CTAs/SM (40 regs, spills) 0.275 ms.
 #define FW_MINB 5
+#endif
+#ifndef FW_MINB_COMPACT
+#define FW_MINB_COMPACT 4 // compaction also carries last_emitted_age / destroyed-capture state
 #endif
 #ifndef FW_MINB_COLLIDE
 #define FW_MINB_COLLIDE 3 // the collision variants are compute-bound and need ~80 registers
@@ -51,6 +55,7 @@ __device__ __forceinline__ void st_pack(T *p, T v) {
 
 __device__ __forceinline__ uint32_t wrap(uint32_t x, uint32_t cap) { return x >= cap ? x - cap : x; }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+constexpr float kF32Min = -3.402823466e+38f; // f32::MIN, initial last_emitted_age (src/core.rs:467)
 
 // ------------------------------------------------------------------------------------------
 // block-wide inclusive scan of one uint per thread (1024 threads max)
@@ -79,38 +84,46 @@ __device__ __forceinline__ uint32_t block_inclusive_scan(uint32_t v, uint32_t *w
     return r;
 }
 
-constexpr uint32_t kErrOverflow = 1u;
-constexpr uint32_t kErrLookback = 2u;
+constexpr uint32_t kErrOverflow = 1u;   // a ring was full: spawns were dropped
+constexpr uint32_t kErrLookback = 2u;   // look-back table too small
+constexpr uint32_t kErrNestedCap = 4u;  // a parent wanted to emit more than the planned bound
 
-__global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant_mask) {
+__global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant_mask,
+                                                    uint32_t what, uint32_t phase) {
     __shared__ uint32_t warp_sums[32];
     const uint32_t n_slots = f.header->n_slots;
     const uint32_t stride = t.slots_cap + 1u;
-    uint32_t my_total = 0;
-    for (uint32_t s = threadIdx.x; s < n_slots; s += blockDim.x) {
-        const StreamDesc d = t.descs[s];
-        if (d.capacity == 0u) continue;
-        StreamState st = t.states[s];
-        const bool fifo = (d.variant == kFifo || d.variant == kFifoCollide);
-        if (fifo) st.head = wrap(st.head + st.dead, d.capacity);
-        st.count -= st.dead;
-        st.dead = 0u;
-        uint32_t spawn = f.spawn_per_slot[s];
-        const uint32_t room = d.capacity - st.count;
-        if (spawn > room) {
-            st.overflow += spawn - room;
-            spawn = room;
-            atomicOr(&t.plan->error_flags, kErrOverflow);
+    if (what & (kPlanDeaths | kPlanAppend)) {
+        const uint32_t *spawn_per_slot = f.spawn_per_slot + (size_t)phase * n_slots;
+        for (uint32_t s = threadIdx.x; s < n_slots; s += blockDim.x) {
+            const StreamDesc d = t.descs[s];
+            if (d.capacity == 0u) continue;
+            StreamState st = t.states[s];
+            if (what & kPlanDeaths) {
+                const bool fifo = (d.variant == kFifo || d.variant == kFifoCollide);
+                if (fifo) st.head = wrap(st.head + st.dead, d.capacity);
+                st.count -= st.dead;
+                st.dead = 0u;
+                st.aabb_min[0] = st.aabb_min[1] = st.aabb_min[2] = 0xFFFFFFFFu;
+                st.aabb_max[0] = st.aabb_max[1] = st.aabb_max[2] = 0u;
+            }
+            if (what & kPlanAppend) {
+                uint32_t spawn = spawn_per_slot[s];
+                const uint32_t room = d.capacity - st.count;
+                if (spawn > room) {
+                    st.overflow += spawn - room;
+                    spawn = room;
+                    atomicOr(&t.plan->error_flags, kErrOverflow);
+                }
+                st.spawn_base = st.count;
+                st.count += spawn;
+            }
+            t.states[s] = st;
         }
-        st.spawn_base = st.count;
-        st.count += spawn;
-        st.aabb_min[0] = st.aabb_min[1] = st.aabb_min[2] = 0xFFFFFFFFu;
-        st.aabb_max[0] = st.aabb_max[1] = st.aabb_max[2] = 0u;
-        t.states[s] = st;
-        my_total += st.count;
+        __syncthreads();
     }
-    __syncthreads();
-    uint32_t base_total = 0;
+    if (!(what & kPlanTiles)) return;
+    uint32_t base_total = 0, my_total = 0;
     for (uint32_t v = 0; v < kNumVariants; v++) {
         uint32_t carry = 0;
         if (variant_mask & (1u << v)) {
@@ -120,7 +133,11 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
                 uint32_t tiles = 0;
                 if (s < n_slots) {
                     const StreamDesc d = t.descs[s];
-                    if (d.capacity != 0u && d.variant == v) tiles = (t.states[s].count + kTile - 1u) / kTile;
+                    if (d.capacity != 0u && d.variant == v) {
+                        const uint32_t n = t.states[s].count;
+                        tiles = (n + kTile - 1u) / kTile;
+                        my_total += n;
+                    }
                 }
                 uint32_t total;
                 const uint32_t incl = block_inclusive_scan(tiles, warp_sums, total);
@@ -145,40 +162,18 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
 }
 
 // ------------------------------------------------------------------------------------------
-// spawn: one thread per new particle (g = index of the particle among this frame's spawns)
-__device__ __forceinline__ uint32_t find_cmd(const FrameDeviceInputs &f, uint32_t g) {
-    // last c with cmds[c].first <= g
-    uint32_t lo = 0, hi = f.header->n_cmds;
-    while (hi - lo > 1u) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (f.cmds[mid].first <= g) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-__device__ __forceinline__ void spawn_one(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t g, uint32_t c_hint) {
-    // command of this particle: the CTA's first particle belongs to c_hint; walk forward
-    uint32_t lo = c_hint;
-    const uint32_t n_cmds = f.header->n_cmds;
-    while (lo + 1u < n_cmds && f.cmds[lo + 1u].first <= g) lo++;
-    const SpawnCmd cmd = f.cmds[lo];
-    const uint32_t j = g - cmd.first;
-    const StreamDesc d = t.descs[cmd.stream];
-    const StreamState st = t.states[cmd.stream];
-    const uint32_t logical = st.spawn_base + cmd.dst_off + j;
-    if (logical >= st.count) return; // dropped by the overflow clamp of the plan kernel
-    const uint32_t slot = wrap(st.head + logical, d.capacity);
-
-    const fw_emission_settings &es = t.emitters[cmd.emitter_idx];
-    const DevParticleSettings &ps = t.settings[cmd.stream];
-    const SpawnerInput in = f.inputs[cmd.input_idx];
-
-    // draws 0..11 in the reference's draw order (src/core.rs:438-466)
-    const uint64_t serial = cmd.serial_base + j;
+// One new particle: the shared body of reference src/core.rs:437-469 (Global: origin = the
+// spawner transform, inherited velocity = parent_velocity) and :506-544 (Nested: origin = the
+// parent particle). Draws 0..11 in the reference's draw order.
+__device__ __forceinline__ void emit_particle(const DeviceTables &t, const fw_emission_settings &es, const DevParticleSettings &ps,
+                                              const StreamDesc &d, uint32_t slot, V3 origin_translation, Q4 origin_rotation,
+                                              V3 inherited_velocity, float modifier_scale, float modifier_speed,
+                                              uint32_t spawner_key, uint32_t emitter_local, uint64_t serial) {
     const uint2 key = make_uint2((uint32_t)t.seed, (uint32_t)(t.seed >> 32));
-    const uint32_t c0 = (uint32_t)serial, c1 = (uint32_t)(serial >> 32), c2 = cmd.spawner_key;
-    const uint4 r0 = philox4x32_10(make_uint4(c0, c1, c2, (cmd.emitter_local << 8) | 0u), key);
-    const uint4 r1 = philox4x32_10(make_uint4(c0, c1, c2, (cmd.emitter_local << 8) | 1u), key);
-    const uint4 r2 = philox4x32_10(make_uint4(c0, c1, c2, (cmd.emitter_local << 8) | 2u), key);
+    const uint32_t c0 = (uint32_t)serial, c1 = (uint32_t)(serial >> 32), c2 = spawner_key;
+    const uint4 r0 = philox4x32_10(make_uint4(c0, c1, c2, (emitter_local << 8) | 0u), key);
+    const uint4 r1 = philox4x32_10(make_uint4(c0, c1, c2, (emitter_local << 8) | 1u), key);
+    const uint4 r2 = philox4x32_10(make_uint4(c0, c1, c2, (emitter_local << 8) | 2u), key);
     const float u_shape0 = u01(r0.x), u_shape1 = u01(r0.y), u_shape2 = u01(r0.z);
     const float u_vel_angle = u01(r0.w), u_vel_radius = u01(r1.x), u_vel_mag = u01(r1.y);
     const float u_radial = u01(r1.z), u_scale = u01(r1.w), u_life = u01(r2.x);
@@ -214,13 +209,11 @@ __device__ __forceinline__ void spawn_one(const DeviceTables &t, const FrameDevi
     };
     const V3 iv = rand_vec3(es.initial_velocity, u_vel_angle, u_vel_radius, u_vel_mag);
     const float radial = u_radial * (es.initial_velocity_radial.max - es.initial_velocity_radial.min) + es.initial_velocity_radial.min;
-    const Q4 orot{in.rotation[0], in.rotation[1], in.rotation[2], in.rotation[3]};
-    // src/core.rs:440-448
-    V3 velocity = (qrot(orot, iv) + normalize_or_zero(spawn_offset) * radial) * in.modifier_speed;
-    const V3 inherit = es.inherit_parent_velocity ? v3(in.parent_velocity[0], in.parent_velocity[1], in.parent_velocity[2]) : v3(0.0f, 0.0f, 0.0f);
-    velocity = velocity + inherit;
-    const float initial_scale = (u_scale * (ps.initial_scale.max - ps.initial_scale.min) + ps.initial_scale.min) * in.modifier_scale;
-    const V3 position = v3(in.translation[0], in.translation[1], in.translation[2]) + spawn_offset;
+    // src/core.rs:440-448 / :509-518
+    V3 velocity = (qrot(origin_rotation, iv) + normalize_or_zero(spawn_offset) * radial) * modifier_speed;
+    velocity = velocity + (es.inherit_parent_velocity ? inherited_velocity : v3(0.0f, 0.0f, 0.0f));
+    const float initial_scale = (u_scale * (ps.initial_scale.max - ps.initial_scale.min) + ps.initial_scale.min) * modifier_scale;
+    const V3 position = origin_translation + spawn_offset;
     const float lifetime = u_life * (ps.lifetime.max - ps.lifetime.min) + ps.lifetime.min;
     const V3 av = rand_vec3(es.initial_angular_velocity, u_ang_angle, u_ang_radius, u_ang_mag);
 
@@ -232,20 +225,154 @@ __device__ __forceinline__ void spawn_one(const DeviceTables &t, const FrameDevi
     a.k[slot] = make_float2(lifetime, initial_scale);
     a.o0[slot] = sample_gradient(ps.base_color, 0.0f);     // :460
     a.o1[slot] = sample_gradient(ps.emissive_color, 0.0f); // :461
-    a.o2[slot] = initial_scale;                            // scale: initial_scale (:457)
+    a.o2[slot] = initial_scale;                            // scale = initial_scale (:457)
+    for (uint32_t j = 0; j < d.n_lea; j++) lea_array(d.base, d.capacity, j)[slot] = kF32Min; // :467
+}
+
+// spawn (Global emitters): one thread per new particle of the phase
+__device__ __forceinline__ uint32_t find_cmd(const FrameDeviceInputs &f, uint32_t begin, uint32_t end, uint32_t g) {
+    uint32_t lo = begin, hi = end; // last c with cmds[c].first <= g
+    while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (f.cmds[mid].first <= g) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 // grid-stride so the launch configuration is frame-independent (CUDA-graph friendly): the
 // number of new particles is read from the frame header on the device
-__global__ void __launch_bounds__(256) spawn_kernel(DeviceTables t, FrameDeviceInputs f) {
+__global__ void __launch_bounds__(256) spawn_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t phase) {
     __shared__ uint32_t s_cmd;
-    const uint32_t total = f.header->total_spawn;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const PhaseInfo ph = f.header->phase[phase];
+    for (uint32_t base = blockIdx.x * blockDim.x; base < ph.total_spawn; base += gridDim.x * blockDim.x) {
         // one binary search per CTA chunk (a chunk of 256 particles spans very few commands)
-        if (threadIdx.x == 0) s_cmd = find_cmd(f, base);
+        if (threadIdx.x == 0) s_cmd = find_cmd(f, ph.cmd_begin, ph.cmd_end, base);
         __syncthreads();
         const uint32_t g = base + threadIdx.x;
-        if (g < total) spawn_one(t, f, g, s_cmd);
+        if (g < ph.total_spawn) {
+            uint32_t c = s_cmd;
+            while (c + 1u < ph.cmd_end && f.cmds[c + 1u].first <= g) c++;
+            const SpawnCmd cmd = f.cmds[c];
+            const StreamDesc d = t.descs[cmd.stream];
+            const StreamState st = t.states[cmd.stream];
+            const uint32_t logical = st.spawn_base + cmd.dst_off + (g - cmd.first);
+            if (logical < st.count) { // else dropped by the overflow clamp of the plan kernel
+                const SpawnerInput in = f.inputs[cmd.input_idx];
+                emit_particle(t, t.emitters[cmd.emitter_idx], t.settings[cmd.stream], d, wrap(st.head + logical, d.capacity),
+                              v3(in.translation[0], in.translation[1], in.translation[2]),
+                              Q4{in.rotation[0], in.rotation[1], in.rotation[2], in.rotation[3]},
+                              v3(in.parent_velocity[0], in.parent_velocity[1], in.parent_velocity[2]), in.modifier_scale,
+                              in.modifier_speed, cmd.spawner_key, cmd.emitter_local, cmd.serial_base + (g - cmd.first));
+            }
+        }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Nested emission, reference src/core.rs:471-546.
+__device__ __forceinline__ float div_euclid_f32(float a, float b) { // core::f32::div_euclid
+    const float q = truncf(a / b);
+    if (fmodf(a, b) < 0.0f) return b > 0.0f ? q - 1.0f : q + 1.0f;
+    return q;
+}
+// step 1: compute_emission_count (:553-575) for every parent particle (:490-500)
+__global__ void __launch_bounds__(256) nested_count_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t phase) {
+    const PhaseInfo ph = f.header->phase[phase];
+    const uint32_t ci = ph.nested_begin + blockIdx.y;
+    if (ci >= ph.nested_end) return;
+    const NestedCmd cmd = f.nested[ci];
+    const fw_emission_settings &es = t.emitters[cmd.emitter_idx];
+    const StreamDesc d = t.descs[cmd.parent_stream];
+    const StreamState st = t.states[cmd.parent_stream];
+    const StreamArrays a = stream_arrays(d.base, d.capacity);
+    float *lea = lea_array(d.base, d.capacity, cmd.lea_index);
+    uint32_t *counts = t.nested_scratch + cmd.scratch_off;
+    const float start = es.offset_start, end = es.offset_end, per_cycle = es.count;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < st.count; j += gridDim.x * blockDim.x) {
+        const uint32_t slot = wrap(st.head + j, d.capacity);
+        const float age = a.m0[slot].w, lifetime = a.k[slot].x, last = lea[slot];
+        const float percent_passed = age / lifetime;
+        const float last_emission_percent = last / lifetime;
+        const float lo = fmaxf(last_emission_percent, start);
+        const float percent_passed_since_emission = fminf(percent_passed, end) - lo;
+        const float percent_between_emissions = (end - start) / per_cycle;
+        const float times = div_euclid_f32(percent_passed_since_emission, percent_between_emissions);
+        uint32_t n = 0; // `as usize`: NaN / negatives -> 0, saturating
+        if (times > 0.0f) n = times >= 4294967040.0f ? 0xFFFFFFFFu : (uint32_t)times;
+        if (n > cmd.per_parent_cap) {
+            n = cmd.per_parent_cap;
+            atomicOr(&t.plan->error_flags, kErrNestedCap);
+        }
+        lea[slot] = (lo + times * percent_between_emissions) * lifetime; // :500
+        counts[j] = n;
+    }
+}
+// step 2: exclusive scan of the per-parent counts (parents emit in Vec order), then append the
+// children to the child stream and reserve their serial numbers. One CTA per command.
+__global__ void __launch_bounds__(1024) nested_scan_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t phase) {
+    __shared__ uint32_t warp_sums[32];
+    const PhaseInfo ph = f.header->phase[phase];
+    const uint32_t ci = ph.nested_begin + blockIdx.x;
+    if (ci >= ph.nested_end) return;
+    const NestedCmd cmd = f.nested[ci];
+    const uint32_t n_parents = t.states[cmd.parent_stream].count;
+    uint32_t *counts = t.nested_scratch + cmd.scratch_off;
+    uint32_t carry = 0;
+    for (uint32_t chunk = 0; chunk < n_parents; chunk += blockDim.x) {
+        const uint32_t j = chunk + threadIdx.x;
+        const uint32_t v = j < n_parents ? counts[j] : 0u;
+        uint32_t total;
+        const uint32_t incl = block_inclusive_scan(v, warp_sums, total);
+        if (j < n_parents) counts[j] = carry + incl - v;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        const StreamDesc cd = t.descs[cmd.child_stream];
+        StreamState *cs = &t.states[cmd.child_stream];
+        uint32_t total = carry;
+        const uint32_t room = cd.capacity - cs->count;
+        if (total > room) {
+            cs->overflow += total - room;
+            total = room;
+            atomicOr(&t.plan->error_flags, kErrOverflow);
+        }
+        NestedOut o;
+        o.total = total;
+        o.spawn_base = cs->count;
+        o.serial_base = t.nested_serial[cmd.emitter_idx];
+        t.nested_out[ci] = o;
+        cs->spawn_base = cs->count;
+        cs->count += total;
+        t.nested_serial[cmd.emitter_idx] = o.serial_base + carry;
+    }
+}
+// step 3: the children (:506-544): origin = the parent particle's position / rotation / velocity
+__global__ void __launch_bounds__(256) nested_spawn_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t phase) {
+    const PhaseInfo ph = f.header->phase[phase];
+    const uint32_t ci = ph.nested_begin + blockIdx.y;
+    if (ci >= ph.nested_end) return;
+    const NestedCmd cmd = f.nested[ci];
+    const NestedOut out = t.nested_out[ci];
+    if (out.total == 0u) return;
+    const StreamDesc pd = t.descs[cmd.parent_stream], cd = t.descs[cmd.child_stream];
+    const StreamState pst = t.states[cmd.parent_stream], cst = t.states[cmd.child_stream];
+    // when parent and child are the same stream the parents are the first n_parents particles
+    const uint32_t n_parents = cmd.parent_stream == cmd.child_stream ? out.spawn_base : pst.count;
+    const uint32_t *offsets = t.nested_scratch + cmd.scratch_off;
+    const StreamArrays pa = stream_arrays(pd.base, pd.capacity);
+    const SpawnerInput in = f.inputs[cmd.input_idx];
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < out.total; g += gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = n_parents; // parent: last j with offsets[j] <= g
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (offsets[mid] <= g) lo = mid; else hi = mid;
+        }
+        const uint32_t pslot = wrap(pst.head + lo, pd.capacity);
+        const float4 p0 = pa.m0[pslot], p1 = pa.m1[pslot], p2 = pa.m2[pslot];
+        emit_particle(t, t.emitters[cmd.emitter_idx], t.settings[cmd.child_stream], cd,
+                      wrap(cst.head + out.spawn_base + g, cd.capacity), v3(p0.x, p0.y, p0.z), Q4{p1.x, p1.y, p1.z, p1.w},
+                      v3(p2.x, p2.y, p2.z), in.modifier_scale, in.modifier_speed, cmd.spawner_key, cmd.emitter_local,
+                      out.serial_base + g);
     }
 }
 
@@ -314,7 +441,8 @@ struct alignas(16) UpdateSmem {
 // CTA of the grid is resident). Thread 0 looks up the next tile's stream and prefetches its
 // settings block with a bulk async copy while the CTA works on the current tile.
 template <bool COMPACT, bool COLLIDE>
-__global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : FW_MINB) update_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant) {
+__global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (COMPACT ? FW_MINB_COMPACT : FW_MINB))
+    update_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant) {
     __shared__ UpdateSmem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t n_tiles = t.plan->n_tiles[variant];
@@ -356,6 +484,11 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : FW
             M3 = ld_pack(a.m3 + slot);
             K = ld_pack(a.k + slot);
         }
+        float lea_v[kMaxLea]; // last_emitted_age moves with the particle when compacting
+        if (COMPACT) {
+#pragma unroll
+            for (uint32_t j = 0; j < kMaxLea; j++) lea_v[j] = (valid && j < d.n_lea) ? lea_array(d.base, d.capacity, j)[slot] : 0.f;
+        }
         // next tile: stream lookup + settings prefetch into the other buffer (every thread left
         // that buffer at the __syncthreads closing the previous iteration)
         if (tid == 0 && tile + gridDim.x < n_tiles) {
@@ -372,6 +505,7 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : FW
         bool alive = valid && !(age >= lifetime); // :596-599
         float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
         float scale = 0.f;
+        bool destroyed_by_collision = false;
         if (alive) {
             const float age_percent = age / lifetime;                       // :601
             scale = iscale * sample_curve(ps.scale_curve, age_percent);     // :602-605
@@ -383,7 +517,10 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : FW
                 pos = pos + vel * dt;                                       // :619-623
             }
             if (should_destroy) {
-                alive = false;                                              // :636-639
+                alive = false;                                              // :636-639: position,
+                destroyed_by_collision = true;                              // velocity, scale are
+                M0 = make_float4(pos.x, pos.y, pos.z, age);                 // already updated
+                M2 = make_float4(vel.x, vel.y, vel.z, M2.w);
             } else {
                 const V3 acc = v3(ps.acceleration[0], ps.acceleration[1], ps.acceleration[2]);
                 vel = vel + (acc - vel * ps.linear_drag) * dt;              // :641-643
@@ -397,6 +534,18 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : FW
                 M1 = make_float4(rot.x, rot.y, rot.z, rot.w);
                 M2 = make_float4(vel.x, vel.y, vel.z, av.x);
                 M3 = make_float2(av.y, av.z);
+            }
+        }
+        // destroyed-particle stream (:588,597,637): the record the handler receives keeps the old
+        // colours (and the old scale unless a collision destroyed it); read them before this
+        // tile publishes anything, i.e. before later tiles may compact over these slots
+        const bool capture = COMPACT && d.destroyed_base != nullptr && valid && !alive;
+        if (capture) {
+            c0 = a.o0[slot];
+            c1 = a.o1[slot];
+            if (!destroyed_by_collision) {
+                scale = a.o2[slot];
+                M0.w = age; // age is bumped before the lifetime test (:594-598)
             }
         }
         const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
@@ -461,20 +610,37 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : FW
                 if (tile_first + kTile >= n_update) stp->dead = excl + tile_dead; // last tile of the stream
             }
             __syncthreads();
-            const uint32_t rank = before + __popc(alive_mask & ((1u << lane) - 1u));
-            dslot = wrap(head + tile_first - sm.excl_dead + rank, d.capacity);
+            const uint32_t alive_before = before + __popc(alive_mask & ((1u << lane) - 1u));
+            dslot = wrap(head + tile_first - sm.excl_dead + alive_before, d.capacity);
+            if (capture) { // destroyed particles, in Vec order, into the side block
+                const uint32_t di = sm.excl_dead + (tid - alive_before);
+                const StreamArrays b = stream_arrays(d.destroyed_base, d.capacity);
+                b.m0[di] = M0;
+                b.m1[di] = M1;
+                b.m2[di] = M2;
+                b.m3[di] = M3;
+                b.k[di] = K;
+                b.o0[di] = c0;
+                b.o1[di] = c1;
+                b.o2[di] = scale;
+            }
         } else {
             const uint32_t n_dead_w = __popc(valid_mask & ~alive_mask);
             if (lane == 0 && n_dead_w) atomicAdd(&stp->dead, n_dead_w);
         }
 
-        // ---- stores: 92 B per survivor (100 B when a compacting stream moves its constants)
+        // ---- stores: 92 B per survivor (more when a compacting stream moves its constants)
         if (alive) {
             st_pack(a.m0 + dslot, M0);
             st_pack(a.m1 + dslot, M1);
             st_pack(a.m2 + dslot, M2);
             st_pack(a.m3 + dslot, M3);
-            if (COMPACT) st_pack(a.k + dslot, K);
+            if (COMPACT) {
+                st_pack(a.k + dslot, K);
+#pragma unroll
+                for (uint32_t j = 0; j < kMaxLea; j++)
+                    if (j < d.n_lea) lea_array(d.base, d.capacity, j)[dslot] = lea_v[j];
+            }
             st_pack(a.o0 + dslot, c0);
             st_pack(a.o1 + dslot, c1);
             st_pack(a.o2 + dslot, scale);
@@ -528,12 +694,13 @@ __global__ void __launch_bounds__(256) pack_copy_kernel(DeviceTables t, uint32_t
     }
 }
 
-// ParticleData rows of one stream (host mirror, tests)
-__global__ void __launch_bounds__(256) gather_particles_kernel(StreamDesc d, uint32_t first, uint32_t n, uint32_t pbr, fw_particle_data *dst) {
+// ParticleData rows of one block (host mirror, destroyed stream, tests)
+__global__ void __launch_bounds__(256) gather_particles_kernel(uint8_t *base, uint32_t capacity, uint32_t first, uint32_t n,
+                                                               uint32_t pbr, fw_particle_data *dst) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const StreamArrays a = stream_arrays(d.base, d.capacity);
-    const uint32_t slot = wrap(first + i, d.capacity);
+    const StreamArrays a = stream_arrays(base, capacity);
+    const uint32_t slot = wrap(first + i, capacity);
     const float4 m0 = a.m0[slot], m1 = a.m1[slot], m2 = a.m2[slot], o0 = a.o0[slot], o1 = a.o1[slot];
     const float2 m3 = a.m3[slot], k = a.k[slot];
     fw_particle_data p;
@@ -563,6 +730,7 @@ __global__ void __launch_bounds__(256) scatter_particles_kernel(StreamDesc d, ui
     a.o0[i] = make_float4(p.base_color[0], p.base_color[1], p.base_color[2], p.base_color[3]);
     a.o1[i] = make_float4(p.emissive_color[0], p.emissive_color[1], p.emissive_color[2], p.emissive_color[3]);
     a.o2[i] = p.scale;
+    for (uint32_t j = 0; j < d.n_lea; j++) lea_array(d.base, d.capacity, j)[i] = kF32Min;
 }
 __global__ void __launch_bounds__(256) ring_copy_kernel(StreamDesc src, uint32_t first, uint32_t n, StreamDesc dst) {
     const StreamArrays a = stream_arrays(src.base, src.capacity), b = stream_arrays(dst.base, dst.capacity);
@@ -576,21 +744,29 @@ __global__ void __launch_bounds__(256) ring_copy_kernel(StreamDesc src, uint32_t
         b.o0[i] = a.o0[s];
         b.o1[i] = a.o1[s];
         b.o2[i] = a.o2[s];
+        for (uint32_t j = 0; j < src.n_lea; j++) lea_array(dst.base, dst.capacity, j)[i] = lea_array(src.base, src.capacity, j)[s];
     }
 }
 
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant_mask, cudaStream_t s) {
-    plan_kernel<<<1, 1024, 0, s>>>(t, f, variant_mask);
+cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant_mask, uint32_t what, uint32_t phase, cudaStream_t s) {
+    plan_kernel<<<1, 1024, 0, s>>>(t, f, variant_mask, what, phase);
     return cudaGetLastError();
 }
-cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t total_spawn, cudaStream_t s) {
-    // total_spawn == 0xFFFFFFFF: "unknown at launch time" (graph replay): a fixed grid that
-    // covers any count by striding; otherwise just enough CTAs
+cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, cudaStream_t s) {
     if (total_spawn == 0) return cudaSuccess;
     const uint32_t fixed = 148u * 8u;
     const uint32_t blocks = total_spawn == 0xFFFFFFFFu ? fixed : std::min(fixed, (total_spawn + 255u) / 256u);
-    spawn_kernel<<<blocks, 256, 0, s>>>(t, f);
+    spawn_kernel<<<blocks, 256, 0, s>>>(t, f, phase);
+    return cudaGetLastError();
+}
+cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t n_cmds, cudaStream_t s) {
+    if (n_cmds == 0) return cudaSuccess;
+    if (n_cmds > 65535u) return cudaErrorInvalidValue;
+    const uint32_t gx = std::max(1u, std::min(148u * 4u, (148u * 8u) / n_cmds));
+    nested_count_kernel<<<dim3(gx, n_cmds), 256, 0, s>>>(t, f, phase);
+    nested_scan_kernel<<<n_cmds, 1024, 0, s>>>(t, f, phase);
+    nested_spawn_kernel<<<dim3(gx, n_cmds), 256, 0, s>>>(t, f, phase);
     return cudaGetLastError();
 }
 cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, cudaStream_t s) {
@@ -633,9 +809,10 @@ cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, ui
     }
     return cudaGetLastError();
 }
-cudaError_t launch_gather_particles(const StreamDesc &d, uint32_t first, uint32_t n, uint32_t pbr, fw_particle_data *dst, cudaStream_t s) {
+cudaError_t launch_gather_particles(uint8_t *base, uint32_t capacity, uint32_t first, uint32_t n, uint32_t pbr,
+                                    fw_particle_data *dst, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    gather_particles_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(d, first, n, pbr, dst);
+    gather_particles_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(base, capacity, first, n, pbr, dst);
     return cudaGetLastError();
 }
 cudaError_t launch_scatter_particles(const StreamDesc &d, uint32_t n, const fw_particle_data *src, cudaStream_t s) {

@@ -204,6 +204,16 @@ class App:
                                       mod.scale, mod.speed, e.data.manual_queued_count))
             e.data.manual_queued_count = 0
         eng.frame(dt, inputs)
+        # particles_destroyed handlers (src/core.rs:660-667): called with the non-empty destroyed Vec
+        for eid, e in list(self._entities.items()):
+            if e.spawner is None:
+                continue
+            for t, ps in enumerate(e.spawner.particle_settings):
+                handler = ps.event_handlers.particles_destroyed
+                if handler is not None:
+                    rows = eng.read_destroyed(eid, t)
+                    if len(rows):
+                        handler(rows)
         # notify_finished_particle_spawners (src/core.rs:674-688); only one-shot style spawners
         # can finish, so the status is only read back for entities that have observers
         for eid, e in list(self._entities.items()):
