@@ -96,3 +96,10 @@ def test_product_does_not_reference_oracle():
                 assert "fwo_" not in text and "fw_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
     out = subprocess.check_output(["nm", "-D", LIB_PATH], text=True)
     assert "fwo_" not in out
+
+
+def test_header_is_plain_c_and_cpp_host_compiles(tmp_path):
+    """include/firework_b200.h compiles as C99; the C++ host mirror compiles against it."""
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", HEADER])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
+                           os.path.join(ROOT, "host", "examples", "sparks.cpp")])
