@@ -170,6 +170,16 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def ncu_traffic(workload: str):
+    """per-launch DRAM traffic of the dominant kernel from the committed ncu capture (or None)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)[workload]
+        return t["dram_bytes_read"] + t["dram_bytes_write"], t["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -362,7 +372,9 @@ def main():
                     "what": "fw_frame with host input structs + fw_counts_all/fw_read_aabb (sync + D2H) every step"},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "fw::update_kernel<false,false>",
+                         "traffic": ncu_traffic(args.workload)[0], "traffic_source": ncu_traffic(args.workload)[1],
+                         "kernel": "fw::update_kernel<false,false>",
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE * per_launch_particles,
                          "algorithmic_bytes_per_particle": ALGO_BYTES_PER_PARTICLE,
                          "particles_per_launch": per_launch_particles, "kernel_ms": upd_kernel_ms,
                          "peak_source": peak_src,
