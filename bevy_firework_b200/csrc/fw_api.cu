@@ -35,7 +35,7 @@ struct Emitter {
     bool enabled = true;
     bool emits_on_other_particles = false;
     uint64_t serial = 0;   // particles spawned since reset (RNG protocol; Global emitters)
-    uint32_t dev_idx = 0;  // index into the device emitter array (and nested_serial)
+    uint32_t dev_idx = 0xFFFFFFFFu; // index into the device emitter array (and nested_serial); ~0 = none yet
     uint32_t lea_index = 0; // Nested: which last_emitted_age array of the target stream
 };
 
@@ -163,6 +163,7 @@ struct fw_context {
     bool profiling = false; // timed frames are launched kernel by kernel (events inside a graph do not time)
     // last exact state snapshot (valid after refresh_exact)
     std::vector<StreamState> snapshot;
+    bool snapshot_valid = false; // no device work was enqueued since `snapshot` was read
 };
 
 namespace {
@@ -179,6 +180,7 @@ int fail(fw_context *ctx, int code, const char *fmt, ...) {
 }
 
 inline void topo_changed(fw_context *ctx) {
+    ctx->snapshot_valid = false;
     ctx->topo_version++;
     ctx->topo_stable_frames = 0;
 }
@@ -412,6 +414,7 @@ uint64_t estimate_capacity(const Spawner &sp, uint32_t type) {
 }
 
 void free_stream(fw_context *ctx, Stream &st) {
+    if (!st.block.base) return; // never got a slot / block (failed reset)
     ctx->tiles_needed -= (st.block.capacity + kTile - 1) / kTile;
     ctx->variant_streams[st.variant]--;
     release_block(ctx, st.block);
@@ -426,7 +429,8 @@ void free_spawner_resources(fw_context *ctx, Spawner &sp) {
     topo_changed(ctx);
     ctx->live_emitters -= (uint32_t)sp.emitters.size();
     for (Stream &st : sp.streams) free_stream(ctx, st);
-    for (Emitter &e : sp.emitters) ctx->free_emitters.push_back(e.dev_idx);
+    for (Emitter &e : sp.emitters)
+        if (e.dev_idx != 0xFFFFFFFFu) ctx->free_emitters.push_back(e.dev_idx);
     sp.streams.clear();
     sp.emitters.clear();
 }
@@ -440,6 +444,9 @@ int upload_desc(fw_context *ctx, const Stream &st) {
 
 // wait for everything, read all stream states, make n_hi exact
 int refresh_exact(fw_context *ctx) {
+    // nothing was submitted since the last exact snapshot: it is still exact (lets a host loop
+    // call fw_counts / fw_read_aabb per spawner without a sync + copy each time)
+    if (ctx->snapshot_valid && ctx->snapshot.size() == ctx->n_slots) return FW_OK;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (FrameSlot &fs : ctx->ring) fs.in_flight = false;
     ctx->snapshot.resize(ctx->n_slots);
@@ -447,6 +454,7 @@ int refresh_exact(fw_context *ctx) {
         CU(ctx, cudaMemcpy(ctx->snapshot.data(), ctx->d_states, sizeof(StreamState) * ctx->n_slots, cudaMemcpyDeviceToHost));
     for (uint32_t s = 0; s < ctx->n_slots; s++)
         if (Stream *st = ctx->slot_owner[s]) st->n_hi = ctx->snapshot[s].count - ctx->snapshot[s].dead;
+    ctx->snapshot_valid = true;
     return FW_OK;
 }
 
@@ -648,20 +656,24 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
     cudaDeviceProp prop;
     CU(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) return fail(nullptr, FW_ERR_NO_DEVICE, "fw_create: device %d is sm_%d%d; this build carries sm_100a code only", cfg->device, prop.major, prop.minor);
-    std::unique_ptr<fw_context> ctx(new fw_context());
-    ctx->device = cfg->device;
-    ctx->seed = cfg->seed;
-    ctx->flags = cfg->flags;
-    ctx->use_graphs = (cfg->flags & FW_FLAG_NO_GRAPHS) == 0;
-    ctx->profiling = (cfg->flags & FW_FLAG_PROFILE) != 0;
+    // on any failure below fw_destroy releases whatever was created so far
+    struct Guard {
+        fw_context *c;
+        ~Guard() { if (c) fw_destroy(c); }
+    } ctx{new fw_context()};
+    ctx.c->device = cfg->device;
+    fw_context *c = ctx.c;
+    c->seed = cfg->seed;
+    c->flags = cfg->flags;
+    c->use_graphs = (cfg->flags & FW_FLAG_NO_GRAPHS) == 0;
+    c->profiling = (cfg->flags & FW_FLAG_PROFILE) != 0;
     CU(nullptr, cudaSetDevice(cfg->device));
     if (cfg->external_stream) {
-        ctx->stream = (cudaStream_t)cfg->external_stream;
+        c->stream = (cudaStream_t)cfg->external_stream;
     } else {
-        CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        ctx->owns_stream = true;
+        CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->owns_stream = true;
     }
-    fw_context *c = ctx.get();
     CU(c, cudaMalloc((void **)&c->d_plan, sizeof(PlanOut)));
     CU(c, cudaMemsetAsync(c->d_plan, 0, sizeof(PlanOut), c->stream));
     for (FrameSlot &fs : c->ring) {
@@ -675,7 +687,8 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
     if ((rc = ensure_emitters(c, 1))) { g_global_error = c->error; return rc; }
     if ((rc = ensure_tiles(c))) { g_global_error = c->error; return rc; }
     CU(c, update_grid_size(c->device, c->grids));
-    *out_ctx = ctx.release();
+    *out_ctx = c;
+    ctx.c = nullptr;
     return FW_OK;
 }
 
@@ -767,71 +780,96 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
     } else {
         free_spawner_resources(ctx, *sp); // data.particles = vec![Vec::new(); n]  (src/core.rs:360)
     }
-    sp->initialized = true; // :361-363
-    topo_changed(ctx);
-    ctx->live_emitters += n_emitters;
-    sp->emitters.resize(n_emitters);
-    for (uint32_t i = 0; i < n_emitters; i++) { // :347-359
-        Emitter &e = sp->emitters[i];
-        e.es = es[i];
-        e.last_emission = 0.f;
-        e.time_passed_in_cycle = 0.f;
-        e.enabled = starts_enabled != 0;
-        e.emits_on_other_particles = es[i].mode == FW_MODE_NESTED;
-        e.serial = 0;
-        e.lea_index = 0;
-        if (e.emits_on_other_particles)
-            for (uint32_t k = 0; k < i; k++)
-                if (es[k].mode == FW_MODE_NESTED && es[k].target_particle_type == es[i].target_particle_type) e.lea_index++;
-        if (!ctx->free_emitters.empty()) {
-            e.dev_idx = ctx->free_emitters.back();
-            ctx->free_emitters.pop_back();
-        } else {
-            int rc = ensure_emitters(ctx, ctx->n_emitters + 1);
-            if (rc) return rc;
-            e.dev_idx = ctx->n_emitters++;
+    // everything below mutates the spawner; on a failure (out of memory, CUDA error) the
+    // half-built spawner is removed again instead of being left inconsistent
+    auto build = [&]() -> int {
+        sp->initialized = true; // :361-363
+        topo_changed(ctx);
+        ctx->live_emitters += n_emitters;
+        sp->emitters.resize(n_emitters);
+        for (uint32_t i = 0; i < n_emitters; i++) { // :347-359
+            Emitter &e = sp->emitters[i];
+            e.es = es[i];
+            e.last_emission = 0.f;
+            e.time_passed_in_cycle = 0.f;
+            e.enabled = starts_enabled != 0;
+            e.emits_on_other_particles = es[i].mode == FW_MODE_NESTED;
+            e.serial = 0;
+            e.lea_index = 0;
+            if (e.emits_on_other_particles)
+                for (uint32_t k = 0; k < i; k++)
+                    if (es[k].mode == FW_MODE_NESTED && es[k].target_particle_type == es[i].target_particle_type) e.lea_index++;
+            if (!ctx->free_emitters.empty()) {
+                e.dev_idx = ctx->free_emitters.back();
+                ctx->free_emitters.pop_back();
+            } else {
+                int rc = ensure_emitters(ctx, ctx->n_emitters + 1);
+                if (rc) return rc;
+                e.dev_idx = ctx->n_emitters++;
+            }
+            CU(ctx, cudaMemcpyAsync(ctx->d_emitters + e.dev_idx, &es[i], sizeof(fw_emission_settings), cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaMemsetAsync(ctx->d_nested_serial + e.dev_idx, 0, sizeof(unsigned long long), ctx->stream));
+            ctx->h_emitters[e.dev_idx] = es[i];
         }
-        CU(ctx, cudaMemcpyAsync(ctx->d_emitters + e.dev_idx, &es[i], sizeof(fw_emission_settings), cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaMemsetAsync(ctx->d_nested_serial + e.dev_idx, 0, sizeof(unsigned long long), ctx->stream));
-        ctx->h_emitters[e.dev_idx] = es[i];
-    }
-    sp->streams.resize(n_types);
-    for (uint32_t t = 0; t < n_types; t++) {
-        Stream &st = sp->streams[t];
-        st.type = t;
-        st.ps = ps[t];
-        st.variant = pick_variant(ps[t]);
-        st.n_hi = 0;
-        st.born_frame = ctx->frame_no + 1;
-        st.injected = false;
-        st.n_lea = 0;
-        for (uint32_t i = 0; i < n_emitters; i++)
-            if (es[i].mode == FW_MODE_NESTED && es[i].target_particle_type == t) st.n_lea++;
-    }
-    for (uint32_t t = 0; t < n_types; t++) {
-        Stream &st = sp->streams[t];
-        if (!ctx->free_slots.empty()) {
-            st.slot = ctx->free_slots.back();
-            ctx->free_slots.pop_back();
-        } else {
-            int rc = ensure_slots(ctx, ctx->n_slots + 1);
-            if (rc) return rc;
-            st.slot = ctx->n_slots++;
+        sp->streams.resize(n_types);
+        for (uint32_t t = 0; t < n_types; t++) {
+            Stream &st = sp->streams[t];
+            st.type = t;
+            st.ps = ps[t];
+            st.variant = pick_variant(ps[t]);
+            st.n_hi = 0;
+            st.born_frame = ctx->frame_no + 1;
+            st.injected = false;
+            st.n_lea = 0;
+            for (uint32_t i = 0; i < n_emitters; i++)
+                if (es[i].mode == FW_MODE_NESTED && es[i].target_particle_type == t) st.n_lea++;
         }
-        int rc = alloc_block(ctx, round_capacity(estimate_capacity(*sp, t)), st.n_lea, st.block);
-        if (rc) return rc;
-        if (ps[t].capture_destroyed && (rc = alloc_block(ctx, st.block.capacity, st.n_lea, st.destroyed))) return rc;
-        ctx->tiles_needed += (st.block.capacity + kTile - 1) / kTile;
-        ctx->variant_streams[st.variant]++;
-        ctx->slot_owner[st.slot] = &st;
-        DevParticleSettings ds;
-        fill_dev_settings(ps[t], ds);
-        CU(ctx, cudaMemcpyAsync(ctx->d_settings + st.slot, &ds, sizeof(ds), cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaMemsetAsync(ctx->d_states + st.slot, 0, sizeof(StreamState), ctx->stream));
-        if ((rc = upload_desc(ctx, st))) return rc;
+        for (uint32_t t = 0; t < n_types; t++) {
+            Stream &st = sp->streams[t];
+            if (!ctx->free_slots.empty()) {
+                st.slot = ctx->free_slots.back();
+                ctx->free_slots.pop_back();
+            } else {
+                int rc = ensure_slots(ctx, ctx->n_slots + 1);
+                if (rc) return rc;
+                st.slot = ctx->n_slots++;
+            }
+            int rc = alloc_block(ctx, round_capacity(estimate_capacity(*sp, t)), st.n_lea, st.block);
+            if (rc) {
+                ctx->free_slots.push_back(st.slot);
+                return rc;
+            }
+            if (ps[t].capture_destroyed && (rc = alloc_block(ctx, st.block.capacity, st.n_lea, st.destroyed))) return rc;
+            ctx->tiles_needed += (st.block.capacity + kTile - 1) / kTile;
+            ctx->variant_streams[st.variant]++;
+            ctx->slot_owner[st.slot] = &st;
+            DevParticleSettings ds;
+            fill_dev_settings(ps[t], ds);
+            CU(ctx, cudaMemcpyAsync(ctx->d_settings + st.slot, &ds, sizeof(ds), cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaMemsetAsync(ctx->d_states + st.slot, 0, sizeof(StreamState), ctx->stream));
+            if ((rc = upload_desc(ctx, st))) return rc;
+        }
+        sp->finished_notified = false;
+        sp->manual_queued_count = 0;
+
+        return FW_OK;
+    };
+    {
+        const int rc = build();
+        if (rc != FW_OK) {
+            const std::string msg = ctx->error;
+            free_spawner_resources(ctx, *sp);
+            ctx->by_key.erase(key);
+            for (size_t i = 0; i < ctx->spawners.size(); i++)
+                if (ctx->spawners[i].get() == sp) {
+                    ctx->spawners.erase(ctx->spawners.begin() + (long)i);
+                    break;
+                }
+            recount_nested(ctx);
+            ctx->error = msg;
+            return rc;
+        }
     }
-    sp->finished_notified = false;
-    sp->manual_queued_count = 0;
     recount_nested(ctx);
     return ensure_tiles(ctx);
 }
@@ -1199,26 +1237,29 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
         if (!fs.graph_exec || fs.graph_version != ctx->topo_version) {
             if (fs.graph_exec) cudaGraphExecDestroy(fs.graph_exec);
             fs.graph_exec = nullptr;
-            CU(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-            const int rc = enqueue(true);
             cudaGraph_t g = nullptr;
-            const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-            if (rc != FW_OK || e != cudaSuccess) {
-                if (g) cudaGraphDestroy(g);
-                (void)cudaGetLastError();
-                ctx->use_graphs = false;
-                return fail(ctx, FW_ERR_CUDA, "frame graph capture failed: %s", e != cudaSuccess ? cudaGetErrorString(e) : ctx->error.c_str());
+            int rc = FW_ERR_CUDA;
+            cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                rc = enqueue(true);
+                e = cudaStreamEndCapture(ctx->stream, &g);
             }
-            const cudaError_t ei = cudaGraphInstantiate(&fs.graph_exec, g, 0);
-            cudaGraphDestroy(g);
+            cudaError_t ei = cudaErrorUnknown;
+            if (rc == FW_OK && e == cudaSuccess) ei = cudaGraphInstantiate(&fs.graph_exec, g, 0);
+            if (g) cudaGraphDestroy(g);
             if (ei != cudaSuccess) {
+                // e.g. an external stream that cannot be captured: launch kernel by kernel from
+                // now on instead of failing the frame
+                (void)cudaGetLastError();
                 fs.graph_exec = nullptr;
                 ctx->use_graphs = false;
-                return fail(ctx, FW_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+            } else {
+                fs.graph_version = ctx->topo_version;
+                fs.graph_launches = launches;
             }
-            fs.graph_version = ctx->topo_version;
-            fs.graph_launches = launches;
         }
+    }
+    if (ctx->use_graphs && !prof && ctx->topo_stable_frames > kGraphWarmFrames && fs.graph_exec && fs.graph_version == ctx->topo_version) {
         launches = fs.graph_launches;
         CU(ctx, cudaGraphLaunch(fs.graph_exec, ctx->stream));
     } else {
@@ -1226,6 +1267,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
         if (rc) return rc;
     }
     CU(ctx, cudaEventRecord(fs.done, ctx->stream));
+    ctx->snapshot_valid = false;
     ctx->frame_no++;
     fs.in_flight = true;
     fs.frame = ctx->frame_no;
@@ -1249,7 +1291,7 @@ int fw_sync(fw_context *ctx) {
         const uint32_t fl = ctx->device_error_flags;
         ctx->device_error_flags = 0;
         cudaMemsetAsync(&ctx->d_plan->error_flags, 0, sizeof(uint32_t), ctx->stream);
-        return fail(ctx, FW_ERR_INTERNAL, "device reported error flags 0x%x (1 = ring overflow, 2 = tile table overflow)", fl);
+        return fail(ctx, FW_ERR_INTERNAL, "device reported error flags 0x%x (1 = a ring overflowed and spawns were dropped, 2 = look-back table too small, 4 = a nested emitter exceeded its planned per-parent bound)", fl);
     }
     return FW_OK;
 }
@@ -1383,6 +1425,7 @@ int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_pa
     st.n_hi = n;
     st.born_frame = ctx->frame_no + 1;
     st.injected = true;
+    ctx->snapshot_valid = false;
     return FW_OK;
 }
 

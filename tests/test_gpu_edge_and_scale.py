@@ -1,0 +1,183 @@
+"""Edge cases the reference handles implicitly (empty / degenerate inputs, dt = 0, bursts, calls
+from several threads) and size-independent properties at BASELINE.json's full sizes (C3: 10 M
+particles in 512 streams), where the oracle is too slow to replay everything."""
+import threading
+
+import numpy as np
+import pytest
+
+from bevy_firework_b200 import (EmissionPacing, EmissionSettings, ParticleSettings, ParticleSpawner, RandF32,
+                                RandVec3, _abi)
+from bevy_firework_b200._native import Engine, FireworkError, frame_input
+from bevy_firework_b200.workloads import grid_positions, stress_spawner
+from _parity import assert_rows_match, reset_both
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+DT = float(f32(1.0) / f32(60.0))
+
+
+def test_empty_context_and_degenerate_spawners(engine, oracle):
+    engine.frame(DT, [])                                  # no spawners at all
+    engine.sync()
+    assert engine.total_live() == 0
+    keys, types, counts = engine.counts_all()
+    assert len(keys) == 0
+    # a spawner with particle types but no emitters, and one whose emitter never fires
+    sp0 = ParticleSpawner(particle_settings=[ParticleSettings()], emission_settings=[])
+    sp1 = ParticleSpawner(emission_settings=[EmissionSettings(emission_pacing=EmissionPacing.rate(0.0))])
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 1, sp0)
+    reset_both(engine, w, 2, sp1)
+    for _ in range(5):
+        engine.frame(DT, [frame_input(1), frame_input(2)])
+        w.frame(DT, [frame_input(1), frame_input(2)])
+    assert engine.counts(1) == w.counts(1) == [0] and engine.counts(2) == w.counts(2) == [0]
+    assert engine.read_aabb(1) is None
+    st, ost = engine.status(1), w.status(1)
+    assert (st.active, st.all_empty, st.finished) == (ost.active, ost.all_empty, ost.finished)
+    assert len(engine.read_particles(2, 0)) == 0 and len(engine.read_instances(2, 0)) == 0
+
+
+def test_zero_dt_and_varying_dt(engine, oracle):
+    """dt is whatever Time::delta_secs() says: 0 (paused virtual time) and uneven steps."""
+    sp = stress_spawner(rate=4000.0, lifetime=0.3)
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 1, sp)
+    rng = np.random.default_rng(0)
+    dts = [DT, 0.0, 0.0, 0.004, 0.05, DT, 0.0] + [float(f32(x)) for x in rng.uniform(0.001, 0.04, 60)]
+    for k, dt in enumerate(dts):
+        engine.frame(dt, [frame_input(1, (0.0, 0.1, 0.0))])
+        w.frame(dt, [frame_input(1, (0.0, 0.1, 0.0))])
+        assert engine.counts(1) == w.counts(1), f"frame {k} dt {dt}"
+    assert_rows_match(engine.read_particles(1, 0), w.read_particles(1, 0),
+                      exact=("age", "lifetime", "initial_scale", "scale", "base_color", "emissive_color"))
+
+
+def test_large_one_shot_burst(engine):
+    """EmissionPacing::OneShot(5_000_000) into one stream: ring sized on demand, every particle
+    spawned exactly once, all identical in age/lifetime, serials all distinct."""
+    n = 5_000_000
+    sp = ParticleSpawner(particle_settings=[ParticleSettings(lifetime=RandF32.constant(1.0), initial_scale=RandF32(0.0, 1.0))],
+                         emission_settings=[EmissionSettings(emission_pacing=EmissionPacing.OneShot(n),
+                                                             initial_velocity=RandVec3(RandF32(0.0, 1.0), (0.0, 1.0, 0.0), 0.5))])
+    ps, nt, es, ne = sp.pods()
+    engine.spawner_reset(1, ps, nt, es, ne, True)
+    engine.frame(DT, [frame_input(1)])
+    assert engine.counts(1) == [n]
+    rows = engine.read_particles(1, 0)
+    assert (rows["age"] == f32(DT)).all() and (rows["lifetime"] == 1.0).all()
+    # initial_scale = u * 1: a 24-bit uniform per particle from distinct Philox counters
+    assert 0.499 < rows["initial_scale"].mean() < 0.501
+    assert len(np.unique(rows["initial_scale"])) > 0.25 * (1 << 24) * (1 - np.exp(-n / (1 << 24)))
+    for _ in range(61):
+        engine.frame(DT, [frame_input(1)])
+    assert engine.counts(1) == [0] and engine.status(1).finished
+
+
+def test_calls_from_different_threads(engine, oracle):
+    """Bevy runs the systems on arbitrary worker threads: same context, one call at a time."""
+    sp = stress_spawner(rate=3000.0)
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 1, sp)
+    errors = []
+
+    def work(k):
+        try:
+            for _ in range(10):
+                engine.frame(DT, [frame_input(1, (0.0, 0.1, 0.0))])
+            engine.counts(1)
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    for k in range(6):
+        t = threading.Thread(target=work, args=(k,))
+        t.start()
+        t.join()
+    for _ in range(60):
+        w.frame(DT, [frame_input(1, (0.0, 0.1, 0.0))])
+    assert not errors
+    assert engine.counts(1) == w.counts(1)
+
+
+def test_two_contexts_are_independent():
+    a, b = Engine(device=0, seed=1), Engine(device=0, seed=1)
+    sp = stress_spawner(rate=2000.0)
+    ps, nt, es, ne = sp.pods()
+    for e in (a, b):
+        e.spawner_reset(5, ps, nt, es, ne, True)
+    for k in range(30):
+        a.frame(DT, [frame_input(5)])
+        if k % 2 == 0:
+            b.frame(DT, [frame_input(5)])
+    assert a.counts(5)[0] > b.counts(5)[0] > 0
+    for _ in range(15):
+        b.frame(DT, [frame_input(5)])
+    assert a.read_particles(5, 0).tobytes() == b.read_particles(5, 0).tobytes()  # same seed, same history
+    a.close()
+    b.close()
+
+
+def test_unknown_and_removed_spawners(engine):
+    sp = stress_spawner(rate=100.0)
+    ps, nt, es, ne = sp.pods()
+    engine.spawner_reset(9, ps, nt, es, ne, True)
+    engine.frame(DT, [frame_input(9)])
+    engine.spawner_remove(9)
+    for call in (lambda: engine.counts(9, 1), lambda: engine.status(9), lambda: engine.read_particles(9, 0),
+                 lambda: engine.spawner_remove(9), lambda: engine.frame(DT, [frame_input(9)])):
+        with pytest.raises(FireworkError) as e:
+            call()
+        assert e.value.code == _abi.FW_ERR_UNKNOWN_SPAWNER
+    engine.frame(DT, [])  # the context keeps working
+
+
+def test_c3_full_size_properties(oracle):
+    """BASELINE config 3 at full size (512 spawners x rate 19531, ~10 M particles): counts per
+    stream must equal the reference's emission arithmetic exactly; ages/lifetimes/colours are
+    functions of the spawn frame only; the per-spawner AABBs must bound every instance row."""
+    import torch
+
+    n_sp, rate, frames = 512, 19531.0, 75
+    eng = Engine(device=0, seed=0x00F12E00)
+    sp = stress_spawner(rate=rate)
+    pos = grid_positions(n_sp)
+    ps, nt, es, ne = sp.pods()
+    inputs = []
+    for i in range(n_sp):
+        eng.spawner_reset(1 + i, ps, nt, es, ne, True)
+        inputs.append(frame_input(1 + i, pos[i]))
+    for _ in range(frames):
+        eng.frame(DT, inputs)
+    # expected live count: particles emitted in the last 60 frames (lifetime 1 s dies on update #61)
+    t = last = 0.0
+    emitted = []
+    for _ in range(frames):
+        t = oracle.lib().fwo_rem_euclid(float(f32(t) + f32(DT)), 1.0)
+        n, last = oracle.compute_emission_count(t, last, 1.0, 0.0, 1.0, rate)
+        emitted.append(n)
+    want = sum(emitted[-60:])
+    keys, types, counts = eng.counts_all()
+    assert len(counts) == n_sp and (counts == want).all()
+    assert eng.total_live() == want * n_sp
+    # one stream in detail: ages are the f32 partial sums of dt, grouped by spawn frame, oldest first
+    rows = eng.read_particles(1 + 300, 0)
+    ages, acc = [], f32(0.0)
+    for _ in range(60):
+        acc = f32(acc + f32(DT))
+        ages.append(acc)
+    want_ages = np.concatenate([np.full(emitted[-60 + j], ages[59 - j], dtype=np.float32) for j in range(60)])
+    assert (rows["age"] == want_ages).all() and (rows["lifetime"] == 1.0).all()
+    # AABB of every spawner bounds its instance rows; extract = concatenation of the streams
+    cap = want * n_sp + 1024
+    host = torch.empty((cap, 16), dtype=torch.float32, pin_memory=True)
+    n_rows = eng.extract_instances(host.data_ptr(), cap)
+    assert n_rows == want * n_sp
+    inst = host.numpy()[:n_rows].view(_abi.particle_instance_dtype()).reshape(n_sp, want)
+    for i in (0, 137, 511):
+        lo, hi = eng.read_aabb(1 + i)
+        p, s = inst[i]["position"], inst[i]["scale"][:, None]
+        assert ((p - s).min(axis=0) == np.array(lo, dtype=np.float32)).all()
+        assert ((p + s).max(axis=0) == np.array(hi, dtype=np.float32)).all()
+    assert (inst[300]["position"] == rows["position"]).all()
+    eng.close()
