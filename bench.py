@@ -70,9 +70,15 @@ def make_workload(name: str, rank: int):
 class Scene:
     """Drives either backend (Engine or OracleWorld: same method names) through the schedule."""
 
-    def __init__(self, backend, workload, rank):
+    def __init__(self, backend, workload, rank, shard=None):
         self.b = backend
         self.label, self.spawners, colliders, self.fill_frames, self.bursts = make_workload(workload, rank)
+        if shard is not None:  # strong scaling: this rank simulates only its block of the spawners
+            world, r = shard
+            from bevy_firework_b200.distributed import shard_range
+
+            base_keys = make_workload(workload, 0)[1]  # keys independent of the rank
+            self.spawners = [base_keys[i] for i in shard_range(len(base_keys), world, r)]
         if colliders:
             backend.set_colliders(colliders)
         from bevy_firework_b200._native import frame_input
@@ -223,6 +229,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extract", action="store_true", help="also time the full instance-row extract (D2H)")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernel by kernel instead of replaying frame graphs")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank runs the whole workload (default); strong: the workload's spawners are "
+                         "sharded over the ranks (BASELINE config 3: 10 M particles over 1..8 GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -263,7 +272,7 @@ def main():
     from bevy_firework_b200._native import Engine
 
     eng = Engine(device=local_rank, seed=W.SEED, profile=False, graphs=not args.no_graphs)  # raises without the CUDA library
-    sc = Scene(eng, args.workload, rank)
+    sc = Scene(eng, args.workload, rank, shard=(world, rank) if args.scaling == "strong" and world > 1 else None)
     for _ in range(sc.fill_frames):  # reach the stationary live count (lifetime/dt + 2 frames)
         sc.step()
     eng.sync()
@@ -362,7 +371,7 @@ def main():
         line = {
             "metric": "particles updated/sec (fused step)", "value": updated_all / (ms_all * 1e-3), "unit": "particles/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": sc.label, "dt": "fl32(1/60)", "live_particles": live_all, "seed": hex(W.SEED),
                        "streams_per_gpu": len(sc.spawners) or 151, "parallelism": f"shard-by-spawner x{world}",
                        "l2": "state per GPU (1.6 GB at C3) is larger than the 126 MB L2; no flush between steps",
@@ -389,8 +398,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             eng.close()
             v, cms, clive, _ = run_cpu(args.workload, args.cpu_steps, 1, cores)
+            # Bevy's default compute pool does not get every core: 4-thread figure too
+            v4 = run_cpu(args.workload, max(2, args.cpu_steps // 2), 1, 4)[0] if cores > 4 else v
             line["cpu_baseline"] = {
-                "value": v, "unit": "particles/s", "cores": cores, "kind": "port",
+                "value": v, "unit": "particles/s", "cores": cores, "kind": "port", "value_4_threads": v4,
                 "sample": f"full workload ({clive} live particles), {args.cpu_steps} timed frames after the fill "
                           f"frames, {cms:.1f} ms/frame; C restatement of the reference loop (oracle/fw_oracle.c), "
                           f"one task per spawner on {cores} threads, sequential spawn"}

@@ -164,6 +164,7 @@ struct fw_context {
     // last exact state snapshot (valid after refresh_exact)
     std::vector<StreamState> snapshot;
     bool snapshot_valid = false; // no device work was enqueued since `snapshot` was read
+    bool readback_is_current = false; // the newest frame's pinned state readback == device state
 };
 
 namespace {
@@ -181,6 +182,7 @@ int fail(fw_context *ctx, int code, const char *fmt, ...) {
 
 inline void topo_changed(fw_context *ctx) {
     ctx->snapshot_valid = false;
+    ctx->readback_is_current = false;
     ctx->topo_version++;
     ctx->topo_stable_frames = 0;
 }
@@ -447,6 +449,20 @@ int refresh_exact(fw_context *ctx) {
     // nothing was submitted since the last exact snapshot: it is still exact (lets a host loop
     // call fw_counts / fw_read_aabb per spawner without a sync + copy each time)
     if (ctx->snapshot_valid && ctx->snapshot.size() == ctx->n_slots) return FW_OK;
+    // the last thing enqueued was a frame: its own asynchronous state readback (pinned) is the
+    // exact state once that frame is done -- no second copy, no full-stream sync
+    if (ctx->readback_is_current && ctx->frame_no > 0) {
+        FrameSlot &ls = ctx->ring[(ctx->frame_no - 1) % kRing];
+        if (ls.frame == ctx->frame_no && ls.states_slots >= ctx->n_slots) {
+            CU(ctx, cudaEventSynchronize(ls.done));
+            ctx->snapshot.assign(ls.states_host, ls.states_host + ctx->n_slots);
+            for (FrameSlot &fs : ctx->ring) fs.in_flight = false; // stream order: older frames are done too
+            for (uint32_t s = 0; s < ctx->n_slots; s++)
+                if (Stream *st = ctx->slot_owner[s]) st->n_hi = ctx->snapshot[s].count - ctx->snapshot[s].dead;
+            ctx->snapshot_valid = true;
+            return FW_OK;
+        }
+    }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (FrameSlot &fs : ctx->ring) fs.in_flight = false;
     ctx->snapshot.resize(ctx->n_slots);
@@ -498,6 +514,7 @@ int grow_stream(fw_context *ctx, Stream &st, uint64_t need) {
         if ((rc = alloc_block(ctx, ncap, st.n_lea, st.destroyed))) return rc;
     }
     // unwrap the ring into the start of the new block
+    ctx->readback_is_current = false;
     CU(ctx, launch_ring_copy(block_desc(st.block, st.variant), first, live, block_desc(nb, st.variant), ctx->stream));
     StreamState ns = s;
     ns.head = 0;
@@ -1268,6 +1285,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     }
     CU(ctx, cudaEventRecord(fs.done, ctx->stream));
     ctx->snapshot_valid = false;
+    ctx->readback_is_current = true;
     ctx->frame_no++;
     fs.in_flight = true;
     fs.frame = ctx->frame_no;
@@ -1426,6 +1444,7 @@ int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_pa
     st.born_frame = ctx->frame_no + 1;
     st.injected = true;
     ctx->snapshot_valid = false;
+    ctx->readback_is_current = false;
     return FW_OK;
 }
 
