@@ -72,9 +72,10 @@ struct FrameSlot {
     uint8_t *host = nullptr; // pinned
     uint8_t *dev = nullptr;
     size_t bytes = 0;
-    StreamState *states_host = nullptr; // pinned readback of all stream states after the frame
+    uint8_t *readback = nullptr;        // pinned copy of the frame's state buffer [PlanOut | states]
+    StreamState *states_host = nullptr; // = readback + sizeof(PlanOut)
     uint32_t states_slots = 0;
-    PlanOut *plan_host = nullptr; // pinned readback of the plan kernel's output
+    PlanOut *plan_host = nullptr;       // = readback
     cudaEvent_t done = nullptr;
     bool in_flight = false;
     uint64_t frame = 0;
@@ -110,7 +111,9 @@ struct fw_context {
     std::vector<uint32_t> free_slots;
     std::vector<Stream *> slot_owner;
     StreamDesc *d_descs = nullptr;
-    StreamState *d_states = nullptr;
+    // double-buffered [PlanOut | StreamState x slots_cap]; frame f writes buffer f&1 and reads the
+    // other one, so the buffer holding the current state is always frame_no & 1
+    uint8_t *d_statebuf[2] = {nullptr, nullptr};
     DevParticleSettings *d_settings = nullptr;
     std::vector<StreamDesc> h_descs;
     uint32_t emitters_cap = 0, n_emitters = 0;
@@ -126,7 +129,6 @@ struct fw_context {
     unsigned long long *d_lookback = nullptr;
     uint32_t tiles_cap = 0;
     uint64_t tiles_needed = 0; // sum over streams of ceil(capacity / kTile)
-    PlanOut *d_plan = nullptr;
     uint32_t device_error_flags = 0; // accumulated from the per-frame plan readbacks
     unsigned long long *d_pack = nullptr; // n_rows + per-slot offsets
     uint32_t pack_cap = 0;
@@ -186,6 +188,12 @@ inline void topo_changed(fw_context *ctx) {
     ctx->topo_version++;
     ctx->topo_stable_frames = 0;
 }
+
+inline size_t statebuf_bytes(uint32_t slots) { return sizeof(PlanOut) + sizeof(StreamState) * (size_t)slots; }
+inline int cur_buf(const fw_context *ctx) { return (int)(ctx->frame_no & 1u); }
+inline StreamState *states_of(fw_context *ctx, int i) { return (StreamState *)(ctx->d_statebuf[i] + sizeof(PlanOut)); }
+inline PlanOut *plan_of(fw_context *ctx, int i) { return (PlanOut *)ctx->d_statebuf[i]; }
+inline StreamState *cur_states(fw_context *ctx) { return states_of(ctx, cur_buf(ctx)); }
 
 #define CU(ctx, call)                                                                              \
     do {                                                                                           \
@@ -312,7 +320,15 @@ int ensure_slots(fw_context *ctx, uint32_t need) {
     while (ncap < need) ncap *= 2;
     int rc;
     if ((rc = grow_device_array(ctx, ctx->d_descs, ctx->slots_cap, ncap))) return rc;
-    if ((rc = grow_device_array(ctx, ctx->d_states, ctx->slots_cap, ncap))) return rc;
+    for (int i = 0; i < 2; i++) {
+        uint8_t *nb = nullptr;
+        CU(ctx, cudaMalloc((void **)&nb, statebuf_bytes(ncap)));
+        CU(ctx, cudaMemsetAsync(nb, 0, statebuf_bytes(ncap), ctx->stream));
+        if (ctx->d_statebuf[i]) CU(ctx, cudaMemcpyAsync(nb, ctx->d_statebuf[i], statebuf_bytes(ctx->slots_cap), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_statebuf[i]) CU(ctx, cudaFree(ctx->d_statebuf[i]));
+        ctx->d_statebuf[i] = nb;
+    }
     if ((rc = grow_device_array(ctx, ctx->d_settings, ctx->slots_cap, ncap))) return rc;
     if (ctx->d_tile_prefix) CU(ctx, cudaFree(ctx->d_tile_prefix));
     ctx->d_tile_prefix = nullptr;
@@ -467,7 +483,7 @@ int refresh_exact(fw_context *ctx) {
     for (FrameSlot &fs : ctx->ring) fs.in_flight = false;
     ctx->snapshot.resize(ctx->n_slots);
     if (ctx->n_slots)
-        CU(ctx, cudaMemcpy(ctx->snapshot.data(), ctx->d_states, sizeof(StreamState) * ctx->n_slots, cudaMemcpyDeviceToHost));
+        CU(ctx, cudaMemcpy(ctx->snapshot.data(), cur_states(ctx), sizeof(StreamState) * ctx->n_slots, cudaMemcpyDeviceToHost));
     for (uint32_t s = 0; s < ctx->n_slots; s++)
         if (Stream *st = ctx->slot_owner[s]) st->n_hi = ctx->snapshot[s].count - ctx->snapshot[s].dead;
     ctx->snapshot_valid = true;
@@ -520,7 +536,7 @@ int grow_stream(fw_context *ctx, Stream &st, uint64_t need) {
     ns.head = 0;
     ns.count = live;
     ns.dead = 0;
-    CU(ctx, cudaMemcpyAsync(ctx->d_states + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(cur_states(ctx) + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, ctx->stream));
     ctx->snapshot[st.slot] = ns;
     ctx->tiles_needed -= (st.block.capacity + kTile - 1) / kTile;
     release_block(ctx, st.block);
@@ -541,10 +557,13 @@ int ensure_frame_slot(fw_context *ctx, FrameSlot &fs, size_t bytes) {
         fs.bytes = nb;
         fs.graph_version = 0;
     }
-    if (fs.states_slots < ctx->slots_cap) {
-        if (fs.states_host) CU(ctx, cudaFreeHost(fs.states_host));
-        fs.states_host = nullptr;
-        CU(ctx, cudaMallocHost((void **)&fs.states_host, sizeof(StreamState) * ctx->slots_cap));
+    if (fs.states_slots < ctx->slots_cap || !fs.readback) {
+        if (fs.readback) CU(ctx, cudaFreeHost(fs.readback));
+        fs.readback = nullptr;
+        CU(ctx, cudaMallocHost((void **)&fs.readback, statebuf_bytes(ctx->slots_cap)));
+        memset(fs.readback, 0, statebuf_bytes(ctx->slots_cap));
+        fs.plan_host = (PlanOut *)fs.readback;
+        fs.states_host = (StreamState *)(fs.readback + sizeof(PlanOut));
         fs.states_slots = ctx->slots_cap;
         fs.graph_version = 0;
     }
@@ -691,11 +710,7 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
         CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->owns_stream = true;
     }
-    CU(c, cudaMalloc((void **)&c->d_plan, sizeof(PlanOut)));
-    CU(c, cudaMemsetAsync(c->d_plan, 0, sizeof(PlanOut), c->stream));
     for (FrameSlot &fs : c->ring) {
-        CU(c, cudaMallocHost((void **)&fs.plan_host, sizeof(PlanOut)));
-        memset(fs.plan_host, 0, sizeof(PlanOut));
         CU(c, cudaEventCreateWithFlags(&fs.done, cudaEventDisableTiming));
         for (auto &ev : fs.ev) CU(c, cudaEventCreate(&ev));
     }
@@ -723,15 +738,15 @@ int fw_destroy(fw_context *ctx) {
     for (FrameSlot &fs : ctx->ring) {
         if (fs.host) cudaFreeHost(fs.host);
         if (fs.dev) cudaFree(fs.dev);
-        if (fs.states_host) cudaFreeHost(fs.states_host);
-        if (fs.plan_host) cudaFreeHost(fs.plan_host);
+        if (fs.readback) cudaFreeHost(fs.readback);
         if (fs.graph_exec) cudaGraphExecDestroy(fs.graph_exec);
         if (fs.done) cudaEventDestroy(fs.done);
         for (auto &ev : fs.ev)
             if (ev) cudaEventDestroy(ev);
     }
     cudaFree(ctx->d_descs);
-    cudaFree(ctx->d_states);
+    cudaFree(ctx->d_statebuf[0]);
+    cudaFree(ctx->d_statebuf[1]);
     cudaFree(ctx->d_settings);
     cudaFree(ctx->d_emitters);
     cudaFree(ctx->d_colliders);
@@ -742,7 +757,6 @@ int fw_destroy(fw_context *ctx) {
     cudaFree(ctx->d_nested_out);
     cudaFree(ctx->d_stage);
     cudaFree(ctx->d_lookback);
-    cudaFree(ctx->d_plan);
     cudaFree(ctx->d_pack);
     cudaFree(ctx->d_extract);
     for (auto &ev : ctx->user_events)
@@ -863,7 +877,7 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
             DevParticleSettings ds;
             fill_dev_settings(ps[t], ds);
             CU(ctx, cudaMemcpyAsync(ctx->d_settings + st.slot, &ds, sizeof(ds), cudaMemcpyHostToDevice, ctx->stream));
-            CU(ctx, cudaMemsetAsync(ctx->d_states + st.slot, 0, sizeof(StreamState), ctx->stream));
+            CU(ctx, cudaMemsetAsync(cur_states(ctx) + st.slot, 0, sizeof(StreamState), ctx->stream));
             if ((rc = upload_desc(ctx, st))) return rc;
         }
         sp->finished_notified = false;
@@ -1138,7 +1152,8 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     const size_t off_cmds = align16(off_spawn + sizeof(uint32_t) * n_phases * std::max(1u, n_slots));
     const size_t off_inputs = align16(off_cmds + sizeof(SpawnCmd) * cmds_cap);
     const size_t off_nested = align16(off_inputs + sizeof(SpawnerInput) * inputs_cap);
-    const size_t bytes = align16(off_nested + sizeof(NestedCmd) * nested_cap);
+    const size_t off_prefix = align16(off_nested + sizeof(NestedCmd) * nested_cap);
+    const size_t bytes = align16(off_prefix + sizeof(uint32_t) * kNumVariants * (n_slots + 1));
     {
         int rc = ensure_frame_slot(ctx, fs, bytes);
         if (rc) return rc;
@@ -1149,6 +1164,29 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     h->n_slots = n_slots;
     h->n_phases = n_phases;
     h->epoch = (uint32_t)((ctx->frame_no + 1) & 0x3FFFFFFFu);
+    // fast path (no nested emitters): no plan kernel. The update tiles come from this host-built
+    // table of upper bounds: ceil(n_hi / tile) per stream, n_hi >= the stream's real count.
+    const bool derive = n_phases == 1;
+    h->derive = derive ? 1u : 0u;
+    if (derive) {
+        uint32_t *hp = (uint32_t *)(fs.host + off_prefix);
+        uint32_t base = 0;
+        for (uint32_t v = 0; v < kNumVariants; v++) {
+            uint32_t run = 0;
+            uint32_t *pv = hp + (size_t)v * (n_slots + 1);
+            if (ctx->variant_streams[v]) {
+                for (uint32_t s = 0; s < n_slots; s++) {
+                    pv[s] = run;
+                    const Stream *st = ctx->slot_owner[s];
+                    if (st && st->variant == v) run += (uint32_t)((std::min<uint64_t>(st->n_hi, st->block.capacity) + kTile - 1) / kTile);
+                }
+                pv[n_slots] = run;
+            }
+            h->host_n_tiles[v] = run;
+            h->host_tile_base[v] = base;
+            base += run;
+        }
+    }
     uint64_t total_spawn = 0;
     {
         SpawnCmd *hc = (SpawnCmd *)(fs.host + off_cmds);
@@ -1173,7 +1211,9 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
 
     DeviceTables t{};
     t.descs = ctx->d_descs;
-    t.states = ctx->d_states;
+    const int old_buf = cur_buf(ctx), new_buf = old_buf ^ 1; // frame f writes buffer f & 1
+    t.states = states_of(ctx, new_buf);
+    t.states_prev = states_of(ctx, old_buf);
     t.settings = ctx->d_settings;
     t.emitters = ctx->d_emitters;
     t.colliders = ctx->d_colliders;
@@ -1182,7 +1222,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     t.tile_prefix = ctx->d_tile_prefix;
     t.slots_cap = ctx->slots_cap;
     t.lookback_capacity = ctx->tiles_cap;
-    t.plan = ctx->d_plan;
+    t.plan = plan_of(ctx, new_buf);
     t.lookback = ctx->d_lookback;
     t.seed = ctx->seed;
     t.nested_scratch = ctx->d_nested_scratch;
@@ -1194,6 +1234,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     f.cmds = (const SpawnCmd *)(fs.dev + off_cmds);
     f.inputs = (const SpawnerInput *)(fs.dev + off_inputs);
     f.nested = (const NestedCmd *)(fs.dev + off_nested);
+    f.host_tile_prefix = (const uint32_t *)(fs.dev + off_prefix);
 
     const bool prof = ctx->profiling;
     uint32_t variant_mask = 0;
@@ -1212,11 +1253,14 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     // depend on this particular frame's counts
     auto enqueue = [&](bool replay) -> int {
         launches = 0;
+        CU(ctx, cudaMemsetAsync(ctx->d_statebuf[new_buf], 0, statebuf_bytes(n_slots), ctx->stream));
         CU(ctx, cudaMemcpyAsync(fs.dev, fs.host, bytes, cudaMemcpyHostToDevice, ctx->stream));
         if (prof) CU(ctx, cudaEventRecord(fs.ev[0], ctx->stream));
         const bool single = n_phases == 1;
-        CU(ctx, launch_plan(t, f, variant_mask, kPlanDeaths | kPlanAppend | (single ? kPlanTiles : 0u), 0, ctx->stream));
-        launches++;
+        if (!derive) { // nested emitters: last frame's buffer -> this frame's buffer, phase 0 appended
+            CU(ctx, launch_plan(t, f, variant_mask, kPlanDeaths | kPlanAppend | (single ? kPlanTiles : 0u), 0, ctx->stream));
+            launches++;
+        }
         if (prof) CU(ctx, cudaEventRecord(fs.ev[1], ctx->stream));
         for (uint32_t p = 0; p < n_phases; p++) {
             if (p > 0 && (replay || phase_total[p])) {
@@ -1244,9 +1288,8 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
             launches++;
         }
         if (prof) CU(ctx, cudaEventRecord(fs.ev[3], ctx->stream));
-        // asynchronous readback of the stream states (bounds for the next frames) + plan output
-        if (ctx->n_slots) CU(ctx, cudaMemcpyAsync(fs.states_host, ctx->d_states, sizeof(StreamState) * ctx->n_slots, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(fs.plan_host, ctx->d_plan, sizeof(PlanOut), cudaMemcpyDeviceToHost, ctx->stream));
+        // asynchronous readback of [PlanOut | stream states] (bounds for the next frames, counts)
+        CU(ctx, cudaMemcpyAsync(fs.readback, ctx->d_statebuf[new_buf], statebuf_bytes(n_slots), cudaMemcpyDeviceToHost, ctx->stream));
         return FW_OK;
     };
     ctx->topo_stable_frames++;
@@ -1294,7 +1337,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     fs.launches = launches;
     fs.particles_spawned = total_spawn;
     fs.h2d_bytes = bytes;
-    fs.d2h_bytes = sizeof(StreamState) * (uint64_t)ctx->n_slots + sizeof(PlanOut);
+    fs.d2h_bytes = statebuf_bytes(n_slots);
     return FW_OK;
 }
 
@@ -1302,13 +1345,13 @@ int fw_sync(fw_context *ctx) {
     ENTER(ctx);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (FrameSlot &fs : ctx->ring) {
+        if (!fs.plan_host) continue;
         ctx->device_error_flags |= fs.plan_host->error_flags;
         fs.plan_host->error_flags = 0;
     }
     if (ctx->device_error_flags) {
         const uint32_t fl = ctx->device_error_flags;
         ctx->device_error_flags = 0;
-        cudaMemsetAsync(&ctx->d_plan->error_flags, 0, sizeof(uint32_t), ctx->stream);
         return fail(ctx, FW_ERR_INTERNAL, "device reported error flags 0x%x (1 = a ring overflowed and spawns were dropped, 2 = look-back table too small, 4 = a nested emitter exceeded its planned per-parent bound)", fl);
     }
     return FW_OK;
@@ -1437,8 +1480,7 @@ int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_pa
     }
     StreamState ns{};
     ns.count = (uint32_t)n;
-    ns.aabb_min[0] = ns.aabb_min[1] = ns.aabb_min[2] = 0xFFFFFFFFu;
-    CU(ctx, cudaMemcpyAsync(ctx->d_states + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(cur_states(ctx) + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     st.n_hi = n;
     st.born_frame = ctx->frame_no + 1;
@@ -1465,7 +1507,7 @@ int fw_read_instances(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_
     if ((rc = ensure_stage(ctx, hdr + (size_t)live * 64))) return rc;
     DeviceTables t{};
     t.descs = ctx->d_descs;
-    t.states = ctx->d_states;
+    t.states = cur_states(ctx);
     CU(ctx, launch_pack_instances(t, st.slot, st.slot + 1, (float4 *)(ctx->d_stage + hdr), live, (unsigned long long *)ctx->d_stage, ctx->stream));
     CU(ctx, cudaMemcpyAsync(out, ctx->d_stage + hdr, (size_t)live * 64, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1506,8 +1548,8 @@ int fw_read_aabb(fw_context *ctx, uint32_t key, float out_min[3], float out_max[
         if (s.count - s.dead == 0) continue;
         live += s.count - s.dead;
         for (int k = 0; k < 3; k++) {
-            mn[k] = std::fmin(mn[k], dec_f32(s.aabb_min[k]));
-            mx[k] = std::fmax(mx[k], dec_f32(s.aabb_max[k]));
+            if (s.aabb_min_inv[k]) mn[k] = std::fmin(mn[k], dec_f32(~s.aabb_min_inv[k]));
+            if (s.aabb_max[k]) mx[k] = std::fmax(mx[k], dec_f32(s.aabb_max[k]));
         }
     }
     if (out_min) memcpy(out_min, mn, sizeof(mn));
@@ -1529,7 +1571,7 @@ int fw_pack_instances_device(fw_context *ctx, void *device_dst, uint64_t cap_row
     }
     DeviceTables t{};
     t.descs = ctx->d_descs;
-    t.states = ctx->d_states;
+    t.states = cur_states(ctx);
     CU(ctx, launch_pack_instances(t, 0, ctx->n_slots, (float4 *)device_dst, cap_rows, ctx->d_pack, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->h_pack, ctx->d_pack, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));

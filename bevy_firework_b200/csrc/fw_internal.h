@@ -120,12 +120,18 @@ __host__ __device__ inline StreamArrays stream_arrays(uint8_t *base, uint32_t ca
     return a;
 }
 
+// Stream states are double-buffered: frame f reads the buffer frame f-1 wrote and writes the
+// other one (zeroed by a memset node first), so every kernel can DERIVE the state it needs --
+// head after last frame's deaths, count after this frame's spawns -- functionally from the old
+// buffer instead of waiting for a serial "plan" kernel.
 struct StreamState { // mutated by kernels
     uint32_t head;
-    uint32_t count;      // live particles (after the plan kernel: including this frame's spawns)
-    uint32_t dead;       // deaths of the last update, applied by the next plan kernel
+    uint32_t count;      // particles that entered this frame's update (live + spawned)
+    uint32_t dead;       // deaths of this frame's update (atomic), applied by the next frame
     uint32_t spawn_base; // logical index of this frame's first spawned particle
-    uint32_t aabb_min[3]; // order-preserving uint encoding of float
+    // per-stream AABB of position -/+ scale as order-preserving uint encodings, zero = empty:
+    // aabb_min_inv = ~enc(min) (so that atomicMax keeps the minimum), aabb_max = enc(max)
+    uint32_t aabb_min_inv[3];
     uint32_t aabb_max[3];
     uint32_t overflow; // spawns dropped because the ring was full (the host grows before that)
     uint32_t pad;
@@ -187,21 +193,29 @@ struct FrameHeader {
     uint32_t n_phases;
     uint32_t epoch;
     uint32_t n_nested;
-    uint32_t pad[2];
+    // derive = 1: the fast path (no nested emitters). There is no plan kernel: spawn and update
+    // derive head / counts from the previous state buffer and the update tiles come from a
+    // host-built table of UPPER BOUNDS (tiles past a stream's real count exit at once).
+    uint32_t derive;
+    uint32_t pad;
+    uint32_t host_n_tiles[kNumVariants];
+    uint32_t host_tile_base[kNumVariants];
     PhaseInfo phase[kMaxPhases];
 };
 
-struct PlanOut { // device, written by the plan kernel
+struct PlanOut { // device, per frame; lives in front of the stream states of the same buffer
     uint32_t n_tiles[kNumVariants];
     uint32_t tile_base[kNumVariants]; // start of each variant inside the look-back array
     uint32_t error_flags;
     uint32_t total_update; // particles entering the update this frame
-    uint32_t pad[2];
+    uint32_t pad[6];
 };
+static_assert(sizeof(PlanOut) == 64, "state buffer layout: [PlanOut (64 B)][StreamState x slots]");
 
 struct DeviceTables {
     const StreamDesc *descs;
-    StreamState *states;
+    StreamState *states;            // this frame's buffer (written)
+    const StreamState *states_prev; // last frame's buffer (read)
     const DevParticleSettings *settings; // indexed by stream slot
     const fw_emission_settings *emitters;
     const fw_collider *colliders;
@@ -222,6 +236,7 @@ struct DeviceTables {
 
 struct FrameDeviceInputs {
     const FrameHeader *header;
+    const uint32_t *host_tile_prefix; // derive path: [kNumVariants][n_slots + 1] upper-bound tiles
     const uint32_t *spawn_per_slot; // [n_phases][n_slots]
     const SpawnCmd *cmds;
     const SpawnerInput *inputs;

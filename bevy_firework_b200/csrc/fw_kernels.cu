@@ -106,13 +106,13 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
         for (uint32_t s = threadIdx.x; s < n_slots; s += blockDim.x) {
             const StreamDesc d = t.descs[s];
             if (d.capacity == 0u) continue;
-            StreamState st = t.states[s];
-            if (what & kPlanDeaths) {
+            StreamState st = (what & kPlanDeaths) ? t.states_prev[s] : t.states[s];
+            if (what & kPlanDeaths) { // last frame's buffer -> this frame's buffer
                 const bool fifo = (d.variant == kFifo || d.variant == kFifoCollide);
                 if (fifo) st.head = wrap(st.head + st.dead, d.capacity);
                 st.count -= st.dead;
                 st.dead = 0u;
-                st.aabb_min[0] = st.aabb_min[1] = st.aabb_min[2] = 0xFFFFFFFFu;
+                st.aabb_min_inv[0] = st.aabb_min_inv[1] = st.aabb_min_inv[2] = 0u;
                 st.aabb_max[0] = st.aabb_max[1] = st.aabb_max[2] = 0u;
             }
             if (what & kPlanAppend) {
@@ -167,6 +167,25 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
     uint32_t total;
     block_inclusive_scan(my_total, warp_sums, total);
     if (threadIdx.x == 0) t.plan->total_update = total;
+}
+
+// ------------------------------------------------------------------------------------------
+// The state of a stream for THIS frame as a pure function of last frame's buffer and this
+// frame's spawn count (the fast path has no plan kernel): deaths of the last update advance the
+// head of a FIFO ring (a compacting ring already moved its survivors to the front), spawns are
+// appended, clamped to the ring's room (the host grows rings before that can happen).
+struct Derived {
+    uint32_t head, c0, n_update, dropped;
+};
+__device__ __forceinline__ Derived derive_state(const StreamState &old, const StreamDesc &d, uint32_t spawn) {
+    Derived r;
+    const bool fifo = (d.variant == kFifo || d.variant == kFifoCollide);
+    r.head = fifo ? wrap(old.head + old.dead, d.capacity) : old.head;
+    r.c0 = old.count - old.dead;
+    const uint32_t room = d.capacity - r.c0;
+    r.dropped = spawn > room ? spawn - room : 0u;
+    r.n_update = r.c0 + (spawn - r.dropped);
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -263,11 +282,22 @@ __global__ void __launch_bounds__(256, 5) spawn_kernel(DeviceTables t, FrameDevi
             while (c + 1u < ph.cmd_end && f.cmds[c + 1u].first <= g) c++;
             const SpawnCmd cmd = f.cmds[c];
             const StreamDesc d = t.descs[cmd.stream];
-            const StreamState st = t.states[cmd.stream];
-            const uint32_t logical = st.spawn_base + cmd.dst_off + (g - cmd.first);
-            if (logical < st.count) { // else dropped by the overflow clamp of the plan kernel
+            uint32_t head, spawn_base, count;
+            if (f.header->derive) {
+                const Derived dv = derive_state(t.states_prev[cmd.stream], d, f.spawn_per_slot[cmd.stream]);
+                head = dv.head;
+                spawn_base = dv.c0;
+                count = dv.n_update;
+            } else {
+                const StreamState st = t.states[cmd.stream];
+                head = st.head;
+                spawn_base = st.spawn_base;
+                count = st.count;
+            }
+            const uint32_t logical = spawn_base + cmd.dst_off + (g - cmd.first);
+            if (logical < count) { // else dropped by the overflow clamp
                 const SpawnerInput in = f.inputs[cmd.input_idx];
-                emit_particle(t, t.emitters[cmd.emitter_idx], t.settings[cmd.stream], d, wrap(st.head + logical, d.capacity),
+                emit_particle(t, t.emitters[cmd.emitter_idx], t.settings[cmd.stream], d, wrap(head + logical, d.capacity),
                               v3(in.translation[0], in.translation[1], in.translation[2]),
                               Q4{in.rotation[0], in.rotation[1], in.rotation[2], in.rotation[3]},
                               v3(in.parent_velocity[0], in.parent_velocity[1], in.parent_velocity[2]), in.modifier_scale,
@@ -425,7 +455,9 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
 
 struct TileRef {
     uint32_t stream;
-    uint32_t tile; // tile index inside the stream
+    uint32_t tile;     // tile index inside the stream
+    uint32_t head;     // ring head for this frame
+    uint32_t n_update; // particles of the stream entering this frame's update
 };
 // stream owning update tile `tile` of a variant: last s with prefix[s] <= tile (prefix[n] > tile)
 __device__ __forceinline__ TileRef find_tile(const uint32_t *__restrict__ prefix, uint32_t n_slots, uint32_t tile) {
@@ -434,7 +466,32 @@ __device__ __forceinline__ TileRef find_tile(const uint32_t *__restrict__ prefix
         const uint32_t mid = (lo + hi) >> 1;
         if (prefix[mid] <= tile) lo = mid; else hi = mid;
     }
-    return TileRef{lo, tile - prefix[lo]};
+    return TileRef{lo, tile - prefix[lo], 0u, 0u};
+}
+// thread 0 of a CTA: everything the CTA needs to know about an upcoming tile. On the derive
+// path the first tile of a stream also publishes the stream's state for this frame.
+__device__ __forceinline__ TileRef prepare_tile(const DeviceTables &t, const FrameDeviceInputs &f, const uint32_t *prefix,
+                                                uint32_t n_slots, uint32_t tile, bool derive) {
+    TileRef r = find_tile(prefix, n_slots, tile);
+    StreamState *stp = &t.states[r.stream];
+    if (derive) {
+        const StreamState old = t.states_prev[r.stream];
+        const Derived dv = derive_state(old, t.descs[r.stream], f.spawn_per_slot[r.stream]);
+        r.head = dv.head;
+        r.n_update = dv.n_update;
+        if (r.tile == 0u) {
+            stp->head = dv.head;
+            stp->count = dv.n_update;
+            stp->spawn_base = dv.c0;
+            stp->overflow = old.overflow + dv.dropped;
+            atomicAdd(&t.plan->total_update, dv.n_update);
+            if (dv.dropped) atomicOr(&t.plan->error_flags, kErrOverflow);
+        }
+    } else {
+        r.head = stp->head;
+        r.n_update = stp->count;
+    }
+    return r;
 }
 
 struct alignas(16) UpdateSmem {
@@ -455,18 +512,20 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
     update_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant) {
     __shared__ UpdateSmem sm;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t n_tiles = t.plan->n_tiles[variant];
+    const bool derive = f.header->derive != 0u;
+    const uint32_t n_tiles = derive ? f.header->host_n_tiles[variant] : t.plan->n_tiles[variant];
     if (blockIdx.x >= n_tiles) return;
-    const uint32_t tile_base = t.plan->tile_base[variant];
+    const uint32_t tile_base = derive ? f.header->host_tile_base[variant] : t.plan->tile_base[variant];
     const uint32_t n_slots = f.header->n_slots;
-    const uint32_t *prefix = t.tile_prefix + (size_t)variant * (t.slots_cap + 1u);
+    const uint32_t *prefix = derive ? f.host_tile_prefix + (size_t)variant * (n_slots + 1u)
+                                    : t.tile_prefix + (size_t)variant * (t.slots_cap + 1u);
     const float dt = f.header->dt;
     const uint32_t epoch = f.header->epoch;
 
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
-        const TileRef r = find_tile(prefix, n_slots, blockIdx.x);
+        const TileRef r = prepare_tile(t, f, prefix, n_slots, blockIdx.x, derive);
         sm.ref[0] = r;
         bulk_load(&sm.settings[0], &t.settings[r.stream], sizeof(DevParticleSettings), &sm.bar[0]);
     }
@@ -477,7 +536,7 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         const TileRef e = sm.ref[buf];
         const StreamDesc d = t.descs[e.stream];
         StreamState *stp = &t.states[e.stream];
-        const uint32_t head = stp->head, n_update = stp->count;
+        const uint32_t head = e.head, n_update = e.n_update;
         const StreamArrays a = stream_arrays(d.base, d.capacity);
         const uint32_t tile_first = e.tile * kTile;
         const uint32_t i = tile_first + tid;
@@ -502,7 +561,7 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         // next tile: stream lookup + settings prefetch into the other buffer (every thread left
         // that buffer at the __syncthreads closing the previous iteration)
         if (tid == 0 && tile + gridDim.x < n_tiles) {
-            const TileRef r = find_tile(prefix, n_slots, tile + gridDim.x);
+            const TileRef r = prepare_tile(t, f, prefix, n_slots, tile + gridDim.x, derive);
             sm.ref[buf ^ 1u] = r;
             bulk_load(&sm.settings[buf ^ 1u], &t.settings[r.stream], sizeof(DevParticleSettings), &sm.bar[buf ^ 1u]);
         }
@@ -576,10 +635,10 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
                 mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
                 mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
             }
-            if (lane < 3u) {
-                const uint32_t lo = lane == 0 ? mn[0] : (lane == 1 ? mn[1] : mn[2]);
+            if (lane < 3u) { // zero = empty, so the minimum is kept as max of the inverted encoding
+                const uint32_t lo_inv = ~(lane == 0 ? mn[0] : (lane == 1 ? mn[1] : mn[2]));
                 const uint32_t hi = lane == 0 ? mx[0] : (lane == 1 ? mx[1] : mx[2]);
-                if (lo < stp->aabb_min[lane]) atomicMin(&stp->aabb_min[lane], lo);
+                if (lo_inv > stp->aabb_min_inv[lane]) atomicMax(&stp->aabb_min_inv[lane], lo_inv);
                 if (hi > stp->aabb_max[lane]) atomicMax(&stp->aabb_max[lane], hi);
             }
         }
@@ -597,7 +656,8 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
                 tile_alive += n;
             }
             if (tid == 0) {
-                const uint32_t tile_valid = min(n_update - tile_first, (uint32_t)kTile);
+                // (the host's tile table holds upper bounds: a tile may lie entirely past the count)
+                const uint32_t tile_valid = tile_first < n_update ? min(n_update - tile_first, (uint32_t)kTile) : 0u;
                 const uint32_t tile_dead = tile_valid - tile_alive;
                 unsigned long long *status = t.lookback + tile_base + tile;
                 const unsigned long long tag = (unsigned long long)epoch << 34;
