@@ -229,6 +229,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extract", action="store_true", help="also time the full instance-row extract (D2H)")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernel by kernel instead of replaying frame graphs")
+    ap.add_argument("--no-concurrent-spawn", action="store_true", help="run the spawn kernel before the update kernel")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank runs the whole workload (default); strong: the workload's spawners are "
                          "sharded over the ranks (BASELINE config 3: 10 M particles over 1..8 GPUs)")
@@ -271,7 +272,8 @@ def main():
 
     from bevy_firework_b200._native import Engine
 
-    eng = Engine(device=local_rank, seed=W.SEED, profile=False, graphs=not args.no_graphs)  # raises without the CUDA library
+    eng = Engine(device=local_rank, seed=W.SEED, profile=False, graphs=not args.no_graphs,
+                 concurrent_spawn=not args.no_concurrent_spawn)  # raises without the CUDA library
     sc = Scene(eng, args.workload, rank, shard=(world, rank) if args.scaling == "strong" and world > 1 else None)
     for _ in range(sc.fill_frames):  # reach the stationary live count (lifetime/dt + 2 frames)
         sc.step()
@@ -375,7 +377,8 @@ def main():
             "config": {"workload": sc.label, "dt": "fl32(1/60)", "live_particles": live_all, "seed": hex(W.SEED),
                        "streams_per_gpu": len(sc.spawners) or 151, "parallelism": f"shard-by-spawner x{world}",
                        "l2": "state per GPU (1.6 GB at C3) is larger than the 126 MB L2; no flush between steps",
-                       "fill_frames": sc.fill_frames, "cuda_graphs": not args.no_graphs},
+                       "fill_frames": sc.fill_frames, "cuda_graphs": not args.no_graphs,
+                       "concurrent_spawn": not args.no_concurrent_spawn},
             "e2e": {"value": updated_e2e_all / (ms_e2e_all * 1e-3), "unit": "particles/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "what": "fw_frame with host input structs + fw_counts_all/fw_read_aabb (sync + D2H) every step"},

@@ -29,6 +29,7 @@ FW_TRANSFORM_GLOBAL, FW_TRANSFORM_LOCAL = 0, 1
 FW_COLLIDER_CUBOID, FW_COLLIDER_SPHERE = 0, 1
 FW_FLAG_PROFILE = 1
 FW_FLAG_NO_GRAPHS = 2
+FW_FLAG_NO_CONCURRENT_SPAWN = 4
 
 f32 = C.c_float
 u32 = C.c_uint32

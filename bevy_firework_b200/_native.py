@@ -72,14 +72,15 @@ class Engine:
     """One ``fw_context``: all particle state of one GPU."""
 
     def __init__(self, device: int = 0, seed: int = 0x00F12E00, profile: bool = False,
-                 external_stream: Optional[int] = None, graphs: bool = True):
+                 external_stream: Optional[int] = None, graphs: bool = True, concurrent_spawn: bool = True):
         self._L = load_library()
         cfg = _abi.fw_config()
         cfg.abi_version = _abi.FW_ABI_VERSION
         cfg.device = device
         cfg.seed = seed
         cfg.external_stream = external_stream
-        cfg.flags = (_abi.FW_FLAG_PROFILE if profile else 0) | (0 if graphs else _abi.FW_FLAG_NO_GRAPHS)
+        cfg.flags = ((_abi.FW_FLAG_PROFILE if profile else 0) | (0 if graphs else _abi.FW_FLAG_NO_GRAPHS)
+                     | (0 if concurrent_spawn else _abi.FW_FLAG_NO_CONCURRENT_SPAWN))
         self._ctx = C.c_void_p()
         rc = self._L.fw_create(C.byref(cfg), C.byref(self._ctx))
         if rc != _abi.FW_OK:

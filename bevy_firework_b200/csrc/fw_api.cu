@@ -76,7 +76,9 @@ struct FrameSlot {
     StreamState *states_host = nullptr; // = readback + sizeof(PlanOut)
     uint32_t states_slots = 0;
     PlanOut *plan_host = nullptr;       // = readback
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr;       // the frame's state readback has landed (recorded on the copy stream)
+    cudaEvent_t ev_h2d = nullptr;     // the frame's parameter block is on the device (copy stream)
+    cudaEvent_t ev_kernels = nullptr; // the frame's kernels are done (main stream)
     bool in_flight = false;
     uint64_t frame = 0;
     std::vector<uint32_t> spawn_per_slot; // host copy (all phases summed), for the n_hi bound
@@ -99,6 +101,12 @@ struct fw_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
+    // forked branch of a frame: spawn_kernel<STEP> runs here concurrently with update_kernel
+    cudaStream_t side_stream = nullptr;
+    // parameter uploads and state readbacks run here, overlapping the neighbouring frames' kernels
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool concurrent_spawn = true;
     uint64_t seed = 0;
     uint32_t flags = 0;
     std::string error;
@@ -189,6 +197,13 @@ inline void topo_changed(fw_context *ctx) {
     ctx->topo_stable_frames = 0;
 }
 
+// wait for everything the context has enqueued (kernels on the main stream, then the readbacks
+// that follow them on the copy stream)
+inline cudaError_t sync_all(fw_context *ctx) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && ctx->copy_stream) e = cudaStreamSynchronize(ctx->copy_stream);
+    return e;
+}
 inline size_t statebuf_bytes(uint32_t slots) { return sizeof(PlanOut) + sizeof(StreamState) * (size_t)slots; }
 inline int cur_buf(const fw_context *ctx) { return (int)(ctx->frame_no & 1u); }
 inline StreamState *states_of(fw_context *ctx, int i) { return (StreamState *)(ctx->d_statebuf[i] + sizeof(PlanOut)); }
@@ -308,7 +323,7 @@ int grow_device_array(fw_context *ctx, T *&ptr, uint32_t old_n, uint32_t new_n) 
     CU(ctx, cudaMalloc((void **)&np, sizeof(T) * (size_t)new_n));
     CU(ctx, cudaMemsetAsync(np, 0, sizeof(T) * (size_t)new_n, ctx->stream));
     if (ptr && old_n) CU(ctx, cudaMemcpyAsync(np, ptr, sizeof(T) * (size_t)old_n, cudaMemcpyDeviceToDevice, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     if (ptr) CU(ctx, cudaFree(ptr));
     ptr = np;
     return FW_OK;
@@ -325,7 +340,7 @@ int ensure_slots(fw_context *ctx, uint32_t need) {
         CU(ctx, cudaMalloc((void **)&nb, statebuf_bytes(ncap)));
         CU(ctx, cudaMemsetAsync(nb, 0, statebuf_bytes(ncap), ctx->stream));
         if (ctx->d_statebuf[i]) CU(ctx, cudaMemcpyAsync(nb, ctx->d_statebuf[i], statebuf_bytes(ctx->slots_cap), cudaMemcpyDeviceToDevice, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, sync_all(ctx));
         if (ctx->d_statebuf[i]) CU(ctx, cudaFree(ctx->d_statebuf[i]));
         ctx->d_statebuf[i] = nb;
     }
@@ -357,7 +372,7 @@ int ensure_tiles(fw_context *ctx) {
     uint64_t ncap = std::max<uint64_t>(4096, (uint64_t)ctx->tiles_cap * 2);
     while (ncap < need) ncap *= 2;
     if (ncap > 0xFFFFFFFFull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "tile table too large");
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     if (ctx->d_lookback) CU(ctx, cudaFree(ctx->d_lookback));
     ctx->d_lookback = nullptr;
     CU(ctx, cudaMalloc((void **)&ctx->d_lookback, sizeof(unsigned long long) * ncap));
@@ -479,7 +494,7 @@ int refresh_exact(fw_context *ctx) {
             return FW_OK;
         }
     }
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     for (FrameSlot &fs : ctx->ring) fs.in_flight = false;
     ctx->snapshot.resize(ctx->n_slots);
     if (ctx->n_slots)
@@ -635,7 +650,7 @@ Spawner *find(fw_context *ctx, uint32_t key) {
 // device staging buffer for ParticleData / ParticleInstance rows of one stream
 int ensure_stage(fw_context *ctx, size_t bytes) {
     if (bytes <= ctx->stage_bytes) return FW_OK;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     if (ctx->d_stage) CU(ctx, cudaFree(ctx->d_stage));
     ctx->d_stage = nullptr;
     ctx->stage_bytes = 0;
@@ -699,6 +714,7 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
     } ctx{new fw_context()};
     ctx.c->device = cfg->device;
     fw_context *c = ctx.c;
+    c->concurrent_spawn = (cfg->flags & FW_FLAG_NO_CONCURRENT_SPAWN) == 0;
     c->seed = cfg->seed;
     c->flags = cfg->flags;
     c->use_graphs = (cfg->flags & FW_FLAG_NO_GRAPHS) == 0;
@@ -710,8 +726,14 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
         CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->owns_stream = true;
     }
+    CU(c, cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (FrameSlot &fs : c->ring) {
         CU(c, cudaEventCreateWithFlags(&fs.done, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&fs.ev_h2d, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&fs.ev_kernels, cudaEventDisableTiming));
         for (auto &ev : fs.ev) CU(c, cudaEventCreate(&ev));
     }
     int rc;
@@ -727,7 +749,7 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
 int fw_destroy(fw_context *ctx) {
     if (!ctx) return FW_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    sync_all(ctx);
     for (auto &sp : ctx->spawners)
         for (Stream &st : sp->streams) {
             if (st.block.base) cudaFree(st.block.base);
@@ -741,6 +763,8 @@ int fw_destroy(fw_context *ctx) {
         if (fs.readback) cudaFreeHost(fs.readback);
         if (fs.graph_exec) cudaGraphExecDestroy(fs.graph_exec);
         if (fs.done) cudaEventDestroy(fs.done);
+        if (fs.ev_h2d) cudaEventDestroy(fs.ev_h2d);
+        if (fs.ev_kernels) cudaEventDestroy(fs.ev_kernels);
         for (auto &ev : fs.ev)
             if (ev) cudaEventDestroy(ev);
     }
@@ -762,6 +786,16 @@ int fw_destroy(fw_context *ctx) {
     for (auto &ev : ctx->user_events)
         if (ev) cudaEventDestroy(ev);
     if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
+    if (ctx->side_stream) {
+        cudaStreamSynchronize(ctx->side_stream);
+        cudaStreamDestroy(ctx->side_stream);
+    }
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FW_OK;
@@ -925,7 +959,7 @@ int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) 
     if (n && !colliders) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_set_colliders: null");
     for (uint32_t i = 0; i < n; i++)
         if (colliders[i].kind > FW_COLLIDER_SPHERE) return fail(ctx, FW_ERR_UNSUPPORTED, "collider %u: only cuboids and spheres are supported", i);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     if (ctx->d_colliders) CU(ctx, cudaFree(ctx->d_colliders));
     ctx->d_colliders = nullptr;
     ctx->n_colliders = n;
@@ -1113,7 +1147,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     }
     if (scratch_need > 0xFFFFFF00ull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "nested emission scratch too large");
     if (scratch_need > ctx->nested_scratch_cap) {
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, sync_all(ctx));
         if (ctx->d_nested_scratch) CU(ctx, cudaFree(ctx->d_nested_scratch));
         ctx->d_nested_scratch = nullptr;
         ctx->nested_scratch_cap = scratch_need + scratch_need / 2 + 4096;
@@ -1121,7 +1155,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
         topo_changed(ctx);
     }
     if (ctx->live_nested > ctx->nested_out_cap) {
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, sync_all(ctx));
         if (ctx->d_nested_out) CU(ctx, cudaFree(ctx->d_nested_out));
         ctx->d_nested_out = nullptr;
         ctx->nested_out_cap = std::max(64u, ctx->live_nested * 2);
@@ -1168,6 +1202,14 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     // table of upper bounds: ceil(n_hi / tile) per stream, n_hi >= the stream's real count.
     const bool derive = n_phases == 1;
     h->derive = derive ? 1u : 0u;
+    // Concurrent spawn+step: when every stream is a plain FIFO ring (no compaction, no collision)
+    // the spawn kernel also gives its new particles their first update, so it needs no ordering
+    // against the update kernel (which then only covers older particles) and runs on a forked
+    // branch. Timed (profiling) frames stay sequential so that kernels are timed in isolation.
+    const bool step_in_spawn = derive && ctx->concurrent_spawn && !ctx->profiling && ctx->variant_streams[kFifo] > 0 &&
+                               ctx->variant_streams[kCompact] == 0 && ctx->variant_streams[kFifoCollide] == 0 &&
+                               ctx->variant_streams[kCompactCollide] == 0;
+    h->step_in_spawn = step_in_spawn ? 1u : 0u;
     if (derive) {
         uint32_t *hp = (uint32_t *)(fs.host + off_prefix);
         uint32_t base = 0;
@@ -1178,7 +1220,11 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
                 for (uint32_t s = 0; s < n_slots; s++) {
                     pv[s] = run;
                     const Stream *st = ctx->slot_owner[s];
-                    if (st && st->variant == v) run += (uint32_t)((std::min<uint64_t>(st->n_hi, st->block.capacity) + kTile - 1) / kTile);
+                    if (st && st->variant == v) {
+                        // upper bound of the particles the update kernel covers in this stream
+                        const uint64_t covered = step_in_spawn ? st->n_hi - std::min<uint64_t>(st->n_hi, add[s]) : st->n_hi;
+                        run += (uint32_t)((std::min<uint64_t>(covered, st->block.capacity) + kTile - 1) / kTile);
+                    }
                 }
                 pv[n_slots] = run;
             }
@@ -1253,8 +1299,8 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     // depend on this particular frame's counts
     auto enqueue = [&](bool replay) -> int {
         launches = 0;
+        bool forked = false;
         CU(ctx, cudaMemsetAsync(ctx->d_statebuf[new_buf], 0, statebuf_bytes(n_slots), ctx->stream));
-        CU(ctx, cudaMemcpyAsync(fs.dev, fs.host, bytes, cudaMemcpyHostToDevice, ctx->stream));
         if (prof) CU(ctx, cudaEventRecord(fs.ev[0], ctx->stream));
         const bool single = n_phases == 1;
         if (!derive) { // nested emitters: last frame's buffer -> this frame's buffer, phase 0 appended
@@ -1268,7 +1314,15 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
                 launches++;
             }
             if (replay || phase_total[p]) {
-                CU(ctx, launch_spawn(t, f, p, replay ? 0xFFFFFFFFu : (uint32_t)phase_total[p], ctx->stream));
+                if (step_in_spawn) { // fork: the spawn+step kernel is independent of the update kernel
+                    CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+                    CU(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+                    CU(ctx, launch_spawn(t, f, p, replay ? 0xFFFFFFFFu : (uint32_t)phase_total[p], true, ctx->side_stream));
+                    CU(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+                    forked = true;
+                } else {
+                    CU(ctx, launch_spawn(t, f, p, replay ? 0xFFFFFFFFu : (uint32_t)phase_total[p], false, ctx->stream));
+                }
                 launches++;
             }
             const uint32_t nn = replay ? nested_slots[p] : (uint32_t)nested[p].size();
@@ -1287,11 +1341,20 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
             CU(ctx, launch_update(t, f, v, ctx->grids[v], ctx->stream));
             launches++;
         }
+        if (forked) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); // join
         if (prof) CU(ctx, cudaEventRecord(fs.ev[3], ctx->stream));
-        // asynchronous readback of [PlanOut | stream states] (bounds for the next frames, counts)
-        CU(ctx, cudaMemcpyAsync(fs.readback, ctx->d_statebuf[new_buf], statebuf_bytes(n_slots), cudaMemcpyDeviceToHost, ctx->stream));
         return FW_OK;
     };
+    // The parameter upload depends on nothing the GPU computes: it goes to the copy stream and
+    // overlaps the previous frame's kernels. The kernels wait for it, and for the readback of
+    // frame f-2, which read the state buffer this frame is about to zero and rewrite.
+    CU(ctx, cudaMemcpyAsync(fs.dev, fs.host, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(ctx, cudaEventRecord(fs.ev_h2d, ctx->copy_stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->stream, fs.ev_h2d, 0));
+    {
+        const FrameSlot &two_back = ctx->ring[(ctx->frame_no + kRing - 2) % kRing];
+        if (ctx->frame_no >= 2 && two_back.frame + 2 == ctx->frame_no + 1) CU(ctx, cudaStreamWaitEvent(ctx->stream, two_back.done, 0));
+    }
     ctx->topo_stable_frames++;
     if (ctx->use_graphs && !prof && ctx->topo_stable_frames > kGraphWarmFrames) {
         if (!fs.graph_exec || fs.graph_version != ctx->topo_version) {
@@ -1326,7 +1389,12 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
         int rc = enqueue(false);
         if (rc) return rc;
     }
-    CU(ctx, cudaEventRecord(fs.done, ctx->stream));
+    // asynchronous readback of [PlanOut | stream states] (counts, AABBs, bounds for the next
+    // frames) on the copy stream: the next frame's kernels only read this buffer
+    CU(ctx, cudaEventRecord(fs.ev_kernels, ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, fs.ev_kernels, 0));
+    CU(ctx, cudaMemcpyAsync(fs.readback, ctx->d_statebuf[new_buf], statebuf_bytes(n_slots), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(ctx, cudaEventRecord(fs.done, ctx->copy_stream));
     ctx->snapshot_valid = false;
     ctx->readback_is_current = true;
     ctx->frame_no++;
@@ -1343,7 +1411,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
 
 int fw_sync(fw_context *ctx) {
     ENTER(ctx);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     for (FrameSlot &fs : ctx->ring) {
         if (!fs.plan_host) continue;
         ctx->device_error_flags |= fs.plan_host->error_flags;
@@ -1439,7 +1507,7 @@ int fw_read_particles(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_
     // pbr is a copy of the type's setting (src/core.rs:462)
     CU(ctx, launch_gather_particles((uint8_t *)st.block.base, st.block.capacity, first, live, st.ps.pbr, (fw_particle_data *)ctx->d_stage, ctx->stream));
     CU(ctx, cudaMemcpyAsync(out, ctx->d_stage, (size_t)live * sizeof(fw_particle_data), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     return FW_OK;
 }
 
@@ -1481,7 +1549,7 @@ int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_pa
     StreamState ns{};
     ns.count = (uint32_t)n;
     CU(ctx, cudaMemcpyAsync(cur_states(ctx) + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     st.n_hi = n;
     st.born_frame = ctx->frame_no + 1;
     st.injected = true;
@@ -1510,7 +1578,7 @@ int fw_read_instances(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_
     t.states = cur_states(ctx);
     CU(ctx, launch_pack_instances(t, st.slot, st.slot + 1, (float4 *)(ctx->d_stage + hdr), live, (unsigned long long *)ctx->d_stage, ctx->stream));
     CU(ctx, cudaMemcpyAsync(out, ctx->d_stage + hdr, (size_t)live * 64, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     return FW_OK;
 }
 
@@ -1530,7 +1598,7 @@ int fw_read_destroyed(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_
     if ((rc = ensure_stage(ctx, (size_t)dead * sizeof(fw_particle_data)))) return rc;
     CU(ctx, launch_gather_particles((uint8_t *)st.destroyed.base, st.destroyed.capacity, 0, dead, st.ps.pbr, (fw_particle_data *)ctx->d_stage, ctx->stream));
     CU(ctx, cudaMemcpyAsync(out, ctx->d_stage, (size_t)dead * sizeof(fw_particle_data), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     return FW_OK;
 }
 
@@ -1562,7 +1630,7 @@ int fw_pack_instances_device(fw_context *ctx, void *device_dst, uint64_t cap_row
     ENTER(ctx);
     if (!device_dst && cap_rows) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_pack_instances_device: null destination");
     if (ctx->pack_cap < ctx->n_slots + 2) {
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, sync_all(ctx));
         if (ctx->d_pack) CU(ctx, cudaFree(ctx->d_pack));
         ctx->d_pack = nullptr;
         ctx->pack_cap = std::max(1024u, (ctx->n_slots + 2) * 2);
@@ -1574,7 +1642,7 @@ int fw_pack_instances_device(fw_context *ctx, void *device_dst, uint64_t cap_row
     t.states = cur_states(ctx);
     CU(ctx, launch_pack_instances(t, 0, ctx->n_slots, (float4 *)device_dst, cap_rows, ctx->d_pack, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->h_pack, ctx->d_pack, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     if (n_rows) *n_rows = *ctx->h_pack;
     if (*ctx->h_pack > cap_rows) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_pack_instances_device: %llu rows, room for %llu", *ctx->h_pack, (unsigned long long)cap_rows);
     return FW_OK;
@@ -1587,7 +1655,7 @@ int fw_extract_instances(fw_context *ctx, void *host_dst, uint64_t cap_rows, uin
     for (auto &sp : ctx->spawners)
         for (Stream &st : sp->streams) bound += std::min<uint64_t>(st.n_hi, st.block.capacity);
     if (bound > ctx->extract_cap) {
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, sync_all(ctx));
         if (ctx->d_extract) CU(ctx, cudaFree(ctx->d_extract));
         ctx->d_extract = nullptr;
         ctx->extract_cap = bound + bound / 8 + 1024;
@@ -1600,7 +1668,7 @@ int fw_extract_instances(fw_context *ctx, void *host_dst, uint64_t cap_rows, uin
     if (n > cap_rows) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_extract_instances: %llu rows, room for %llu", (unsigned long long)n, (unsigned long long)cap_rows);
     if (n) {
         CU(ctx, cudaMemcpyAsync(host_dst, ctx->d_extract, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, sync_all(ctx));
     }
     return FW_OK;
 }
@@ -1629,7 +1697,7 @@ int fw_set_profiling(fw_context *ctx, uint32_t on) {
 
 int fw_profile_last(fw_context *ctx, fw_frame_profile *out) {
     ENTER(ctx);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_all(ctx));
     // absorb in submission order
     for (uint32_t k = 0; k < kRing; k++) absorb_profile(ctx, ctx->ring[(ctx->frame_no + k) % kRing]);
     if (out) *out = ctx->prof_last;

@@ -197,7 +197,7 @@ struct FrameHeader {
     // derive head / counts from the previous state buffer and the update tiles come from a
     // host-built table of UPPER BOUNDS (tiles past a stream's real count exit at once).
     uint32_t derive;
-    uint32_t pad;
+    uint32_t step_in_spawn; // derive path only: spawn_kernel<STEP> runs concurrently with update_kernel
     uint32_t host_n_tiles[kNumVariants];
     uint32_t host_tile_base[kNumVariants];
     PhaseInfo phase[kMaxPhases];
@@ -250,7 +250,9 @@ constexpr uint32_t kPlanDeaths = 1u, kPlanAppend = 2u, kPlanTiles = 4u;
 cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant_mask, uint32_t what,
                         uint32_t phase, cudaStream_t s);
 // total_spawn: particles of the phase, or 0xFFFFFFFF = unknown at launch time (graph replay)
-cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, cudaStream_t s);
+// step: the kernel also applies this frame's update to the particles it creates (see spawn_kernel)
+cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, bool step,
+                         cudaStream_t s);
 // the nested emitters of a phase: count per parent, scan + append, spawn the children
 cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t n_cmds, cudaStream_t s);
 cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, cudaStream_t s);

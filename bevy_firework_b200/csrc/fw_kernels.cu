@@ -192,10 +192,29 @@ __device__ __forceinline__ Derived derive_state(const StreamState &old, const St
 // One new particle: the shared body of reference src/core.rs:437-469 (Global: origin = the
 // spawner transform, inherited velocity = parent_velocity) and :506-544 (Nested: origin = the
 // parent particle). Draws 0..11 in the reference's draw order.
-__device__ __forceinline__ void emit_particle(const DeviceTables &t, const fw_emission_settings &es, const DevParticleSettings &ps,
-                                              const StreamDesc &d, uint32_t slot, V3 origin_translation, Q4 origin_rotation,
-                                              V3 inherited_velocity, float modifier_scale, float modifier_speed,
-                                              uint32_t spawner_key, uint32_t emitter_local, uint64_t serial) {
+struct ParticleRegs { // one particle in the pack layout
+    float4 m0, m1, m2;
+    float2 m3, k;
+    float4 o0, o1;
+    float o2;
+};
+__device__ __forceinline__ void store_particle(const StreamDesc &d, uint32_t slot, const ParticleRegs &p, bool init_lea) {
+    const StreamArrays a = stream_arrays(d.base, d.capacity);
+    a.m0[slot] = p.m0;
+    a.m1[slot] = p.m1;
+    a.m2[slot] = p.m2;
+    a.m3[slot] = p.m3;
+    if (init_lea) a.k[slot] = p.k; // (also: constants are only written at spawn)
+    a.o0[slot] = p.o0;
+    a.o1[slot] = p.o1;
+    a.o2[slot] = p.o2;
+    if (init_lea)
+        for (uint32_t j = 0; j < d.n_lea; j++) lea_array(d.base, d.capacity, j)[slot] = kF32Min; // :467
+}
+__device__ __forceinline__ ParticleRegs make_particle(const DeviceTables &t, const fw_emission_settings &es, const DevParticleSettings &ps,
+                                                      V3 origin_translation, Q4 origin_rotation,
+                                                      V3 inherited_velocity, float modifier_scale, float modifier_speed,
+                                                      uint32_t spawner_key, uint32_t emitter_local, uint64_t serial) {
     const uint2 key = make_uint2((uint32_t)t.seed, (uint32_t)(t.seed >> 32));
     const uint32_t c0 = (uint32_t)serial, c1 = (uint32_t)(serial >> 32), c2 = spawner_key;
     const uint4 r0 = philox4x32_10(make_uint4(c0, c1, c2, (emitter_local << 8) | 0u), key);
@@ -244,16 +263,93 @@ __device__ __forceinline__ void emit_particle(const DeviceTables &t, const fw_em
     const float lifetime = u_life * (ps.lifetime.max - ps.lifetime.min) + ps.lifetime.min;
     const V3 av = rand_vec3(es.initial_angular_velocity, u_ang_angle, u_ang_radius, u_ang_mag);
 
-    const StreamArrays a = stream_arrays(d.base, d.capacity);
-    a.m0[slot] = make_float4(position.x, position.y, position.z, 0.0f); // age = 0
-    a.m1[slot] = make_float4(es.initial_rotation[0], es.initial_rotation[1], es.initial_rotation[2], es.initial_rotation[3]);
-    a.m2[slot] = make_float4(velocity.x, velocity.y, velocity.z, av.x);
-    a.m3[slot] = make_float2(av.y, av.z);
-    a.k[slot] = make_float2(lifetime, initial_scale);
-    a.o0[slot] = sample_gradient(ps.base_color, 0.0f);     // :460
-    a.o1[slot] = sample_gradient(ps.emissive_color, 0.0f); // :461
-    a.o2[slot] = initial_scale;                            // scale = initial_scale (:457)
-    for (uint32_t j = 0; j < d.n_lea; j++) lea_array(d.base, d.capacity, j)[slot] = kF32Min; // :467
+    ParticleRegs p;
+    p.m0 = make_float4(position.x, position.y, position.z, 0.0f); // age = 0
+    p.m1 = make_float4(es.initial_rotation[0], es.initial_rotation[1], es.initial_rotation[2], es.initial_rotation[3]);
+    p.m2 = make_float4(velocity.x, velocity.y, velocity.z, av.x);
+    p.m3 = make_float2(av.y, av.z);
+    p.k = make_float2(lifetime, initial_scale);
+    p.o0 = sample_gradient(ps.base_color, 0.0f);     // :460
+    p.o1 = sample_gradient(ps.emissive_color, 0.0f); // :461
+    p.o2 = initial_scale;                            // scale = initial_scale (:457)
+    return p;
+}
+__device__ __forceinline__ void emit_particle(const DeviceTables &t, const fw_emission_settings &es, const DevParticleSettings &ps,
+                                              const StreamDesc &d, uint32_t slot, V3 origin_translation, Q4 origin_rotation,
+                                              V3 inherited_velocity, float modifier_scale, float modifier_speed,
+                                              uint32_t spawner_key, uint32_t emitter_local, uint64_t serial) {
+    store_particle(d, slot, make_particle(t, es, ps, origin_translation, origin_rotation, inherited_velocity, modifier_scale,
+                                          modifier_speed, spawner_key, emitter_local, serial), true);
+}
+
+// ------------------------------------------------------------------------------------------
+// One particle, one frame: reference src/core.rs:591-658 in the reference's order. Returns
+// whether the particle survives; the packs are updated in place, colours / scale are outputs.
+template <bool COLLIDE>
+__device__ __forceinline__ bool step_particle(const DeviceTables &t, const DevParticleSettings &ps, float dt, bool valid, float4 &M0,
+                                              float4 &M1, float4 &M2, float2 &M3, float2 K, float4 &c0, float4 &c1, float &scale,
+                                              float &age_out, bool &destroyed_by_collision) {
+    const float lifetime = K.x, iscale = K.y;
+    const float age = M0.w + dt;              // :594
+    bool alive = valid && !(age >= lifetime); // :596-599
+    age_out = age;
+    destroyed_by_collision = false;
+    if (alive) {
+        const float age_percent = age / lifetime;                   // :601
+        scale = iscale * sample_curve(ps.scale_curve, age_percent); // :602-605
+        V3 pos = v3(M0.x, M0.y, M0.z), vel = v3(M2.x, M2.y, M2.z);
+        bool should_destroy = false;
+        if (COLLIDE) {
+            particle_collision(t.colliders, t.collider_bounds, t.n_colliders, ps.collision, pos, vel, dt, should_destroy); // :608-617
+        } else {
+            pos = pos + vel * dt; // :619-623
+        }
+        if (should_destroy) {
+            alive = false;                              // :636-639: position, velocity and scale
+            destroyed_by_collision = true;              // are already updated
+            M0 = make_float4(pos.x, pos.y, pos.z, age);
+            M2 = make_float4(vel.x, vel.y, vel.z, M2.w);
+        } else {
+            const V3 acc = v3(ps.acceleration[0], ps.acceleration[1], ps.acceleration[2]);
+            vel = vel + (acc - vel * ps.linear_drag) * dt; // :641-643
+            V3 av = v3(M2.w, M3.x, M3.y);
+            const Q4 rot = qmul(q_from_scaled_axis(av * dt), Q4{M1.x, M1.y, M1.z, M1.w}); // :645-647
+            const V3 aacc = v3(ps.angular_acceleration[0], ps.angular_acceleration[1], ps.angular_acceleration[2]);
+            av = av + (aacc - av * ps.angular_drag) * dt;         // :648-650
+            c0 = sample_gradient(ps.base_color, age_percent);     // :652-653
+            c1 = sample_gradient(ps.emissive_color, age_percent); // :654-655
+            M0 = make_float4(pos.x, pos.y, pos.z, age);
+            M1 = make_float4(rot.x, rot.y, rot.z, rot.w);
+            M2 = make_float4(vel.x, vel.y, vel.z, av.x);
+            M3 = make_float2(av.y, av.z);
+        }
+    }
+    return alive;
+}
+// per-stream AABB of position -/+ scale (reference src/render.rs:681-692) for the spawn+step
+// kernel, where the lanes of a warp may belong to different streams: reduce over the lanes of
+// `group` (all of the same stream; every lane of the group must call)
+__device__ __forceinline__ void accumulate_aabb(StreamState *stp, uint32_t group, bool alive, const float4 &M0, float scale) {
+    uint32_t mn[3], mx[3];
+    mn[0] = alive ? enc_f32(M0.x - scale) : 0xFFFFFFFFu;
+    mn[1] = alive ? enc_f32(M0.y - scale) : 0xFFFFFFFFu;
+    mn[2] = alive ? enc_f32(M0.z - scale) : 0xFFFFFFFFu;
+    mx[0] = alive ? enc_f32(M0.x + scale) : 0u;
+    mx[1] = alive ? enc_f32(M0.y + scale) : 0u;
+    mx[2] = alive ? enc_f32(M0.z + scale) : 0u;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        mn[k] = __reduce_min_sync(group, mn[k]);
+        mx[k] = __reduce_max_sync(group, mx[k]);
+    }
+    // zero = empty, so the minimum is kept as the max of the inverted encoding
+    if ((group & ((1u << lane_id()) - 1u)) == 0u) { // the group's first lane
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (~mn[k] > stp->aabb_min_inv[k]) atomicMax(&stp->aabb_min_inv[k], ~mn[k]);
+            if (mx[k] > stp->aabb_max[k]) atomicMax(&stp->aabb_max[k], mx[k]);
+        }
+    }
 }
 
 // spawn (Global emitters): one thread per new particle of the phase
@@ -268,40 +364,87 @@ __device__ __forceinline__ uint32_t find_cmd(const FrameDeviceInputs &f, uint32_
 // grid-stride so the launch configuration is frame-independent (CUDA-graph friendly): the
 // number of new particles is read from the frame header on the device
 // 5 CTAs/SM: the C3 frame spawns 163 k particles = 1.08 waves at 4 CTAs/SM (ncu: 1.10 waves, the
-// tail wave doubled the kernel time); at 5 CTAs/SM it is a single wave
+// tail wave doubled the kernel time); at 5 CTAs/SM it is a single wave.
+// STEP: the kernel also applies this frame's update (src/core.rs:591-658) to the particles it
+// creates, so that it can run CONCURRENTLY with update_kernel, which then only touches older
+// particles (FIFO streams without collision only; the host decides, header.step_in_spawn).
+template <bool STEP>
 __global__ void __launch_bounds__(256, 5) spawn_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t phase) {
     __shared__ uint32_t s_cmd;
     const PhaseInfo ph = f.header->phase[phase];
+    const float dt = f.header->dt;
+    const uint32_t n_slots = f.header->n_slots;
     for (uint32_t base = blockIdx.x * blockDim.x; base < ph.total_spawn; base += gridDim.x * blockDim.x) {
         // one binary search per CTA chunk (a chunk of 256 particles spans very few commands)
         if (threadIdx.x == 0) s_cmd = find_cmd(f, ph.cmd_begin, ph.cmd_end, base);
         __syncthreads();
         const uint32_t g = base + threadIdx.x;
-        if (g < ph.total_spawn) {
+        const bool in_range = g < ph.total_spawn;
+        bool have = false;
+        uint32_t stream = 0xFFFFFFFFu, slot = 0;
+        StreamDesc d{};
+        ParticleRegs p{};
+        if (in_range) {
             uint32_t c = s_cmd;
             while (c + 1u < ph.cmd_end && f.cmds[c + 1u].first <= g) c++;
             const SpawnCmd cmd = f.cmds[c];
-            const StreamDesc d = t.descs[cmd.stream];
+            stream = cmd.stream;
+            d = t.descs[stream];
             uint32_t head, spawn_base, count;
             if (f.header->derive) {
-                const Derived dv = derive_state(t.states_prev[cmd.stream], d, f.spawn_per_slot[cmd.stream]);
+                const StreamState old = t.states_prev[stream];
+                const Derived dv = derive_state(old, d, f.spawn_per_slot[stream]);
                 head = dv.head;
                 spawn_base = dv.c0;
                 count = dv.n_update;
+                if (STEP && cmd.dst_off == 0u && g == cmd.first) {
+                    // a stream without update tiles this frame (no older particles): its first
+                    // new particle publishes the stream state instead of update tile 0
+                    const uint32_t *pv = f.host_tile_prefix + (size_t)d.variant * (n_slots + 1u);
+                    if (pv[stream + 1u] == pv[stream]) {
+                        StreamState *stp = &t.states[stream];
+                        stp->head = dv.head;
+                        stp->count = dv.n_update;
+                        stp->spawn_base = dv.c0;
+                        stp->overflow = old.overflow + dv.dropped;
+                        atomicAdd(&t.plan->total_update, dv.n_update);
+                        if (dv.dropped) atomicOr(&t.plan->error_flags, kErrOverflow);
+                    }
+                }
             } else {
-                const StreamState st = t.states[cmd.stream];
+                const StreamState st = t.states[stream];
                 head = st.head;
                 spawn_base = st.spawn_base;
                 count = st.count;
             }
             const uint32_t logical = spawn_base + cmd.dst_off + (g - cmd.first);
-            if (logical < count) { // else dropped by the overflow clamp
+            have = logical < count; // else dropped by the overflow clamp
+            if (have) {
+                slot = wrap(head + logical, d.capacity);
                 const SpawnerInput in = f.inputs[cmd.input_idx];
-                emit_particle(t, t.emitters[cmd.emitter_idx], t.settings[cmd.stream], d, wrap(head + logical, d.capacity),
-                              v3(in.translation[0], in.translation[1], in.translation[2]),
-                              Q4{in.rotation[0], in.rotation[1], in.rotation[2], in.rotation[3]},
-                              v3(in.parent_velocity[0], in.parent_velocity[1], in.parent_velocity[2]), in.modifier_scale,
-                              in.modifier_speed, cmd.spawner_key, cmd.emitter_local, cmd.serial_base + (g - cmd.first));
+                p = make_particle(t, t.emitters[cmd.emitter_idx], t.settings[stream],
+                                  v3(in.translation[0], in.translation[1], in.translation[2]),
+                                  Q4{in.rotation[0], in.rotation[1], in.rotation[2], in.rotation[3]},
+                                  v3(in.parent_velocity[0], in.parent_velocity[1], in.parent_velocity[2]), in.modifier_scale,
+                                  in.modifier_speed, cmd.spawner_key, cmd.emitter_local, cmd.serial_base + (g - cmd.first));
+            }
+        }
+        if (!STEP) {
+            if (have) store_particle(d, slot, p, true);
+        } else {
+            // first update step of the new particle, then one store of the final state
+            float age;
+            bool by_collision;
+            const bool alive = step_particle<false>(t, t.settings[have ? stream : 0u], dt, have, p.m0, p.m1, p.m2, p.m3, p.k, p.o0, p.o1,
+                                                    p.o2, age, by_collision);
+            if (alive) store_particle(d, slot, p, true);
+            // AABB and death count per stream: lanes of a warp may belong to different streams
+            const uint32_t group = __match_any_sync(0xffffffffu, stream);
+            if (stream != 0xFFFFFFFFu) {
+                StreamState *stp = &t.states[stream];
+                accumulate_aabb(stp, group, alive, p.m0, p.o2);
+                const uint32_t dead_mask = __ballot_sync(group, have && !alive) & group;
+                if (dead_mask && (group & ((1u << lane_id()) - 1u)) == 0u) atomicAdd(&stp->dead, __popc(dead_mask));
             }
         }
         __syncthreads();
@@ -478,7 +621,9 @@ __device__ __forceinline__ TileRef prepare_tile(const DeviceTables &t, const Fra
         const StreamState old = t.states_prev[r.stream];
         const Derived dv = derive_state(old, t.descs[r.stream], f.spawn_per_slot[r.stream]);
         r.head = dv.head;
-        r.n_update = dv.n_update;
+        // concurrent spawn+step (header.step_in_spawn): this frame's new particles get their first
+        // update inside the spawn kernel, the update kernel only covers the older ones
+        r.n_update = f.header->step_in_spawn ? dv.c0 : dv.n_update;
         if (r.tile == 0u) {
             stp->head = dv.head;
             stp->count = dv.n_update;
@@ -568,43 +713,11 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
         const DevParticleSettings &ps = sm.settings[buf];
 
-        // ---- reference src/core.rs:591-658, same order
-        const float lifetime = K.x, iscale = K.y;
-        const float age = M0.w + dt;              // :594
-        bool alive = valid && !(age >= lifetime); // :596-599
+        // ---- reference src/core.rs:591-658
         float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-        float scale = 0.f;
-        bool destroyed_by_collision = false;
-        if (alive) {
-            const float age_percent = age / lifetime;                       // :601
-            scale = iscale * sample_curve(ps.scale_curve, age_percent);     // :602-605
-            V3 pos = v3(M0.x, M0.y, M0.z), vel = v3(M2.x, M2.y, M2.z);
-            bool should_destroy = false;
-            if (COLLIDE) {
-                particle_collision(t.colliders, t.collider_bounds, t.n_colliders, ps.collision, pos, vel, dt, should_destroy); // :608-617
-            } else {
-                pos = pos + vel * dt;                                       // :619-623
-            }
-            if (should_destroy) {
-                alive = false;                                              // :636-639: position,
-                destroyed_by_collision = true;                              // velocity, scale are
-                M0 = make_float4(pos.x, pos.y, pos.z, age);                 // already updated
-                M2 = make_float4(vel.x, vel.y, vel.z, M2.w);
-            } else {
-                const V3 acc = v3(ps.acceleration[0], ps.acceleration[1], ps.acceleration[2]);
-                vel = vel + (acc - vel * ps.linear_drag) * dt;              // :641-643
-                V3 av = v3(M2.w, M3.x, M3.y);
-                const Q4 rot = qmul(q_from_scaled_axis(av * dt), Q4{M1.x, M1.y, M1.z, M1.w}); // :645-647
-                const V3 aacc = v3(ps.angular_acceleration[0], ps.angular_acceleration[1], ps.angular_acceleration[2]);
-                av = av + (aacc - av * ps.angular_drag) * dt;               // :648-650
-                c0 = sample_gradient(ps.base_color, age_percent);           // :652-653
-                c1 = sample_gradient(ps.emissive_color, age_percent);       // :654-655
-                M0 = make_float4(pos.x, pos.y, pos.z, age);
-                M1 = make_float4(rot.x, rot.y, rot.z, rot.w);
-                M2 = make_float4(vel.x, vel.y, vel.z, av.x);
-                M3 = make_float2(av.y, av.z);
-            }
-        }
+        float scale = 0.f, age;
+        bool destroyed_by_collision;
+        bool alive = step_particle<COLLIDE>(t, ps, dt, valid, M0, M1, M2, M3, K, c0, c1, scale, age, destroyed_by_collision);
         // destroyed-particle stream (:588,597,637): the record the handler receives keeps the old
         // colours (and the old scale unless a collision destroyed it); read them before this
         // tile publishes anything, i.e. before later tiles may compact over these slots
@@ -621,7 +734,9 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
         const uint32_t n_alive_w = __popc(alive_mask);
 
-        // ---- per-stream AABB of position -/+ scale (reference src/render.rs:681-692)
+        // ---- per-stream AABB of position -/+ scale (reference src/render.rs:681-692). Measured: this
+        // inline form (one axis per lane, bounds pre-checked through L1) costs nothing, whereas reading
+        // the bounds from L2 first put 10 % on the kernel (profiles/r1_tuning.md)
         {
             uint32_t mn[3], mx[3];
             mn[0] = alive ? enc_f32(M0.x - scale) : 0xFFFFFFFFu;
@@ -635,7 +750,7 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
                 mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
                 mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
             }
-            if (lane < 3u) { // zero = empty, so the minimum is kept as max of the inverted encoding
+            if (lane < 3u) {
                 const uint32_t lo_inv = ~(lane == 0 ? mn[0] : (lane == 1 ? mn[1] : mn[2]));
                 const uint32_t hi = lane == 0 ? mx[0] : (lane == 1 ? mx[1] : mx[2]);
                 if (lo_inv > stp->aabb_min_inv[lane]) atomicMax(&stp->aabb_min_inv[lane], lo_inv);
@@ -823,11 +938,12 @@ cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint3
     plan_kernel<<<1, 1024, 0, s>>>(t, f, variant_mask, what, phase);
     return cudaGetLastError();
 }
-cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, cudaStream_t s) {
+cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, bool step, cudaStream_t s) {
     if (total_spawn == 0) return cudaSuccess;
     const uint32_t fixed = 148u * 5u; // one resident wave; larger counts stride
     const uint32_t blocks = total_spawn == 0xFFFFFFFFu ? fixed : std::min(fixed, (total_spawn + 255u) / 256u);
-    spawn_kernel<<<blocks, 256, 0, s>>>(t, f, phase);
+    if (step) spawn_kernel<true><<<blocks, 256, 0, s>>>(t, f, phase);
+    else spawn_kernel<false><<<blocks, 256, 0, s>>>(t, f, phase);
     return cudaGetLastError();
 }
 cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t n_cmds, cudaStream_t s) {

@@ -213,6 +213,7 @@ typedef struct fw_config {
 
 #define FW_FLAG_PROFILE 1u   /* record CUDA events around every kernel of a frame */
 #define FW_FLAG_NO_GRAPHS 2u /* always launch kernel by kernel (never replay frames as CUDA graphs) */
+#define FW_FLAG_NO_CONCURRENT_SPAWN 4u /* always run the spawn kernel before the update kernel */
 
 typedef struct fw_context fw_context;
 

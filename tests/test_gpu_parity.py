@@ -397,14 +397,15 @@ def test_pack_instances_device(engine):
     assert host.tobytes() == want.tobytes()
 
 
-def test_graph_replay_matches_direct_launches():
-    """frames replayed as CUDA graphs (stable topology) give bit-identical state to
-    kernel-by-kernel launches, including across a topology change mid-run."""
+def test_graph_replay_and_concurrent_spawn_match_plain_launches():
+    """frames replayed as CUDA graphs, and frames whose spawn+first-step kernel runs concurrently
+    with the update kernel, give bit-identical state to plain sequential kernel-by-kernel launches,
+    including across a topology change mid-run."""
     from bevy_firework_b200._native import Engine
 
     results = []
-    for graphs in (True, False):
-        eng = Engine(device=0, seed=1234, graphs=graphs)
+    for graphs, concurrent in ((False, False), (True, True), (False, True), (True, False)):
+        eng = Engine(device=0, seed=1234, graphs=graphs, concurrent_spawn=concurrent)
         sp = stress_spawner(rate=9000.0, lifetime=0.5)
         ps, nt, es, ne = sp.pods()
         eng.spawner_reset(1, ps, nt, es, ne, True)
@@ -414,8 +415,9 @@ def test_graph_replay_matches_direct_launches():
                 eng.spawner_reset(2, ps, nt, es, ne, True)
                 inp.append(frame_input(2, (3.0, 0.1, 0.0)))
             eng.frame(DT, inp)
-        results.append((eng.read_particles(1, 0), eng.read_particles(2, 0), eng.read_aabb(1)))
+        results.append((eng.read_particles(1, 0), eng.read_particles(2, 0), eng.read_aabb(1), eng.read_aabb(2), eng.counts(2)))
         eng.close()
-    assert results[0][0].tobytes() == results[1][0].tobytes()
-    assert results[0][1].tobytes() == results[1][1].tobytes()
-    assert results[0][2] == results[1][2]
+    for r in results[1:]:
+        assert r[0].tobytes() == results[0][0].tobytes()
+        assert r[1].tobytes() == results[0][1].tobytes()
+        assert r[2:] == results[0][2:]
