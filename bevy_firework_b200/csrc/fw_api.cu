@@ -7,6 +7,7 @@
 //
 // There is no CPU fallback: every entry point needs a live CUDA context.
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -131,6 +132,7 @@ struct fw_context {
     fw_collider *d_colliders = nullptr;
     float4 *d_collider_bounds = nullptr;
     uint32_t n_colliders = 0;
+    uint32_t n_bvh_nodes = 0; // 2 float4 per node in d_collider_bounds
     uint32_t *d_tile_prefix = nullptr; // kNumVariants x (slots_cap + 1)
     uint8_t *d_stage = nullptr;        // staging of ParticleData rows (host mirror reads/writes)
     size_t stage_bytes = 0;
@@ -954,6 +956,48 @@ int fw_spawner_remove(fw_context *ctx, uint32_t key) {
     return FW_OK;
 }
 
+// Collider BVH in depth-first order: node k = (nodes[2k] = min.xyz | skip link, nodes[2k+1] =
+// max.xyz | collider index or 0xFFFFFFFF for an inner node); the skip link is the first node
+// after k's subtree (a leaf stores its layers bits there instead: its skip link is k + 1). A non-finite bound (NaN transform) becomes the whole line: it never culls.
+static inline float bvh_sane(float v, float fallback) { return std::isfinite(v) ? v : fallback; }
+static void build_bvh(std::vector<float4> &nodes, std::vector<uint32_t> &order, const std::vector<float> &lo,
+                      const std::vector<float> &hi, const std::vector<uint32_t> &layers, uint32_t begin, uint32_t end) {
+    float blo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    auto centre = [&](uint32_t i, int a) { return 0.5f * bvh_sane(lo[3 * i + a], -FLT_MAX) + 0.5f * bvh_sane(hi[3 * i + a], FLT_MAX); };
+    for (uint32_t k = begin; k < end; k++) {
+        const uint32_t i = order[k];
+        for (int a = 0; a < 3; a++) {
+            blo[a] = std::min(blo[a], bvh_sane(lo[3 * i + a], -FLT_MAX));
+            bhi[a] = std::max(bhi[a], bvh_sane(hi[3 * i + a], FLT_MAX));
+            clo[a] = std::min(clo[a], centre(i, a));
+            chi[a] = std::max(chi[a], centre(i, a));
+        }
+    }
+    const size_t me = nodes.size();
+    nodes.push_back(make_float4(blo[0], blo[1], blo[2], 0.f));
+    nodes.push_back(make_float4(bhi[0], bhi[1], bhi[2], 0.f));
+    uint32_t leaf = 0xFFFFFFFFu;
+    if (end - begin == 1) {
+        leaf = order[begin];
+    } else {
+        int axis = 0;
+        for (int a = 1; a < 3; a++)
+            if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
+        const uint32_t mid = begin + (end - begin) / 2;
+        std::nth_element(order.begin() + begin, order.begin() + mid, order.begin() + end, [&](uint32_t p, uint32_t q) {
+            const float cp = centre(p, axis), cq = centre(q, axis);
+            return cp < cq || (cp == cq && p < q);
+        });
+        build_bvh(nodes, order, lo, hi, layers, begin, mid);
+        build_bvh(nodes, order, lo, hi, layers, mid, end);
+    }
+    const uint32_t skip = (uint32_t)(nodes.size() / 2);
+    const uint32_t link = leaf == 0xFFFFFFFFu ? skip : layers[leaf]; // a leaf's skip link is k + 1
+    memcpy(&nodes[me].w, &link, 4);
+    memcpy(&nodes[me + 1].w, &leaf, 4);
+}
+
 int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) {
     ENTER(ctx);
     if (n && !colliders) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_set_colliders: null");
@@ -963,36 +1007,42 @@ int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) 
     if (ctx->d_colliders) CU(ctx, cudaFree(ctx->d_colliders));
     ctx->d_colliders = nullptr;
     ctx->n_colliders = n;
+    ctx->n_bvh_nodes = 0;
     topo_changed(ctx);
     if (ctx->d_collider_bounds) CU(ctx, cudaFree(ctx->d_collider_bounds));
     ctx->d_collider_bounds = nullptr;
     if (n) {
         CU(ctx, cudaMalloc((void **)&ctx->d_colliders, sizeof(fw_collider) * n));
         CU(ctx, cudaMemcpy(ctx->d_colliders, colliders, sizeof(fw_collider) * n, cudaMemcpyHostToDevice));
-        // broad-phase bounds: world AABB of every collider, inflated well beyond fp32 rounding
-        std::vector<float4> bounds(2 * (size_t)n);
+        // broad phase: world AABB of every collider, inflated well beyond fp32 rounding, under a
+        // binary BVH (median split of the centroids along the widest axis, one collider per leaf)
+        // stored in depth-first order with skip links, so the kernel walks it without a stack
+        std::vector<float> lo(3 * (size_t)n), hi(3 * (size_t)n);
         for (uint32_t i = 0; i < n; i++) {
             const fw_collider &c = colliders[i];
             const double x = c.rotation[0], y = c.rotation[1], z = c.rotation[2], w = c.rotation[3];
             const double R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)},
                                     {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
                                     {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
-            float lo[3], hi[3];
             for (int a = 0; a < 3; a++) {
                 double ext = c.kind == FW_COLLIDER_SPHERE
                                  ? std::fabs((double)c.half_extents[0])
                                  : std::fabs(R[a][0] * c.half_extents[0]) + std::fabs(R[a][1] * c.half_extents[1]) + std::fabs(R[a][2] * c.half_extents[2]);
                 const double margin = 1e-3 + 1e-3 * (std::fabs((double)c.translation[a]) + ext);
-                lo[a] = (float)(c.translation[a] - ext - margin);
-                hi[a] = (float)(c.translation[a] + ext + margin);
+                lo[3 * i + a] = (float)(c.translation[a] - ext - margin);
+                hi[3 * i + a] = (float)(c.translation[a] + ext + margin);
             }
-            float layers_bits;
-            memcpy(&layers_bits, &c.layers, 4);
-            bounds[2 * i] = make_float4(lo[0], lo[1], lo[2], layers_bits);
-            bounds[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
         }
-        CU(ctx, cudaMalloc((void **)&ctx->d_collider_bounds, sizeof(float4) * bounds.size()));
-        CU(ctx, cudaMemcpy(ctx->d_collider_bounds, bounds.data(), sizeof(float4) * bounds.size(), cudaMemcpyHostToDevice));
+        std::vector<float4> nodes;
+        nodes.reserve(4 * (size_t)n);
+        std::vector<uint32_t> order(n);
+        for (uint32_t i = 0; i < n; i++) order[i] = i;
+        std::vector<uint32_t> layers(n);
+        for (uint32_t i = 0; i < n; i++) layers[i] = colliders[i].layers;
+        build_bvh(nodes, order, lo, hi, layers, 0, n);
+        ctx->n_bvh_nodes = (uint32_t)(nodes.size() / 2);
+        CU(ctx, cudaMalloc((void **)&ctx->d_collider_bounds, sizeof(float4) * nodes.size()));
+        CU(ctx, cudaMemcpy(ctx->d_collider_bounds, nodes.data(), sizeof(float4) * nodes.size(), cudaMemcpyHostToDevice));
     }
     return FW_OK;
 }
@@ -1265,6 +1315,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     t.colliders = ctx->d_colliders;
     t.collider_bounds = ctx->d_collider_bounds;
     t.n_colliders = ctx->n_colliders;
+    t.n_bvh_nodes = ctx->n_bvh_nodes;
     t.tile_prefix = ctx->d_tile_prefix;
     t.slots_cap = ctx->slots_cap;
     t.lookback_capacity = ctx->tiles_cap;

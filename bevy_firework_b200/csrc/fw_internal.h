@@ -219,8 +219,9 @@ struct DeviceTables {
     const DevParticleSettings *settings; // indexed by stream slot
     const fw_emission_settings *emitters;
     const fw_collider *colliders;
-    const float4 *collider_bounds; // 2 per collider: inflated world AABB min (+ layers bits), max
+    const float4 *collider_bounds; // collider BVH, 2 float4 per node (see cast_ray in fw_math.cuh)
     uint32_t n_colliders;
+    uint32_t n_bvh_nodes;
     // tile_prefix[v * slots_cap + s] = number of update tiles of variant v in slots < s
     uint32_t *tile_prefix;
     uint32_t slots_cap;

@@ -285,25 +285,25 @@ __device__ __forceinline__ void emit_particle(const DeviceTables &t, const fw_em
 // ------------------------------------------------------------------------------------------
 // One particle, one frame: reference src/core.rs:591-658 in the reference's order. Returns
 // whether the particle survives; the packs are updated in place, colours / scale are outputs.
+// COLLIDE: warp-synchronous (every lane of the warp must call; cand_queue = this thread's column of
+// the CTA's candidate queue, see cast_ray).
 template <bool COLLIDE>
 __device__ __forceinline__ bool step_particle(const DeviceTables &t, const DevParticleSettings &ps, float dt, bool valid, float4 &M0,
                                               float4 &M1, float4 &M2, float2 &M3, float2 K, float4 &c0, float4 &c1, float &scale,
-                                              float &age_out, bool &destroyed_by_collision) {
+                                              float &age_out, bool &destroyed_by_collision, uint32_t *cand_queue = nullptr) {
     const float lifetime = K.x, iscale = K.y;
     const float age = M0.w + dt;              // :594
     bool alive = valid && !(age >= lifetime); // :596-599
     age_out = age;
     destroyed_by_collision = false;
+    V3 pos = v3(M0.x, M0.y, M0.z), vel = v3(M2.x, M2.y, M2.z);
+    bool should_destroy = false;
+    if (COLLIDE) // :608-617, hoisted out of the branch so that the warp stays converged inside
+        particle_collision(t.colliders, t.collider_bounds, t.n_bvh_nodes, ps.collision, alive, pos, vel, dt, cand_queue, should_destroy);
     if (alive) {
         const float age_percent = age / lifetime;                   // :601
         scale = iscale * sample_curve(ps.scale_curve, age_percent); // :602-605
-        V3 pos = v3(M0.x, M0.y, M0.z), vel = v3(M2.x, M2.y, M2.z);
-        bool should_destroy = false;
-        if (COLLIDE) {
-            particle_collision(t.colliders, t.collider_bounds, t.n_colliders, ps.collision, pos, vel, dt, should_destroy); // :608-617
-        } else {
-            pos = pos + vel * dt; // :619-623
-        }
+        if (!COLLIDE) pos = pos + vel * dt;                         // :619-623
         if (should_destroy) {
             alive = false;                              // :636-639: position, velocity and scale
             destroyed_by_collision = true;              // are already updated
@@ -646,6 +646,14 @@ struct alignas(16) UpdateSmem {
     uint32_t warp_alive[kUpdateThreads / 32];
     uint32_t excl_dead; // dead particles of the stream before this tile (compact variants)
 };
+template <bool COLLIDE>
+struct CandQueue { // broad-phase candidates of cast_ray, one column per thread
+    uint32_t q[kCandQueue * kUpdateThreads];
+};
+template <>
+struct CandQueue<false> {
+    uint32_t q[1];
+};
 
 // The fused per-frame update. One CTA processes whole tiles of 256 consecutive particles of one
 // stream; persistent grid, tile = blockIdx.x + k*gridDim.x in increasing order (required by the
@@ -656,6 +664,7 @@ template <bool COMPACT, bool COLLIDE>
 __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (COMPACT ? FW_MINB_COMPACT : FW_MINB))
     update_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant) {
     __shared__ UpdateSmem sm;
+    __shared__ CandQueue<COLLIDE> cq;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const bool derive = f.header->derive != 0u;
     const uint32_t n_tiles = derive ? f.header->host_n_tiles[variant] : t.plan->n_tiles[variant];
@@ -717,7 +726,8 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
         float scale = 0.f, age;
         bool destroyed_by_collision;
-        bool alive = step_particle<COLLIDE>(t, ps, dt, valid, M0, M1, M2, M3, K, c0, c1, scale, age, destroyed_by_collision);
+        bool alive = step_particle<COLLIDE>(t, ps, dt, valid, M0, M1, M2, M3, K, c0, c1, scale, age, destroyed_by_collision,
+                                            COLLIDE ? cq.q + tid : nullptr);
         // destroyed-particle stream (:588,597,637): the record the handler receives keeps the old
         // colours (and the old scale unless a collision destroyed it); read them before this
         // tile publishes anything, i.e. before later tiles may compact over these slots

@@ -281,84 +281,120 @@ __device__ __forceinline__ bool ray_ball_local(float radius, V3 o, V3 d, float m
     normal = n;
     return true;
 }
-// Broad phase: bounds[2i] = (world AABB min.xyz, layers bits), bounds[2i+1] = (max.xyz, -),
-// inflated on the host by far more than any fp32 rounding of the exact test, so a collider is
-// skipped only when the exact test below could not report a hit within max_distance: the result
-// is identical to testing every collider (the CPU oracle does exactly that). NaN never culls.
-__device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ colliders, const float4 *__restrict__ bounds,
-                                         uint32_t n, uint32_t filter_mask, V3 o, V3 d, float max_distance,
-                                         float &distance, V3 &normal) {
+// Broad phase: a BVH over the colliders' world AABBs (built by fw_set_colliders; node k =
+// bvh[2k] = min.xyz | skip link (leaf: layers bits), bvh[2k+1] = max.xyz | collider index or
+// 0xFFFFFFFF for an inner node), walked in depth-first order without a stack: a node whose box
+// misses the ray segment's box jumps to its skip link (a leaf's is k + 1). The boxes are inflated
+// on the host by far more than any fp32 rounding of the exact test, so a collider is skipped only
+// when the exact test below could not report a hit within max_distance: the result is identical
+// to testing every collider in index order (the CPU oracle does exactly that; equal distances
+// resolve to the lowest collider index). NaN never culls.
+//
+// Warp-synchronous: ALL 32 lanes of the warp must call (lanes without a ray pass act = false).
+// The lanes of a warp walk different paths, so the walk only collects candidate leaves into a
+// small per-lane queue in shared memory (queue[j * kUpdateThreads], j < kCandQueue); the long
+// exact test then runs over the queues with the warp converged: a warp pays
+// max-over-lanes(candidates) exact tests instead of one per divergent loop trip (ncu on C5 before
+// the split: 2.7 active lanes per instruction in the exact test, profiles/r1_tuning.md).
+constexpr uint32_t kCandQueue = 4;
+__device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ colliders, const float4 *__restrict__ bvh,
+                                         uint32_t n_nodes, uint32_t filter_mask, bool act, V3 o, V3 d, float max_distance,
+                                         uint32_t *queue, float &distance, V3 &normal) {
     bool found = false;
     float best = 0.0f;
+    uint32_t best_i = 0xFFFFFFFFu;
     V3 best_n = v3(0.0f, 0.0f, 0.0f);
     const V3 e = o + d * max_distance;
     const V3 slo = v3(fminf(o.x, e.x), fminf(o.y, e.y), fminf(o.z, e.z));
     const V3 shi = v3(fmaxf(o.x, e.x), fmaxf(o.y, e.y), fmaxf(o.z, e.z));
     const bool cull_ok = isfinite(e.x) && isfinite(e.y) && isfinite(e.z) && isfinite(o.x) && isfinite(o.y) && isfinite(o.z);
-    for (uint32_t i = 0; i < n; i++) {
-        const float4 blo = __ldg(bounds + 2u * i), bhi = __ldg(bounds + 2u * i + 1u);
-        if ((__float_as_uint(blo.w) & filter_mask) == 0u) continue;
-        if (cull_ok && (shi.x < blo.x || slo.x > bhi.x || shi.y < blo.y || slo.y > bhi.y || shi.z < blo.z || slo.z > bhi.z)) continue;
-        const fw_collider &c = colliders[i];
-        Q4 rot{c.rotation[0], c.rotation[1], c.rotation[2], c.rotation[3]};
-        Q4 inv = qconj(rot);
-        V3 tr = v3(c.translation[0], c.translation[1], c.translation[2]);
-        V3 ol = qrot(inv, o - tr);
-        V3 dl = qrot(inv, d);
-        float toi;
-        V3 nl;
-        bool hit;
-        if (c.kind == FW_COLLIDER_SPHERE) hit = ray_ball_local(c.half_extents[0], ol, dl, max_distance, toi, nl);
-        else hit = ray_cuboid_local(v3(c.half_extents[0], c.half_extents[1], c.half_extents[2]), ol, dl, max_distance, toi, nl);
-        if (hit && (!found || toi < best)) {
-            found = true;
-            best = toi;
-            best_n = qrot(rot, nl);
+    uint32_t k = act ? 0u : n_nodes;
+    do {
+        uint32_t cnt = 0;
+        while (k < n_nodes && cnt < kCandQueue) {
+            const float4 blo = __ldg(bvh + 2u * k), bhi = __ldg(bvh + 2u * k + 1u);
+            const uint32_t leaf = __float_as_uint(bhi.w);
+            const bool disjoint = cull_ok && (shi.x < blo.x || slo.x > bhi.x || shi.y < blo.y || slo.y > bhi.y || shi.z < blo.z || slo.z > bhi.z);
+            if (leaf == 0xFFFFFFFFu) {
+                k = disjoint ? __float_as_uint(blo.w) : k + 1u;
+            } else {
+                k++;
+                if (!disjoint && (__float_as_uint(blo.w) & filter_mask) != 0u) queue[(cnt++) * kUpdateThreads] = leaf;
+            }
         }
-    }
+        const uint32_t rounds = __reduce_max_sync(0xffffffffu, cnt);
+        for (uint32_t j = 0; j < rounds; j++) {
+            if (j < cnt) {
+                const uint32_t cand = queue[j * kUpdateThreads];
+                const fw_collider &c = colliders[cand];
+                Q4 rot{c.rotation[0], c.rotation[1], c.rotation[2], c.rotation[3]};
+                Q4 inv = qconj(rot);
+                V3 tr = v3(c.translation[0], c.translation[1], c.translation[2]);
+                V3 ol = qrot(inv, o - tr);
+                V3 dl = qrot(inv, d);
+                float toi;
+                V3 nl;
+                bool hit;
+                if (c.kind == FW_COLLIDER_SPHERE) hit = ray_ball_local(c.half_extents[0], ol, dl, max_distance, toi, nl);
+                else hit = ray_cuboid_local(v3(c.half_extents[0], c.half_extents[1], c.half_extents[2]), ol, dl, max_distance, toi, nl);
+                if (hit && (!found || toi < best || (toi == best && cand < best_i))) {
+                    found = true;
+                    best = toi;
+                    best_i = cand;
+                    best_n = qrot(rot, nl);
+                }
+            }
+            __syncwarp();
+        }
+    } while (__any_sync(0xffffffffu, k < n_nodes));
     distance = best;
     normal = best_n;
     return found;
 }
 
-// reference src/core.rs:744-800 particle_collision
-__device__ __forceinline__ void particle_collision(const fw_collider *__restrict__ colliders, const float4 *__restrict__ bounds,
-                                                   uint32_t n_colliders, const fw_collision_settings &cs, V3 &pos, V3 &vel,
-                                                   float delta, bool &should_destroy) {
+// reference src/core.rs:744-800 particle_collision. Warp-synchronous like cast_ray: every lane of
+// the warp calls, lanes without a live particle pass active = false (their pos / vel stay untouched).
+__device__ __forceinline__ void particle_collision(const fw_collider *__restrict__ colliders, const float4 *__restrict__ bvh,
+                                                   uint32_t n_bvh_nodes, const fw_collision_settings &cs, bool active, V3 &pos,
+                                                   V3 &vel, float delta, uint32_t *queue, bool &should_destroy) {
     const float orig_delta = delta;
     int n_steps = 0;
     should_destroy = false;
-    while (delta > 0.0f && n_steps < 4) {
+    bool go = active && delta > 0.0f; // `while delta > 0 && n_steps < 4` (:755)
+    while (__any_sync(0xffffffffu, go)) {
         float len = length(vel);
         V3 dir = (isfinite(len) && len > 0.0f) ? vel / len : v3(0.0f, 1.0f, 0.0f);
         float distance;
         V3 hit_normal;
-        if (cast_ray(colliders, bounds, n_colliders, cs.filter_mask, pos, dir, length(vel) * delta, distance, hit_normal)) {
-            if (distance == 0.0f) {
-                V3 normal = hit_normal;
-                if (is_zero(normal)) {
-                    if (!is_zero(vel)) normal = normalize(vel);
-                    else normal = v3(0.0f, 1.0f, 0.0f);
+        const bool hit = cast_ray(colliders, bvh, n_bvh_nodes, cs.filter_mask, go, pos, dir, length(vel) * delta, queue, distance, hit_normal);
+        if (go) {
+            if (hit) {
+                if (distance == 0.0f) {
+                    V3 normal = hit_normal;
+                    if (is_zero(normal)) {
+                        if (!is_zero(vel)) normal = normalize(vel);
+                        else normal = v3(0.0f, 1.0f, 0.0f);
+                    }
+                    pos = pos + (normal * fmaxf(length(vel), 1.0f)) * delta;
+                } else {
+                    pos = pos + normalize_or_zero(vel) * distance;
+                    V3 vel_reject = reject_from(vel, hit_normal);
+                    V3 vel_project = project_onto(vel, hit_normal);
+                    float friction_dv = fminf(length(vel_project), length(vel_reject)) * cs.friction;
+                    vel = (vel_reject - normalize_or_zero(vel_reject) * friction_dv) - vel_project * cs.restitution;
+                    pos = pos + hit_normal * 0.0001f;
+                    delta = delta - distance;
+                    if (delta < 0.0f) delta = 0.0f;
+                    if (delta > orig_delta) delta = orig_delta;
                 }
-                pos = pos + (normal * fmaxf(length(vel), 1.0f)) * delta;
+                should_destroy = cs.destroy_on_collision != 0u;
             } else {
-                pos = pos + normalize_or_zero(vel) * distance;
-                V3 vel_reject = reject_from(vel, hit_normal);
-                V3 vel_project = project_onto(vel, hit_normal);
-                float friction_dv = fminf(length(vel_project), length(vel_reject)) * cs.friction;
-                vel = (vel_reject - normalize_or_zero(vel_reject) * friction_dv) - vel_project * cs.restitution;
-                pos = pos + hit_normal * 0.0001f;
-                delta = delta - distance;
-                if (delta < 0.0f) delta = 0.0f;
-                if (delta > orig_delta) delta = orig_delta;
+                pos = pos + vel * delta;
+                delta = 0.0f;
             }
-            should_destroy = cs.destroy_on_collision != 0u;
-            if (should_destroy) return;
-        } else {
-            pos = pos + vel * delta;
-            delta = 0.0f;
+            n_steps += 1;
+            go = !should_destroy && delta > 0.0f && n_steps < 4; // early return at :788-791
         }
-        n_steps += 1;
     }
 }
 
