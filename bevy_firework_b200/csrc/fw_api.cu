@@ -98,6 +98,9 @@ struct FrameSlot {
 
 } // namespace
 
+// most update tiles a ring of `capacity` slots can have (slot-aligned FIFO tiles: one extra)
+static inline uint64_t max_tiles_of(uint64_t capacity) { return (capacity + kTile - 1) / kTile + 1; }
+
 struct fw_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -138,7 +141,7 @@ struct fw_context {
     size_t stage_bytes = 0;
     unsigned long long *d_lookback = nullptr;
     uint32_t tiles_cap = 0;
-    uint64_t tiles_needed = 0; // sum over streams of ceil(capacity / kTile)
+    uint64_t tiles_needed = 0; // sum over streams of max_tiles_of(capacity)
     uint32_t device_error_flags = 0; // accumulated from the per-frame plan readbacks
     unsigned long long *d_pack = nullptr; // n_rows + per-slot offsets
     uint32_t pack_cap = 0;
@@ -450,7 +453,7 @@ uint64_t estimate_capacity(const Spawner &sp, uint32_t type) {
 
 void free_stream(fw_context *ctx, Stream &st) {
     if (!st.block.base) return; // never got a slot / block (failed reset)
-    ctx->tiles_needed -= (st.block.capacity + kTile - 1) / kTile;
+    ctx->tiles_needed -= max_tiles_of(st.block.capacity);
     ctx->variant_streams[st.variant]--;
     release_block(ctx, st.block);
     release_block(ctx, st.destroyed);
@@ -555,10 +558,10 @@ int grow_stream(fw_context *ctx, Stream &st, uint64_t need) {
     ns.dead = 0;
     CU(ctx, cudaMemcpyAsync(cur_states(ctx) + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, ctx->stream));
     ctx->snapshot[st.slot] = ns;
-    ctx->tiles_needed -= (st.block.capacity + kTile - 1) / kTile;
+    ctx->tiles_needed -= max_tiles_of(st.block.capacity);
     release_block(ctx, st.block);
     st.block = nb;
-    ctx->tiles_needed += (ncap + kTile - 1) / kTile;
+    ctx->tiles_needed += max_tiles_of(ncap);
     return upload_desc(ctx, st);
 }
 
@@ -907,7 +910,7 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
                 return rc;
             }
             if (ps[t].capture_destroyed && (rc = alloc_block(ctx, st.block.capacity, st.n_lea, st.destroyed))) return rc;
-            ctx->tiles_needed += (st.block.capacity + kTile - 1) / kTile;
+            ctx->tiles_needed += max_tiles_of(st.block.capacity);
             ctx->variant_streams[st.variant]++;
             ctx->slot_owner[st.slot] = &st;
             DevParticleSettings ds;
@@ -1273,7 +1276,9 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
                     if (st && st->variant == v) {
                         // upper bound of the particles the update kernel covers in this stream
                         const uint64_t covered = step_in_spawn ? st->n_hi - std::min<uint64_t>(st->n_hi, add[s]) : st->n_hi;
-                        run += (uint32_t)((std::min<uint64_t>(covered, st->block.capacity) + kTile - 1) / kTile);
+                        // (FIFO tiles are aligned to physical slots: up to 31 idle lanes in front, see update_kernel)
+                        const uint64_t lead = (v == kFifo || v == kFifoCollide) ? 31 : 0;
+                        if (covered) run += (uint32_t)((std::min<uint64_t>(covered, st->block.capacity) + lead + kTile - 1) / kTile);
                     }
                 }
                 pv[n_slots] = run;

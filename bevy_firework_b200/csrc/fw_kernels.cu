@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
                     const StreamDesc d = t.descs[s];
                     if (d.capacity != 0u && d.variant == v) {
                         const uint32_t n = t.states[s].count;
-                        tiles = (n + kTile - 1u) / kTile;
+                        const bool fifo = (v == kFifo || v == kFifoCollide); // slot-aligned tiles, see update_kernel
+                        tiles = n ? (n + (fifo ? (t.states[s].head & 31u) : 0u) + kTile - 1u) / kTile : 0u;
                         my_total += n;
                     }
                 }
@@ -692,9 +693,14 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         StreamState *stp = &t.states[e.stream];
         const uint32_t head = e.head, n_update = e.n_update;
         const StreamArrays a = stream_arrays(d.base, d.capacity);
+        // FIFO rings: tiles are aligned to the ring's physical slots, not to the logical index --
+        // the head moves by an arbitrary count every frame, and a warp whose 32 slots start at a
+        // multiple of 32 touches 4 full 128-byte lines per float4 pack instead of straddling 5
+        // (the first `shift` lanes of a stream's tile 0 idle). Compacting rings keep head % 32 == 0.
+        const uint32_t shift = COMPACT ? 0u : (head & 31u);
         const uint32_t tile_first = e.tile * kTile;
-        const uint32_t i = tile_first + tid;
-        const bool valid = i < n_update;
+        const uint32_t i = tile_first + tid - shift;
+        const bool valid = tile_first + tid >= shift && i < n_update;
         const uint32_t slot = wrap(head + (valid ? i : 0u), d.capacity);
 
         // ---- loads: 64 B per particle, five independent coalesced requests per thread

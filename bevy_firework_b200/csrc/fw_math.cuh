@@ -313,14 +313,12 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
         uint32_t cnt = 0;
         while (k < n_nodes && cnt < kCandQueue) {
             const float4 blo = __ldg(bvh + 2u * k), bhi = __ldg(bvh + 2u * k + 1u);
-            const uint32_t leaf = __float_as_uint(bhi.w);
-            const bool disjoint = cull_ok && (shi.x < blo.x || slo.x > bhi.x || shi.y < blo.y || slo.y > bhi.y || shi.z < blo.z || slo.z > bhi.z);
-            if (leaf == 0xFFFFFFFFu) {
-                k = disjoint ? __float_as_uint(blo.w) : k + 1u;
-            } else {
-                k++;
-                if (!disjoint && (__float_as_uint(blo.w) & filter_mask) != 0u) queue[(cnt++) * kUpdateThreads] = leaf;
-            }
+            const uint32_t leaf = __float_as_uint(bhi.w), link = __float_as_uint(blo.w);
+            // (bitwise, not short-circuit: one predicate chain instead of six branches)
+            const bool disjoint = cull_ok & ((shi.x < blo.x) | (slo.x > bhi.x) | (shi.y < blo.y) | (slo.y > bhi.y) | (shi.z < blo.z) | (slo.z > bhi.z));
+            const bool inner = leaf == 0xFFFFFFFFu;
+            k = (inner & disjoint) ? link : k + 1u;
+            if (!inner & !disjoint & ((link & filter_mask) != 0u)) queue[(cnt++) * kUpdateThreads] = leaf;
         }
         const uint32_t rounds = __reduce_max_sync(0xffffffffu, cnt);
         for (uint32_t j = 0; j < rounds; j++) {
