@@ -154,6 +154,10 @@ class fw_frame_profile(C.Structure):
                 ("h2d_bytes", u64), ("d2h_bytes", u64)]
 
 
+class fw_gather_handle(C.Structure):
+    _fields_ = [("ipc", C.c_uint8 * 64), ("address", u64), ("bytes", u64), ("device", C.c_int32), ("pid", C.c_int32)]
+
+
 # numpy structured dtypes of the two row formats (for zero-copy readback)
 def particle_data_dtype():
     import numpy as np
@@ -201,6 +205,11 @@ EXPORTS = {
     "fw_read_destroyed": (C.c_int, [_ctx, u32, u32, C.c_void_p, u64, P(u64)]),
     "fw_read_aabb": (C.c_int, [_ctx, u32, P(f32 * 3), P(f32 * 3), P(u32)]),
     "fw_pack_instances_device": (C.c_int, [_ctx, C.c_void_p, u64, P(u64)]),
+    "fw_gather_create": (C.c_int, [_ctx, u32, u32, u64, P(fw_gather_handle)]),
+    "fw_gather_connect": (C.c_int, [_ctx, P(fw_gather_handle), u32]),
+    "fw_gather_instances": (C.c_int, [_ctx]),
+    "fw_gather_result": (C.c_int, [_ctx, P(C.c_void_p), P(u64), u32, P(u64)]),
+    "fw_gather_destroy": (C.c_int, [_ctx]),
     "fw_total_live": (C.c_int, [_ctx, P(u64)]),
     "fw_set_profiling": (C.c_int, [_ctx, u32]),
     "fw_profile_last": (C.c_int, [_ctx, P(fw_frame_profile)]),
@@ -220,5 +229,5 @@ POD_TYPES = {
     "fw_spawner_frame_input": fw_spawner_frame_input, "fw_particle_data": fw_particle_data,
     "fw_particle_instance": fw_particle_instance, "fw_collider": fw_collider,
     "fw_config": fw_config, "fw_spawner_status": fw_spawner_status,
-    "fw_frame_profile": fw_frame_profile,
+    "fw_frame_profile": fw_frame_profile, "fw_gather_handle": fw_gather_handle,
 }

@@ -87,6 +87,8 @@ class Engine:
             self._ctx = C.c_void_p()
             raise FireworkError(rc, self._L.fw_last_global_error().decode())
         self._n_types = {}
+        self._n_streams = 0
+        self._counts_buf = None
         self.device = device
 
     # -- plumbing
@@ -115,11 +117,12 @@ class Engine:
     def spawner_reset(self, key, ps, n_types, es, n_emitters, starts_enabled=True):
         self._check(self._L.fw_spawner_reset(self._ctx, key, ps, n_types, es, n_emitters,
                                              1 if starts_enabled else 0))
+        self._n_streams += n_types - self._n_types.get(key, 0)
         self._n_types[key] = n_types
 
     def spawner_remove(self, key):
         self._check(self._L.fw_spawner_remove(self._ctx, key))
-        self._n_types.pop(key, None)
+        self._n_streams -= self._n_types.pop(key, 0)
 
     def set_colliders(self, colliders: Sequence[_abi.fw_collider]):
         arr = (_abi.fw_collider * max(len(colliders), 1))()
@@ -141,13 +144,18 @@ class Engine:
         return [int(out[i]) for i in range(n_types)]
 
     def counts_all(self):
-        n = C.c_uint32()
-        cap = max(sum(self._n_types.values()), 1)
-        keys, types, counts = (C.c_uint32 * cap)(), (C.c_uint32 * cap)(), (C.c_uint32 * cap)()
-        self._check(self._L.fw_counts_all(self._ctx, keys, types, counts, cap, C.byref(n)))
+        """(keys, types, counts) of every stream in creation order; the arrays are views of buffers
+        this Engine reuses between calls (copy them to keep them)."""
+        cap = self._n_streams
+        buf = self._counts_buf
+        if buf is None or buf[0] < cap:
+            arrs = [np.zeros(max(cap, 1), dtype=np.uint32) for _ in range(3)]
+            u32p = C.POINTER(C.c_uint32)
+            buf = self._counts_buf = (max(cap, 1), arrs, [a.ctypes.data_as(u32p) for a in arrs], C.c_uint32())
+        _, arrs, ptrs, n = buf
+        self._check(self._L.fw_counts_all(self._ctx, ptrs[0], ptrs[1], ptrs[2], buf[0], C.byref(n)))
         k = n.value
-        return (np.ctypeslib.as_array(keys)[:k].copy(), np.ctypeslib.as_array(types)[:k].copy(),
-                np.ctypeslib.as_array(counts)[:k].copy())
+        return arrs[0][:k], arrs[1][:k], arrs[2][:k]
 
     def total_live(self) -> int:
         n = C.c_uint64()
@@ -200,6 +208,31 @@ class Engine:
         n = C.c_uint64()
         self._check(self._L.fw_extract_instances(self._ctx, host_ptr, cap_rows, C.byref(n)))
         return int(n.value)
+
+    # -- multi-GPU render extract over peer memory (fw_gather_*)
+    def gather_create(self, n_ranks: int, my_rank: int, cap_rows_per_rank: int) -> bytes:
+        """allocate this rank's gather buffer; returns its handle as bytes (send it to the peers)"""
+        h = _abi.fw_gather_handle()
+        self._check(self._L.fw_gather_create(self._ctx, n_ranks, my_rank, cap_rows_per_rank, C.byref(h)))
+        return bytes(h)
+
+    def gather_connect(self, handles: Sequence[bytes]):
+        arr = (_abi.fw_gather_handle * len(handles))(*[_abi.fw_gather_handle.from_buffer_copy(b) for b in handles])
+        self._check(self._L.fw_gather_connect(self._ctx, arr, len(handles)))
+
+    def gather_instances(self):
+        """collective, asynchronous: every rank must issue it before any rank waits for the result"""
+        self._check(self._L.fw_gather_instances(self._ctx))
+
+    def gather_result(self, n_ranks: int):
+        """-> (device pointer of region 0, rows per rank, region stride in rows); synchronises"""
+        ptr, stride = C.c_void_p(), C.c_uint64()
+        rows = (C.c_uint64 * n_ranks)()
+        self._check(self._L.fw_gather_result(self._ctx, C.byref(ptr), rows, n_ranks, C.byref(stride)))
+        return int(ptr.value or 0), [int(r) for r in rows], int(stride.value)
+
+    def gather_destroy(self):
+        self._check(self._L.fw_gather_destroy(self._ctx))
 
     def event_record(self, slot: int):
         self._check(self._L.fw_event_record(self._ctx, slot))

@@ -6,6 +6,8 @@
 // management of device memory. Everything per-particle runs in fw_kernels.cu.
 //
 // There is no CPU fallback: every entry point needs a live CUDA context.
+#include <unistd.h>
+
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -108,7 +110,8 @@ struct fw_context {
     // forked branch of a frame: spawn_kernel<STEP> runs here concurrently with update_kernel
     cudaStream_t side_stream = nullptr;
     // parameter uploads and state readbacks run here, overlapping the neighbouring frames' kernels
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // parameter uploads (H2D) only: never waits for kernels
+    cudaStream_t rb_stream = nullptr;   // per-frame state readbacks (D2H), each behind its frame's kernels
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool concurrent_spawn = true;
     uint64_t seed = 0;
@@ -148,6 +151,13 @@ struct fw_context {
     unsigned long long *h_pack = nullptr; // pinned
     float4 *d_extract = nullptr;          // staging of fw_extract_instances
     uint64_t extract_cap = 0;
+    // multi-GPU render extract over peer memory (fw_gather_*)
+    uint8_t *d_gather = nullptr; // this rank's gather buffer: [GatherHeader | n_ranks regions]
+    GatherPeers gather{};        // base[r] = rank r's buffer as mapped here (base[my_rank] = d_gather)
+    bool gather_ipc[kMaxGatherRanks] = {false}; // base[r] came from cudaIpcOpenMemHandle
+    bool gather_connected = false;
+    uint64_t gather_epoch = 0;
+    GatherHeader *h_gather = nullptr; // pinned copy of our header (fw_gather_result)
     cudaEvent_t user_events[16] = {};
 
     std::map<size_t, std::vector<void *>> block_cache; // bytes -> free device blocks
@@ -203,10 +213,11 @@ inline void topo_changed(fw_context *ctx) {
 }
 
 // wait for everything the context has enqueued (kernels on the main stream, then the readbacks
-// that follow them on the copy stream)
+// that follow them on the readback stream)
 inline cudaError_t sync_all(fw_context *ctx) {
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess && ctx->copy_stream) e = cudaStreamSynchronize(ctx->copy_stream);
+    if (e == cudaSuccess && ctx->rb_stream) e = cudaStreamSynchronize(ctx->rb_stream);
     return e;
 }
 inline size_t statebuf_bytes(uint32_t slots) { return sizeof(PlanOut) + sizeof(StreamState) * (size_t)slots; }
@@ -693,7 +704,7 @@ uint32_t fw_abi_sizeof(const char *name) {
     if (!strcmp(name, #T)) return (uint32_t)sizeof(T);
     SZ(fw_rand_f32) SZ(fw_rand_vec3) SZ(fw_curve_f32) SZ(fw_gradient) SZ(fw_collision_settings)
     SZ(fw_particle_settings) SZ(fw_emission_settings) SZ(fw_spawner_frame_input) SZ(fw_particle_data)
-    SZ(fw_particle_instance) SZ(fw_collider) SZ(fw_config) SZ(fw_spawner_status) SZ(fw_frame_profile)
+    SZ(fw_particle_instance) SZ(fw_collider) SZ(fw_config) SZ(fw_spawner_status) SZ(fw_frame_profile) SZ(fw_gather_handle)
 #undef SZ
     return 0;
 }
@@ -733,6 +744,7 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
     }
     CU(c, cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
     CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&c->rb_stream, cudaStreamNonBlocking));
     CU(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CU(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (FrameSlot &fs : c->ring) {
@@ -751,10 +763,12 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
     return FW_OK;
 }
 
+static void gather_release(fw_context *ctx);
 int fw_destroy(fw_context *ctx) {
     if (!ctx) return FW_OK;
     cudaSetDevice(ctx->device);
     sync_all(ctx);
+    gather_release(ctx);
     for (auto &sp : ctx->spawners)
         for (Stream &st : sp->streams) {
             if (st.block.base) cudaFree(st.block.base);
@@ -794,6 +808,10 @@ int fw_destroy(fw_context *ctx) {
     if (ctx->side_stream) {
         cudaStreamSynchronize(ctx->side_stream);
         cudaStreamDestroy(ctx->side_stream);
+    }
+    if (ctx->rb_stream) {
+        cudaStreamSynchronize(ctx->rb_stream);
+        cudaStreamDestroy(ctx->rb_stream);
     }
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
@@ -1446,11 +1464,13 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
         if (rc) return rc;
     }
     // asynchronous readback of [PlanOut | stream states] (counts, AABBs, bounds for the next
-    // frames) on the copy stream: the next frame's kernels only read this buffer
+    // frames) on its own stream (the next frame's kernels only read this buffer). Not the upload
+    // stream: behind this copy, the next frame's parameter upload would wait for this frame's
+    // kernels instead of overlapping them
     CU(ctx, cudaEventRecord(fs.ev_kernels, ctx->stream));
-    CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, fs.ev_kernels, 0));
-    CU(ctx, cudaMemcpyAsync(fs.readback, ctx->d_statebuf[new_buf], statebuf_bytes(n_slots), cudaMemcpyDeviceToHost, ctx->copy_stream));
-    CU(ctx, cudaEventRecord(fs.done, ctx->copy_stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->rb_stream, fs.ev_kernels, 0));
+    CU(ctx, cudaMemcpyAsync(fs.readback, ctx->d_statebuf[new_buf], statebuf_bytes(n_slots), cudaMemcpyDeviceToHost, ctx->rb_stream));
+    CU(ctx, cudaEventRecord(fs.done, ctx->rb_stream));
     ctx->snapshot_valid = false;
     ctx->readback_is_current = true;
     ctx->frame_no++;
@@ -1726,6 +1746,142 @@ int fw_extract_instances(fw_context *ctx, void *host_dst, uint64_t cap_rows, uin
         CU(ctx, cudaMemcpyAsync(host_dst, ctx->d_extract, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, sync_all(ctx));
     }
+    return FW_OK;
+}
+
+// ---- multi-GPU render extract over NVLink peer memory (reference consumer
+// src/render.rs:439-461 wants every instance row on the GPU that draws)
+static void gather_release(fw_context *ctx) {
+    for (uint32_t r = 0; r < kMaxGatherRanks; r++) {
+        if (ctx->gather_ipc[r] && ctx->gather.base[r]) cudaIpcCloseMemHandle(ctx->gather.base[r]);
+        ctx->gather_ipc[r] = false;
+        ctx->gather.base[r] = nullptr;
+    }
+    if (ctx->d_gather) cudaFree(ctx->d_gather);
+    ctx->d_gather = nullptr;
+    if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
+    ctx->h_gather = nullptr;
+    ctx->gather_connected = false;
+    ctx->gather.n_ranks = 0;
+    (void)cudaGetLastError();
+}
+
+int fw_gather_create(fw_context *ctx, uint32_t n_ranks, uint32_t my_rank, uint64_t cap_rows_per_rank, fw_gather_handle *out) {
+    ENTER(ctx);
+    if (!out || n_ranks == 0 || n_ranks > kMaxGatherRanks || my_rank >= n_ranks || cap_rows_per_rank == 0)
+        return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_gather_create: n_ranks %u (max %u), my_rank %u, cap %llu", n_ranks,
+                    kMaxGatherRanks, my_rank, (unsigned long long)cap_rows_per_rank);
+    CU(ctx, sync_all(ctx));
+    gather_release(ctx);
+    const size_t bytes = kGatherHeaderBytes + (size_t)n_ranks * cap_rows_per_rank * 64;
+    CU(ctx, cudaMalloc((void **)&ctx->d_gather, bytes));
+    CU(ctx, cudaMemset(ctx->d_gather, 0, kGatherHeaderBytes));
+    CU(ctx, cudaMallocHost((void **)&ctx->h_gather, sizeof(GatherHeader)));
+    ctx->gather.n_ranks = n_ranks;
+    ctx->gather.my_rank = my_rank;
+    ctx->gather.cap_rows_per_rank = cap_rows_per_rank;
+    ctx->gather.base[my_rank] = ctx->d_gather;
+    ctx->gather_epoch = 0;
+    memset(out, 0, sizeof(*out));
+    cudaIpcMemHandle_t h;
+    CU(ctx, cudaIpcGetMemHandle(&h, ctx->d_gather));
+    static_assert(sizeof(h) <= sizeof(out->ipc), "fw_gather_handle.ipc too small");
+    memcpy(out->ipc, &h, sizeof(h));
+    out->address = (uint64_t)(uintptr_t)ctx->d_gather;
+    out->bytes = bytes;
+    out->device = ctx->device;
+    out->pid = (int32_t)getpid();
+    return FW_OK;
+}
+
+int fw_gather_connect(fw_context *ctx, const fw_gather_handle *handles, uint32_t n_handles) {
+    ENTER(ctx);
+    if (!ctx->d_gather) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_gather_connect: call fw_gather_create first");
+    if (!handles || n_handles != ctx->gather.n_ranks)
+        return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_gather_connect: %u handles for %u ranks", n_handles, ctx->gather.n_ranks);
+    const size_t bytes = kGatherHeaderBytes + (size_t)ctx->gather.n_ranks * ctx->gather.cap_rows_per_rank * 64;
+    for (uint32_t r = 0; r < n_handles; r++) {
+        if (r == ctx->gather.my_rank) continue;
+        if (handles[r].bytes != bytes)
+            return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_gather_connect: rank %u created its buffer with another geometry", r);
+        if (handles[r].pid == (int32_t)getpid()) { // another context of this process: plain peer access
+            if (handles[r].device != ctx->device) {
+                int can = 0;
+                CU(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, handles[r].device));
+                if (!can) return fail(ctx, FW_ERR_UNSUPPORTED, "fw_gather_connect: device %d cannot access device %d", ctx->device, handles[r].device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(handles[r].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(ctx, e);
+                (void)cudaGetLastError();
+            }
+            ctx->gather.base[r] = (uint8_t *)(uintptr_t)handles[r].address;
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles[r].ipc, sizeof(h));
+            void *p = nullptr;
+            CU(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            ctx->gather.base[r] = (uint8_t *)p;
+            ctx->gather_ipc[r] = true;
+        }
+    }
+    ctx->gather_connected = true;
+    return FW_OK;
+}
+
+int fw_gather_instances(fw_context *ctx) {
+    ENTER(ctx);
+    if (!ctx->gather_connected) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_gather_instances: not connected (fw_gather_create / fw_gather_connect)");
+    if (ctx->pack_cap < ctx->n_slots + 2) {
+        CU(ctx, sync_all(ctx));
+        if (ctx->d_pack) CU(ctx, cudaFree(ctx->d_pack));
+        ctx->d_pack = nullptr;
+        ctx->pack_cap = std::max(1024u, (ctx->n_slots + 2) * 2);
+        CU(ctx, cudaMalloc((void **)&ctx->d_pack, sizeof(unsigned long long) * ctx->pack_cap));
+    }
+    if (!ctx->h_pack) CU(ctx, cudaMallocHost((void **)&ctx->h_pack, sizeof(unsigned long long)));
+    const GatherPeers &g = ctx->gather;
+    const unsigned long long epoch = ++ctx->gather_epoch;
+    const unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
+    DeviceTables t{};
+    t.descs = ctx->d_descs;
+    t.states = cur_states(ctx);
+    PackDst dst{};
+    dst.n = g.n_ranks;
+    for (uint32_t r = 0; r < g.n_ranks; r++)
+        dst.rows[r] = (float4 *)(g.base[r] + kGatherHeaderBytes + (size_t)g.my_rank * g.cap_rows_per_rank * 64);
+    // every rank is done reading the previous epoch (stream order on each rank) before anyone
+    // overwrites it; then the rows; then "landed" flags + counts, and wait for everybody's
+    CU(ctx, launch_gather_signal(g, kGatherReady, epoch, nullptr, timeout_ns, ctx->stream));
+    CU(ctx, launch_pack_instances(t, 0, ctx->n_slots, dst, g.cap_rows_per_rank, ctx->d_pack, ctx->stream));
+    CU(ctx, launch_gather_signal(g, kGatherDone, epoch, ctx->d_pack, timeout_ns, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->h_pack, ctx->d_pack, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    return FW_OK;
+}
+
+int fw_gather_result(fw_context *ctx, void **device_rows, uint64_t *rows_per_rank, uint32_t n_ranks, uint64_t *region_stride_rows) {
+    ENTER(ctx);
+    if (!ctx->gather_connected || ctx->gather_epoch == 0) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_gather_result: no gather was issued");
+    if (n_ranks < ctx->gather.n_ranks && rows_per_rank) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_gather_result: room for %u ranks, %u needed", n_ranks, ctx->gather.n_ranks);
+    CU(ctx, cudaMemcpyAsync(ctx->h_gather, ctx->d_gather, sizeof(GatherHeader), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, sync_all(ctx));
+    if (ctx->h_gather->error) {
+        const unsigned long long who = ctx->h_gather->error - 1;
+        CU(ctx, cudaMemset(&((GatherHeader *)ctx->d_gather)->error, 0, sizeof(unsigned long long)));
+        return fail(ctx, FW_ERR_INTERNAL, "fw_gather: timed out waiting for rank %llu", who);
+    }
+    if (*ctx->h_pack > ctx->gather.cap_rows_per_rank)
+        return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_gather: this rank has %llu rows, its region holds %llu", *ctx->h_pack,
+                    (unsigned long long)ctx->gather.cap_rows_per_rank);
+    if (device_rows) *device_rows = ctx->d_gather + kGatherHeaderBytes;
+    if (region_stride_rows) *region_stride_rows = ctx->gather.cap_rows_per_rank;
+    if (rows_per_rank)
+        for (uint32_t r = 0; r < ctx->gather.n_ranks; r++) rows_per_rank[r] = ctx->h_gather->rows[r];
+    return FW_OK;
+}
+
+int fw_gather_destroy(fw_context *ctx) {
+    ENTER(ctx);
+    CU(ctx, sync_all(ctx));
+    gather_release(ctx);
     return FW_OK;
 }
 

@@ -244,6 +244,30 @@ struct FrameDeviceInputs {
     const NestedCmd *nested;
 };
 
+// ---- multi-GPU render extract over peer memory: every rank owns a gather
+// buffer [GatherHeader (4096 B) | n_ranks regions of cap_rows_per_rank 64-byte rows] that all
+// ranks map (CUDA IPC or same-process peer access); rank r's pack kernel stores its rows into
+// region r of EVERY buffer.
+constexpr uint32_t kMaxGatherRanks = 16;
+constexpr size_t kGatherHeaderBytes = 4096;
+constexpr uint32_t kGatherReady = 0, kGatherDone = 1;
+struct GatherHeader {                           // written by the peers, system-scope release/acquire
+    unsigned long long rows[kMaxGatherRanks];   // rows[r]: rank r's row count of the current epoch
+    unsigned long long ready[kMaxGatherRanks];  // ready[r] = e: rank r no longer reads epoch e-1
+    unsigned long long done[kMaxGatherRanks];   // done[r] = e: rank r's rows of epoch e have landed
+    unsigned long long error;                   // 1 + rank that timed out, 0 = none
+};
+static_assert(sizeof(GatherHeader) <= kGatherHeaderBytes, "gather header");
+struct GatherPeers {
+    uint8_t *base[kMaxGatherRanks]; // every rank's gather buffer as mapped in this process
+    uint32_t n_ranks, my_rank;
+    uint64_t cap_rows_per_rank;
+};
+struct PackDst {
+    float4 *rows[kMaxGatherRanks];
+    uint32_t n;
+};
+
 // launchers (fw_kernels.cu)
 // plan: what = bit 0 apply last frame's deaths, bit 1 append the Global spawns of `phase`,
 // bit 2 build the tile prefix tables
@@ -261,6 +285,10 @@ cudaError_t update_grid_size(int device, int *grids /*[kNumVariants]*/);
 // live ParticleInstance rows of the streams [slot_begin, slot_end) -> contiguous 64-byte rows
 cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, float4 *dst,
                                   uint64_t cap_rows, unsigned long long *n_rows_and_offsets, cudaStream_t s);
+cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, const PackDst &dst,
+                                  uint64_t cap_rows, unsigned long long *n_rows_and_offsets, cudaStream_t s);
+cudaError_t launch_gather_signal(const GatherPeers &p, uint32_t which, unsigned long long epoch, const unsigned long long *rows_src,
+                                 unsigned long long timeout_ns, cudaStream_t s);
 // one stream <-> fw_particle_data rows (host mirror / fw_write_particles)
 cudaError_t launch_gather_particles(uint8_t *base, uint32_t capacity, uint32_t first, uint32_t n, uint32_t pbr,
                                     fw_particle_data *dst, cudaStream_t s);

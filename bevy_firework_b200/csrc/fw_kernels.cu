@@ -863,8 +863,11 @@ __global__ void pack_prefix_kernel(DeviceTables t, uint32_t slot_begin, uint32_t
         out[0] = acc;
     }
 }
+// PackDst: where the rows go -- one caller buffer, or (multi-GPU render extract) this rank's
+// region of the gather buffer of EVERY rank: peer buffers are mapped over NVLink, so the all-gather
+// is just these stores (one HBM read, n_dst coalesced 16-byte writes per chunk).
 __global__ void __launch_bounds__(256) pack_copy_kernel(DeviceTables t, uint32_t slot_begin, uint32_t slot_end,
-                                                        const unsigned long long *offsets, float4 *dst, uint64_t cap_rows) {
+                                                        const unsigned long long *offsets, PackDst dst, uint64_t cap_rows) {
     const uint32_t s = slot_begin + blockIdx.y;
     if (s >= slot_end) return;
     const StreamDesc d = t.descs[s];
@@ -891,7 +894,50 @@ __global__ void __launch_bounds__(256) pack_copy_kernel(DeviceTables t, uint32_t
         } else {
             v = a.o1[slot];
         }
-        dst[(off + r) * 4u + c] = v;
+        for (uint32_t k = 0; k < dst.n; k++) dst.rows[k][(off + r) * 4u + c] = v;
+    }
+}
+
+// Device-side barrier between the ranks of a gather (one warp, lane r <-> rank r): publish
+// `epoch` in slot [which][my_rank] of every rank's header (with this rank's row count when
+// which == kGatherDone), then wait until every rank has published it in OUR header. System-scope
+// release / acquire; the pack kernel that precedes a kGatherDone signal in stream order has
+// completed, the fence makes its peer stores visible before the flag. A rank that never shows
+// up is a timeout (error word set), never a hang.
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void __launch_bounds__(32) gather_signal_kernel(GatherPeers p, uint32_t which, unsigned long long epoch,
+                                                           const unsigned long long *rows_src, unsigned long long timeout_ns) {
+    const uint32_t r = threadIdx.x;
+    if (r >= p.n_ranks) return;
+    GatherHeader *peer = (GatherHeader *)p.base[r];
+    GatherHeader *mine = (GatherHeader *)p.base[p.my_rank];
+    if (which == kGatherDone) {
+        unsigned long long n = rows_src[0];
+        if (n > p.cap_rows_per_rank) n = p.cap_rows_per_rank; // the pack kernel dropped the rest
+        *(volatile unsigned long long *)&peer->rows[p.my_rank] = n;
+    }
+    __threadfence_system();
+    st_release_sys(which == kGatherDone ? &peer->done[p.my_rank] : &peer->ready[p.my_rank], epoch);
+    const unsigned long long *flag = which == kGatherDone ? &mine->done[r] : &mine->ready[r];
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) < epoch) {
+        if (global_timer_ns() - t0 > timeout_ns) {
+            *(volatile unsigned long long *)&mine->error = 1ull + r;
+            break;
+        }
+        __nanosleep(256);
     }
 }
 
@@ -999,7 +1045,7 @@ cudaError_t update_grid_size(int device, int *grids) {
     for (int v = 0; v < (int)kNumVariants; v++) grids[v] = sms * (occ[v] > 0 ? occ[v] : 1);
     return cudaSuccess;
 }
-cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, float4 *dst,
+cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, const PackDst &dst,
                                   uint64_t cap_rows, unsigned long long *out, cudaStream_t s) {
     pack_prefix_kernel<<<1, 32, 0, s>>>(t, slot_begin, slot_end, out);
     if (slot_end > slot_begin) {
@@ -1009,6 +1055,18 @@ cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, ui
             pack_copy_kernel<<<grid, 256, 0, s>>>(t, slot_begin + y0, slot_end, out + y0, dst, cap_rows);
         }
     }
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, float4 *dst,
+                                  uint64_t cap_rows, unsigned long long *out, cudaStream_t s) {
+    PackDst d{};
+    d.rows[0] = dst;
+    d.n = 1;
+    return launch_pack_instances(t, slot_begin, slot_end, d, cap_rows, out, s);
+}
+cudaError_t launch_gather_signal(const GatherPeers &p, uint32_t which, unsigned long long epoch, const unsigned long long *rows_src,
+                                 unsigned long long timeout_ns, cudaStream_t s) {
+    gather_signal_kernel<<<1, 32, 0, s>>>(p, which, epoch, rows_src, timeout_ns);
     return cudaGetLastError();
 }
 cudaError_t launch_gather_particles(uint8_t *base, uint32_t capacity, uint32_t first, uint32_t n, uint32_t pbr,

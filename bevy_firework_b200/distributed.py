@@ -1,6 +1,9 @@
 """Multi-GPU plumbing: one process per GPU, spawners sharded across ranks, no collective on the
 simulation path. The only exchange is the optional render extract: an
-all-gather-v of the per-GPU ParticleInstance buffers over NCCL (NVLink / NVSwitch).
+all-gather-v of the per-GPU ParticleInstance buffers, either through NCCL
+(``all_gather_instances``) or fused into the pack kernel as peer stores over NVLink / NVSwitch
+(``PeerGather``: the library's ``fw_gather_*`` exports; torch.distributed only carries the 88-byte
+buffer handles once).
 
 ``torch.distributed`` is used purely as plumbing; with the ``gloo`` backend the same code runs
 on CPU tensors (tests/test_distributed_gloo.py).
@@ -64,3 +67,49 @@ def all_gather_instances(engine, group=None, slack_rows: int = 1 << 16) -> Tuple
     buf = torch.empty((cap, 16), dtype=torch.float32, device=f"cuda:{engine.device}")
     n = engine.pack_instances_device(buf.data_ptr(), cap)
     return all_gather_rows(buf[:n], group)
+
+
+class PeerGather:
+    """All-gather-v of the instance rows fused into the pack kernel: every rank maps every rank's
+    gather buffer (CUDA IPC) and ``fw_gather_instances`` stores this rank's rows straight into its
+    region of all of them, with device-side ready / landed flags instead of a host barrier.
+
+        pg = PeerGather(engine, cap_rows_per_rank)      # collective (handle exchange)
+        pg.issue()                                      # collective, asynchronous
+        rows, counts = pg.result()                      # torch view of the gathered rows
+    """
+
+    def __init__(self, engine, cap_rows_per_rank: int, group=None):
+        self.engine = engine
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        mine = engine.gather_create(self.world, self.rank, int(cap_rows_per_rank))
+        handles: List[bytes] = [b""] * self.world
+        dist.all_gather_object(handles, mine, group=group)
+        engine.gather_connect(handles)
+        self.group = group
+
+    def issue(self):
+        self.engine.gather_instances()
+
+    def result(self) -> Tuple[torch.Tensor, List[int]]:
+        """rows of all ranks concatenated in rank order (a copy; the regions themselves stay in the
+        gather buffer at ``rank * stride`` rows for consumers that draw per region)"""
+        ptr, counts, stride = self.engine.gather_result(self.world)
+        dev = torch.device("cuda", self.engine.device)
+        parts = [_device_view(ptr + r * stride * 64, counts[r], dev) for r in range(self.world)]
+        return torch.cat(parts, dim=0), counts
+
+    def close(self):
+        self.engine.gather_destroy()
+
+
+def _device_view(ptr: int, n_rows: int, device) -> torch.Tensor:
+    """[n_rows, 16] float32 tensor aliasing library-owned device memory"""
+    if n_rows == 0:
+        return torch.empty((0, 16), dtype=torch.float32, device=device)
+
+    class _Mem:
+        __cuda_array_interface__ = {"shape": (n_rows, 16), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+    return torch.as_tensor(_Mem(), device=device)

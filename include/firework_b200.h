@@ -301,6 +301,35 @@ int fw_read_aabb(fw_context *ctx, uint32_t spawner_key, float out_min[3], float 
  * *n_rows is valid after fw_sync. */
 int fw_pack_instances_device(fw_context *ctx, void *device_dst, uint64_t cap_rows,
                              uint64_t *n_rows);
+/* ---- multi-GPU render extract over NVLink peer memory. One context per
+ * GPU (same process or one process per GPU); spawners are sharded across them and never interact
+ * (src/core.rs:583-589), so the only exchange is the hand-off of the instance rows that
+ * extract_firework_components (src/render.rs:439-461) wants on the GPU that draws. Every rank owns
+ * a gather buffer [header | n_ranks regions of cap_rows_per_rank rows]; fw_gather_instances packs
+ * this rank's live rows and STORES them into its region of every rank's buffer (peer-mapped over
+ * NVLink / NVSwitch), bracketed by device-side ready / landed flags -- an all-gather-v with no
+ * host synchronisation and no staging copy. */
+#define FW_GATHER_MAX_RANKS 16
+typedef struct fw_gather_handle { /* how another context / process maps a rank's gather buffer */
+    uint8_t ipc[64];              /* cudaIpcMemHandle_t */
+    uint64_t address;             /* device address in the creating process (same-process peers) */
+    uint64_t bytes;
+    int32_t device;               /* CUDA ordinal in the creating process */
+    int32_t pid;
+} fw_gather_handle;
+/* allocate this rank's gather buffer; *out is what the other ranks pass to fw_gather_connect */
+int fw_gather_create(fw_context *ctx, uint32_t n_ranks, uint32_t my_rank, uint64_t cap_rows_per_rank,
+                     fw_gather_handle *out);
+/* map every rank's buffer: handles[r] = rank r's fw_gather_create output (handles[my_rank] ignored) */
+int fw_gather_connect(fw_context *ctx, const fw_gather_handle *handles, uint32_t n_handles);
+/* collective: every rank calls it once per extract. Asynchronous on the context's stream. */
+int fw_gather_instances(fw_context *ctx);
+/* waits for the last fw_gather_instances; rank r's rows_per_rank[r] rows (same order as
+ * fw_pack_instances_device) start at *device_rows + r * *region_stride_rows * 64 bytes */
+int fw_gather_result(fw_context *ctx, void **device_rows, uint64_t *rows_per_rank, uint32_t n_ranks,
+                     uint64_t *region_stride_rows);
+int fw_gather_destroy(fw_context *ctx);
+
 /* total live particles over the context (synchronises) */
 int fw_total_live(fw_context *ctx, uint64_t *out);
 

@@ -52,6 +52,18 @@ def _worker(rank, world, port, out_dir):
         rows, counts = all_gather_instances(eng)
         np.save(os.path.join(out_dir, f"rows{rank}.npy"), rows.cpu().numpy())
         np.save(os.path.join(out_dir, f"counts{rank}.npy"), np.array(counts))
+        # the same exchange fused into the pack kernel (peer stores over NVLink, CUDA IPC mapping),
+        # twice: the second epoch exercises the ready / landed flag protocol on a reused buffer
+        from bevy_firework_b200.distributed import PeerGather
+
+        pg = PeerGather(eng, cap_rows_per_rank=max(counts) + 1024)
+        for _ in range(2):
+            pg.issue()
+            prow, pcounts = pg.result()
+        np.save(os.path.join(out_dir, f"prows{rank}.npy"), prow.cpu().numpy())
+        assert pcounts == counts, (pcounts, counts)
+        dist.barrier()
+        pg.close()
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -68,6 +80,8 @@ def test_two_rank_shard_and_all_gather(tmp_path):
     r0, r1 = np.load(tmp_path / "rows0.npy"), np.load(tmp_path / "rows1.npy")
     counts = np.load(tmp_path / "counts0.npy")
     assert r0.shape == r1.shape and (r0 == r1).all()      # both GPUs hold the whole scene
+    for r in range(world):                                 # peer-store gather == NCCL gather, bit for bit
+        assert np.load(tmp_path / f"prows{r}.npy").tobytes() == r0.tobytes()
     assert r0.shape[0] == counts.sum()
     # sharding does not change the result: a single GPU simulating all 8 spawners produces the
     # same rows (RNG streams are keyed by spawner, not by rank)
@@ -81,3 +95,42 @@ def test_two_rank_shard_and_all_gather(tmp_path):
     eng.close()
     assert single.shape == r0.shape
     assert single.tobytes() == r0.tobytes()
+
+
+def test_peer_gather_two_contexts_one_process():
+    """one process driving two GPUs (how a single Bevy app would): plain peer access instead of IPC"""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from bevy_firework_b200._native import Engine
+    from bevy_firework_b200.distributed import shard_range
+
+    engs = [Engine(device=r, seed=0x00F12E00) for r in range(2)]
+    for r, e in enumerate(engs):
+        _simulate(e, shard_range(N_SPAWNERS, 2, r))
+    lives = [e.total_live() for e in engs]
+    handles = [e.gather_create(2, r, max(lives) + 256) for r, e in enumerate(engs)]
+    for e in engs:
+        e.gather_connect(handles)
+    for e in engs:       # every rank issues before anyone waits
+        e.gather_instances()
+    got = []
+    for e in engs:
+        ptr, counts, stride = e.gather_result(2)
+        assert counts == lives
+        from bevy_firework_b200.distributed import _device_view
+
+        dev = torch.device("cuda", e.device)
+        got.append(torch.cat([_device_view(ptr + r * stride * 64, counts[r], dev) for r in range(2)]).cpu().numpy())
+    assert got[0].tobytes() == got[1].tobytes()
+    # against each context's own packed rows
+    ref = []
+    for e in engs:
+        buf = torch.empty((e.total_live() + 16, 16), dtype=torch.float32, device=f"cuda:{e.device}")
+        n = e.pack_instances_device(buf.data_ptr(), buf.shape[0])
+        ref.append(buf[:n].cpu().numpy())
+    assert np.concatenate(ref).tobytes() == got[0].tobytes()
+    for e in engs:
+        e.gather_destroy()
+        e.close()
