@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- particles updated/sec of the fused per-frame step (spawn + update) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3r|c2|c1|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one frame of the hot path (fw_frame = plan + spawn + update kernels) over the whole
@@ -35,6 +35,9 @@ if ROOT not in sys.path:
 from bevy_firework_b200 import workloads as W  # noqa: E402
 
 ALGO_BYTES_PER_PARTICLE = 156  # 64 B read + 92 B written
+# dominant kernel and its algorithmic bytes per particle, per workload: the
+# compacting variant also moves the two constants (lifetime, initial_scale) with the particle
+KERNEL_OF = {"c3r": ("fw::update_kernel<true,false>", 164), "c5": ("fw::update_kernel<false,true>", 156)}
 DT = float(np.float32(1.0) / np.float32(60.0))
 
 
@@ -48,6 +51,12 @@ def make_workload(name: str, rank: int):
         pos = W.grid_positions(512)
         return ("C3 stress_test.rs x512 spawners, rate 19531/s, lifetime 1 s (~10 M live particles per GPU)",
                 [(base + i, sp, p, ident) for i, p in enumerate(pos)], None, 64, None)
+    if name == "c3r":
+        sp = W.stress_spawner(rate=19531.0, lifetime=1.0, lifetime_spread=0.5)
+        pos = W.grid_positions(512)
+        return ("C3r = C3 with lifetime U[0.5, 1.5] s: deaths anywhere in the Vec, in-place stable compaction "
+                "(~10 M live particles per GPU)",
+                [(base + i, sp, p, ident) for i, p in enumerate(pos)], None, 96, None)
     if name == "c2":
         sp = W.stress_spawner(rate=15625.0)
         pos = W.grid_positions(64)
@@ -224,7 +233,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c3r", "c4", "c5"])
     ap.add_argument("--cpu-steps", type=int, default=8, help="timed frames of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extract", action="store_true", help="also time the full instance-row extract (D2H)")
@@ -325,7 +334,7 @@ def main():
     e2e_steps = max(10, min(args.steps, 200))
     for _ in range(e2e_steps):
         sc.step()
-        k_, t_, counts = eng.counts_all()      # fw_sync + D2H of every stream's state
+        k_, t_, counts = eng.counts_all()      # waits for the frame's state readback (D2H), exact counts
         if keys:
             eng.read_aabb(keys[0])             # served from the same snapshot
     eng.event_record(3)
@@ -335,7 +344,7 @@ def main():
     ms_e2e = max(ms_e2e_dev, ms_e2e_wall)
     updated_e2e = int(prof2.particles_updated)
     h2d = int(prof2.h2d_bytes // max(n2, 1))
-    d2h = int(prof2.d2h_bytes // max(n2, 1)) * 2  # async bound readback + the synchronous snapshot
+    d2h = int(prof2.d2h_bytes // max(n2, 1))  # the frame's own state readback serves fw_counts_all / fw_read_aabb
 
     extract = None
     if args.extract:
@@ -369,7 +378,8 @@ def main():
         peak, peak_src = measured_peak_gbs()
         upd_kernel_ms = kprof.update_ms / args.steps
         per_launch_particles = int(kprof.particles_updated) / args.steps
-        achieved = ALGO_BYTES_PER_PARTICLE * per_launch_particles / (upd_kernel_ms * 1e-3) / 1e9
+        kernel_name, algo_bytes = KERNEL_OF.get(args.workload, ("fw::update_kernel<false,false>", ALGO_BYTES_PER_PARTICLE))
+        achieved = algo_bytes * per_launch_particles / (upd_kernel_ms * 1e-3) / 1e9
         line = {
             "metric": "particles updated/sec (fused step)", "value": updated_all / (ms_all * 1e-3), "unit": "particles/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps,
@@ -385,9 +395,9 @@ def main():
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.workload)[0], "traffic_source": ncu_traffic(args.workload)[1],
-                         "kernel": "fw::update_kernel<false,false>",
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE * per_launch_particles,
-                         "algorithmic_bytes_per_particle": ALGO_BYTES_PER_PARTICLE,
+                         "kernel": kernel_name,
+                         "algorithmic_bytes_per_launch": algo_bytes * per_launch_particles,
+                         "algorithmic_bytes_per_particle": algo_bytes,
                          "particles_per_launch": per_launch_particles, "kernel_ms": upd_kernel_ms,
                          "peak_source": peak_src,
                          "how": f"CUDA events around the kernel, mean of {args.steps} launches in a second timed "

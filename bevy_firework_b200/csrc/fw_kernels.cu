@@ -586,14 +586,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
         : "memory");
 }
 
-// look-back status word of a tile: epoch<<34 | flag<<32 | value
+// look-back status word of a tile: epoch<<34 | flag<<32 | value. The whole message is this one
+// 64-bit word, so relaxed gpu-scope accesses are enough (as in CUB's single-word tile status): a
+// release store would first drain the CTA's previous tile of particle stores, an acquire load
+// invalidates L1 -- measured on C3r as 16 % + 38 % of the kernel (profiles/r1_tuning.md). The
+// in-place hazard (a later tile storing over slots this tile read) is covered by construction:
+// the word is written after a __syncthreads() that follows the USE of every loaded value, i.e.
+// when this tile's loads have long returned.
 constexpr unsigned long long kFlagAgg = 1ull, kFlagPrefix = 2ull;
-__device__ __forceinline__ void st_release(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *p) {
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
     unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -676,7 +682,6 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
                                     : t.tile_prefix + (size_t)variant * (t.slots_cap + 1u);
     const float dt = f.header->dt;
     const uint32_t epoch = f.header->epoch;
-
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
@@ -786,7 +791,7 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
                 if (w < warp) before += n;
                 tile_alive += n;
             }
-            if (tid == 0) {
+            if (warp == 0) {
                 // (the host's tile table holds upper bounds: a tile may lie entirely past the count)
                 const uint32_t tile_valid = tile_first < n_update ? min(n_update - tile_first, (uint32_t)kTile) : 0u;
                 const uint32_t tile_dead = tile_valid - tile_alive;
@@ -794,21 +799,29 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
                 const unsigned long long tag = (unsigned long long)epoch << 34;
                 uint32_t excl = 0;
                 if (e.tile != 0u) {
-                    st_release(status, tag | (kFlagAgg << 32) | tile_dead);
-                    // decoupled look-back over the preceding tiles of the same stream
-                    const unsigned long long *p = status - 1;
-                    for (uint32_t back = 0; back < e.tile;) {
-                        const unsigned long long w = ld_acquire(p);
-                        if ((w >> 34) != (unsigned long long)epoch || ((w >> 32) & 3ull) == 0ull) continue; // not yet published
-                        excl += (uint32_t)w;
-                        if (((w >> 32) & 3ull) == kFlagPrefix) break;
-                        back++;
-                        p--;
+                    if (lane == 0) st_status(status, tag | (kFlagAgg << 32) | tile_dead);
+                    // decoupled look-back over the preceding tiles of the same stream, 32 at a time
+                    // (one lane per predecessor; a serial walk by one thread cost ~0.35 us per step
+                    // and 77 steps per stream at C3r, profiles/r1_tuning.md)
+                    for (uint32_t nearest = e.tile - 1u;; nearest -= 32u) {
+                        const bool in_stream = lane <= nearest; // predecessor nearest - lane exists
+                        unsigned long long w;
+                        bool ready;
+                        do {
+                            w = in_stream ? ld_status(status - 1 - lane - (e.tile - 1u - nearest)) : (tag | (kFlagPrefix << 32));
+                            ready = (w >> 34) == (unsigned long long)epoch && ((w >> 32) & 3ull) != 0ull;
+                        } while (!__all_sync(0xffffffffu, ready));
+                        const uint32_t prefix_lanes = __ballot_sync(0xffffffffu, ((w >> 32) & 3ull) == kFlagPrefix);
+                        const uint32_t upto = prefix_lanes ? (uint32_t)__ffs((int)prefix_lanes) - 1u : 31u;
+                        excl += __reduce_add_sync(0xffffffffu, lane <= upto ? (uint32_t)w : 0u);
+                        if (prefix_lanes) break;
                     }
                 }
-                st_release(status, tag | (kFlagPrefix << 32) | (excl + tile_dead));
-                sm.excl_dead = excl;
-                if (tile_first + kTile >= n_update) stp->dead = excl + tile_dead; // last tile of the stream
+                if (lane == 0) {
+                    st_status(status, tag | (kFlagPrefix << 32) | (excl + tile_dead));
+                    sm.excl_dead = excl;
+                    if (tile_first + kTile >= n_update) stp->dead = excl + tile_dead; // last tile of the stream
+                }
             }
             __syncthreads();
             const uint32_t alive_before = before + __popc(alive_mask & ((1u << lane) - 1u));

@@ -49,11 +49,12 @@ def sparks_spawner(rate: float = 1000.0) -> ParticleSpawner:
     )
 
 
-def stress_spawner(rate: float = 160000.0, lifetime: float = 1.0) -> ParticleSpawner:
-    """examples/stress_test.rs:91-129 (C2/C3)."""
+def stress_spawner(rate: float = 160000.0, lifetime: float = 1.0, lifetime_spread: float = 0.0) -> ParticleSpawner:
+    """examples/stress_test.rs:91-129 (C2/C3). ``lifetime_spread`` > 0 draws the lifetime from
+    [lifetime - spread, lifetime + spread] (deaths anywhere in the Vec: the compacting update)."""
     return ParticleSpawner(
         particle_settings=[ParticleSettings(
-            lifetime=RandF32.constant(lifetime),
+            lifetime=RandF32(lifetime - lifetime_spread, lifetime + lifetime_spread) if lifetime_spread else RandF32.constant(lifetime),
             initial_scale=RandF32(0.02, 0.08),
             scale_curve=FireworkCurve.constant(1.0),
             base_color=_fire_gradient((10.0, 7.0, 1.0, 1.0)),
