@@ -178,6 +178,7 @@ struct fw_context {
     NestedOut *d_nested_out = nullptr;
     uint32_t nested_out_cap = 0;
     int grids[kNumVariants] = {0, 0, 0, 0};
+    int team_size = 0; // CTAs per team of the compacting update kernels (= SM count)
     uint32_t variant_streams[kNumVariants] = {0, 0, 0, 0};
 
     // profile accumulators
@@ -757,7 +758,7 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
     if ((rc = ensure_slots(c, 1))) { g_global_error = c->error; return rc; }
     if ((rc = ensure_emitters(c, 1))) { g_global_error = c->error; return rc; }
     if ((rc = ensure_tiles(c))) { g_global_error = c->error; return rc; }
-    CU(c, update_grid_size(c->device, c->grids));
+    CU(c, update_grid_size(c->device, c->grids, &c->team_size));
     *out_ctx = c;
     ctx.c = nullptr;
     return FW_OK;
@@ -1412,7 +1413,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
         if (prof) CU(ctx, cudaEventRecord(fs.ev[2], ctx->stream));
         for (uint32_t v = 0; v < kNumVariants; v++) {
             if (!ctx->variant_streams[v]) continue;
-            CU(ctx, launch_update(t, f, v, ctx->grids[v], ctx->stream));
+            CU(ctx, launch_update(t, f, v, ctx->grids[v], ctx->team_size, ctx->stream));
             launches++;
         }
         if (forked) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); // join

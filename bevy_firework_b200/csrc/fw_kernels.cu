@@ -14,6 +14,7 @@
 //
 // Built with -fmad=false (see fw_math.cuh).
 #include <algorithm>
+#include <cstdio>
 
 #include "fw_math.cuh"
 
@@ -25,7 +26,7 @@
 #define FW_MINB 5
 #endif
 #ifndef FW_MINB_COMPACT
-#define FW_MINB_COMPACT 4 // compaction also carries last_emitted_age / destroyed-capture state
+#define FW_MINB_COMPACT 5 // 48 registers, no spills; C3r: 4 CTAs/SM 0.667 ms, 5 0.601 ms, 6 (40 regs) 0.591 ms
 #endif
 #ifndef FW_MINB_COLLIDE
 #define FW_MINB_COLLIDE 3 // the collision variants are compute-bound and need ~80 registers
@@ -574,6 +575,7 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -651,7 +653,10 @@ struct alignas(16) UpdateSmem {
     uint64_t bar[2];
     TileRef ref[2];
     uint32_t warp_alive[kUpdateThreads / 32];
-    uint32_t excl_dead; // dead particles of the stream before this tile (compact variants)
+    uint32_t sink[kUpdateThreads / 32];          // see consume-before-publish in update_kernel
+    uint32_t team_cut[16];                       // first tile of every team's share (compact variants)
+    uint32_t lb_sum[kUpdateThreads / 32];        // look-back partial sums, one per warp
+    uint32_t lb_has_prefix[kUpdateThreads / 32]; // that warp's 32 predecessors include an inclusive prefix
 };
 template <bool COLLIDE>
 struct CandQueue { // broad-phase candidates of cast_ray, one column per thread
@@ -669,29 +674,65 @@ struct CandQueue<false> {
 // settings block with a bulk async copy while the CTA works on the current tile.
 template <bool COMPACT, bool COLLIDE>
 __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (COMPACT ? FW_MINB_COMPACT : FW_MINB))
-    update_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant) {
+    update_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant, uint32_t team_size) {
     __shared__ UpdateSmem sm;
     __shared__ CandQueue<COLLIDE> cq;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const bool derive = f.header->derive != 0u;
-    const uint32_t n_tiles = derive ? f.header->host_n_tiles[variant] : t.plan->n_tiles[variant];
-    if (blockIdx.x >= n_tiles) return;
-    const uint32_t tile_base = derive ? f.header->host_tile_base[variant] : t.plan->tile_base[variant];
+    const uint32_t all_tiles = derive ? f.header->host_n_tiles[variant] : t.plan->n_tiles[variant];
+    // Tile order. FIFO tiles are independent: CTA b takes tiles b, b + grid, ... A compacting tile
+    // waits for the aggregates of the preceding tiles of its stream, which couples the CTAs that
+    // share a stream; with one global round robin the stream boundaries shift every round and the
+    // whole grid falls into lock-step (everybody loads, then everybody computes, then everybody
+    // stores: nothing overlaps, C3r 0.60 ms). So the grid is split into TEAMS of team_size CTAs
+    // (one CTA slot of every SM), each team owns a contiguous share of the tiles and deals it
+    // round robin among its members: teams only meet at the one stream that straddles a boundary,
+    // drift apart in phase, and the CTAs resident on an SM are again in different phases.
+    // Team shares start at stream boundaries (a stream that straddled two teams would make the
+    // later team wait for the END of the earlier team's share); if that leaves the shares badly
+    // unbalanced (few, huge streams) everybody falls back to the global round robin.
     const uint32_t n_slots = f.header->n_slots;
     const uint32_t *prefix = derive ? f.host_tile_prefix + (size_t)variant * (n_slots + 1u)
                                     : t.tile_prefix + (size_t)variant * (t.slots_cap + 1u);
+    uint32_t tile_begin = blockIdx.x, tile_stride = gridDim.x, n_tiles = all_tiles;
+    if (COMPACT && team_size != 0u && gridDim.x >= 2u * team_size && all_tiles != 0u) {
+        const uint32_t n_teams = min(gridDim.x / team_size, 15u);
+        if (tid <= n_teams) {
+            uint32_t cut = (uint32_t)((uint64_t)all_tiles * tid / n_teams);
+            if (tid != 0u && tid != n_teams) cut = prefix[find_tile(prefix, n_slots, cut).stream]; // snap down to the stream's first tile
+            sm.team_cut[tid] = cut;
+        }
+        __syncthreads();
+        uint32_t biggest = 0;
+        for (uint32_t k = 0; k < n_teams; k++) biggest = max(biggest, sm.team_cut[k + 1u] - sm.team_cut[k]);
+        if (biggest <= 2u * (all_tiles / n_teams + 1u)) {
+            const uint32_t team = blockIdx.x / team_size;
+            if (team >= n_teams) return; // (grid not a multiple of the team size)
+            n_tiles = sm.team_cut[team + 1u];
+            tile_begin = sm.team_cut[team] + blockIdx.x % team_size;
+            tile_stride = team_size;
+        }
+    }
+    if (tile_begin >= n_tiles) return;
+    const uint32_t tile_base = derive ? f.header->host_tile_base[variant] : t.plan->tile_base[variant];
     const float dt = f.header->dt;
     const uint32_t epoch = f.header->epoch;
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
-        const TileRef r = prepare_tile(t, f, prefix, n_slots, blockIdx.x, derive);
+        const TileRef r = prepare_tile(t, f, prefix, n_slots, tile_begin, derive);
         sm.ref[0] = r;
         bulk_load(&sm.settings[0], &t.settings[r.stream], sizeof(DevParticleSettings), &sm.bar[0]);
     }
     __syncthreads();
     uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+#ifdef FW_DEBUG_TIMING
+    long long dbg[6] = {0, 0, 0, 0, 0, 0}, dbg_t = clock64();
+#define FW_DBG(k) { const long long now__ = clock64(); dbg[k] += now__ - dbg_t; dbg_t = now__; }
+#else
+#define FW_DBG(k)
+#endif
+    for (uint32_t tile = tile_begin; tile < n_tiles; tile += tile_stride, it++) {
         const uint32_t buf = it & 1u;
         const TileRef e = sm.ref[buf];
         const StreamDesc d = t.descs[e.stream];
@@ -724,110 +765,139 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
             for (uint32_t j = 0; j < kMaxLea; j++) lea_v[j] = (valid && j < d.n_lea) ? lea_array(d.base, d.capacity, j)[slot] : 0.f;
         }
         // next tile: stream lookup + settings prefetch into the other buffer (every thread left
-        // that buffer at the __syncthreads closing the previous iteration)
-        if (tid == 0 && tile + gridDim.x < n_tiles) {
-            const TileRef r = prepare_tile(t, f, prefix, n_slots, tile + gridDim.x, derive);
-            sm.ref[buf ^ 1u] = r;
-            bulk_load(&sm.settings[buf ^ 1u], &t.settings[r.stream], sizeof(DevParticleSettings), &sm.bar[buf ^ 1u]);
-        }
-        mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
-        const DevParticleSettings &ps = sm.settings[buf];
+        // that buffer at the __syncthreads closing the previous iteration). ~2.5k cycles of
+        // dependent loads for one thread: on thread 0, unless the tile's aggregate waits for warp 0
+        // (compacting variants: the last warp does it, after the aggregate is out)
+        const uint32_t prep_tid = COMPACT ? kUpdateThreads - 32u : 0u;
+        auto prepare_next = [&]() {
+            if (tid == prep_tid && tile + tile_stride < n_tiles) {
+                const TileRef r = prepare_tile(t, f, prefix, n_slots, tile + tile_stride, derive);
+                sm.ref[buf ^ 1u] = r;
+                bulk_load(&sm.settings[buf ^ 1u], &t.settings[r.stream], sizeof(DevParticleSettings), &sm.bar[buf ^ 1u]);
+            }
+        };
+        if (!COMPACT) prepare_next();
 
-        // ---- reference src/core.rs:591-658
+        // ---- compacting variants, part 1: this tile's death count (its look-back aggregate) goes
+        // out as early as possible -- every later tile of the stream waits for it. Without
+        // collisions a particle dies iff age + dt >= lifetime (:594-599), known as soon as the
+        // loads are back; destroy_on_collision is only known after the step (EARLY == false).
+        constexpr bool EARLY = COMPACT && !COLLIDE;
         float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
         float scale = 0.f, age;
-        bool destroyed_by_collision;
-        bool alive = step_particle<COLLIDE>(t, ps, dt, valid, M0, M1, M2, M3, K, c0, c1, scale, age, destroyed_by_collision,
-                                            COLLIDE ? cq.q + tid : nullptr);
-        // destroyed-particle stream (:588,597,637): the record the handler receives keeps the old
-        // colours (and the old scale unless a collision destroyed it); read them before this
-        // tile publishes anything, i.e. before later tiles may compact over these slots
-        const bool capture = COMPACT && d.destroyed_base != nullptr && valid && !alive;
-        if (capture) {
-            c0 = a.o0[slot];
-            c1 = a.o1[slot];
-            if (!destroyed_by_collision) {
-                scale = a.o2[slot];
-                M0.w = age; // age is bumped before the lifetime test (:594-598)
-            }
-        }
-        const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
-        const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
-        const uint32_t n_alive_w = __popc(alive_mask);
-
-        // ---- per-stream AABB of position -/+ scale (reference src/render.rs:681-692). Measured: this
-        // inline form (one axis per lane, bounds pre-checked through L1) costs nothing, whereas reading
-        // the bounds from L2 first put 10 % on the kernel (profiles/r1_tuning.md)
-        {
-            uint32_t mn[3], mx[3];
-            mn[0] = alive ? enc_f32(M0.x - scale) : 0xFFFFFFFFu;
-            mn[1] = alive ? enc_f32(M0.y - scale) : 0xFFFFFFFFu;
-            mn[2] = alive ? enc_f32(M0.z - scale) : 0xFFFFFFFFu;
-            mx[0] = alive ? enc_f32(M0.x + scale) : 0u;
-            mx[1] = alive ? enc_f32(M0.y + scale) : 0u;
-            mx[2] = alive ? enc_f32(M0.z + scale) : 0u;
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
-                mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
-            }
-            if (lane < 3u) {
-                const uint32_t lo_inv = ~(lane == 0 ? mn[0] : (lane == 1 ? mn[1] : mn[2]));
-                const uint32_t hi = lane == 0 ? mx[0] : (lane == 1 ? mx[1] : mx[2]);
-                if (lo_inv > stp->aabb_min_inv[lane]) atomicMax(&stp->aabb_min_inv[lane], lo_inv);
-                if (hi > stp->aabb_max[lane]) atomicMax(&stp->aabb_max[lane], hi);
-            }
-        }
-
-        // ---- destination slot of a survivor
-        uint32_t dslot = slot;
-        if (COMPACT) {
-            if (lane == 0) sm.warp_alive[warp] = n_alive_w;
-            __syncthreads(); // every load of this tile has been consumed by now
-            uint32_t before = 0, tile_alive = 0;
+        uint32_t alive_mask = 0, before = 0, tile_dead = 0;
+        unsigned long long *status = t.lookback + tile_base + tile;
+        const unsigned long long tag = (unsigned long long)epoch << 34;
+        auto publish_aggregate = [&](bool alive_now) {
+            alive_mask = __ballot_sync(0xffffffffu, alive_now);
+            if (lane == 0) sm.warp_alive[warp] = __popc(alive_mask);
+            __syncthreads(); // every load of this tile has returned by now (see consume_loads)
+            uint32_t tile_alive = 0;
 #pragma unroll
             for (uint32_t w = 0; w < kUpdateThreads / 32; w++) {
                 const uint32_t n = sm.warp_alive[w];
                 if (w < warp) before += n;
                 tile_alive += n;
             }
-            if (warp == 0) {
-                // (the host's tile table holds upper bounds: a tile may lie entirely past the count)
-                const uint32_t tile_valid = tile_first < n_update ? min(n_update - tile_first, (uint32_t)kTile) : 0u;
-                const uint32_t tile_dead = tile_valid - tile_alive;
-                unsigned long long *status = t.lookback + tile_base + tile;
-                const unsigned long long tag = (unsigned long long)epoch << 34;
-                uint32_t excl = 0;
-                if (e.tile != 0u) {
-                    if (lane == 0) st_status(status, tag | (kFlagAgg << 32) | tile_dead);
-                    // decoupled look-back over the preceding tiles of the same stream, 32 at a time
-                    // (one lane per predecessor; a serial walk by one thread cost ~0.35 us per step
-                    // and 77 steps per stream at C3r, profiles/r1_tuning.md)
-                    for (uint32_t nearest = e.tile - 1u;; nearest -= 32u) {
-                        const bool in_stream = lane <= nearest; // predecessor nearest - lane exists
-                        unsigned long long w;
-                        bool ready;
-                        do {
-                            w = in_stream ? ld_status(status - 1 - lane - (e.tile - 1u - nearest)) : (tag | (kFlagPrefix << 32));
-                            ready = (w >> 34) == (unsigned long long)epoch && ((w >> 32) & 3ull) != 0ull;
-                        } while (!__all_sync(0xffffffffu, ready));
-                        const uint32_t prefix_lanes = __ballot_sync(0xffffffffu, ((w >> 32) & 3ull) == kFlagPrefix);
-                        const uint32_t upto = prefix_lanes ? (uint32_t)__ffs((int)prefix_lanes) - 1u : 31u;
-                        excl += __reduce_add_sync(0xffffffffu, lane <= upto ? (uint32_t)w : 0u);
-                        if (prefix_lanes) break;
+            // (the host's tile table holds upper bounds: a tile may lie entirely past the count)
+            const uint32_t tile_valid = tile_first < n_update ? min(n_update - tile_first, (uint32_t)kTile) : 0u;
+            tile_dead = tile_valid - tile_alive;
+            if (tid == 0 && e.tile != 0u) st_status(status, tag | (kFlagAgg << 32) | tile_dead);
+        };
+        if (EARLY) {
+            // In place is safe because the aggregate is published after a barrier that follows the
+            // RETURN of every load of the tile: a real instruction consumes each loaded register
+            // (the math that uses them for good only comes after the barrier)
+            const bool alive_early = valid && !(M0.w + dt >= K.x);
+            uint32_t sink = __float_as_uint(M1.w) ^ __float_as_uint(M2.w) ^ __float_as_uint(M3.y);
+#pragma unroll
+            for (uint32_t j = 0; j < kMaxLea; j++) sink ^= __float_as_uint(lea_v[j]);
+            if (d.destroyed_base != nullptr && valid && !alive_early) { // destroyed-particle record, see below
+                c0 = a.o0[slot];
+                c1 = a.o1[slot];
+                scale = a.o2[slot];
+                sink ^= __float_as_uint(c0.w) ^ __float_as_uint(c1.w) ^ __float_as_uint(scale);
+            }
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sm.sink[warp])), "r"(sink) : "memory");
+            publish_aggregate(alive_early);
+            FW_DBG(0)
+            prepare_next();
+        }
+        mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
+        const DevParticleSettings &ps = sm.settings[buf];
+
+        // ---- reference src/core.rs:591-658
+        bool destroyed_by_collision;
+        bool alive = step_particle<COLLIDE>(t, ps, dt, valid, M0, M1, M2, M3, K, c0, c1, scale, age, destroyed_by_collision,
+                                            COLLIDE ? cq.q + tid : nullptr);
+        // destroyed-particle stream (:588,597,637): the record the handler receives keeps the old
+        // colours (and the old scale unless a collision destroyed it); read them before this
+        // tile publishes its prefix, i.e. before later tiles may compact over these slots
+        // (EARLY read them above, before the aggregate went out)
+        const bool capture = COMPACT && d.destroyed_base != nullptr && valid && !alive;
+        if (capture) {
+            if (!EARLY) {
+                c0 = a.o0[slot];
+                c1 = a.o1[slot];
+                if (!destroyed_by_collision) scale = a.o2[slot];
+            }
+            if (!destroyed_by_collision) M0.w = age; // age is bumped before the lifetime test (:594-598)
+        }
+        FW_DBG(1)
+        if (COMPACT && !EARLY) {
+            publish_aggregate(alive);
+            prepare_next();
+        }
+        if (!COMPACT) alive_mask = __ballot_sync(0xffffffffu, alive);
+        const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
+
+        // ---- destination slot of a survivor
+        uint32_t dslot = slot;
+        if (COMPACT) {
+            // part 2: decoupled look-back over the preceding tiles of the same stream, 256 at a
+            // time: one THREAD per predecessor, so a stream of up to 256 tiles needs a single round
+            // of status loads (a serial walk by one thread cost ~0.35 us per step, a walk by one
+            // warp up to three dependent rounds at C3r's 77 tiles; profiles/r1_tuning.md)
+            uint32_t excl = 0;
+            if (e.tile != 0u) {
+                for (uint32_t nearest = e.tile - 1u;; nearest -= (uint32_t)kTile) {
+                    const bool in_stream = tid <= nearest; // predecessor nearest - tid exists
+                    unsigned long long w;
+                    bool ready;
+                    do {
+                        w = in_stream ? ld_status(status - 1 - tid - (e.tile - 1u - nearest)) : (tag | (kFlagPrefix << 32));
+                        ready = (w >> 34) == (unsigned long long)epoch && ((w >> 32) & 3ull) != 0ull;
+                    } while (!__all_sync(0xffffffffu, ready));
+                    FW_DBG(2)
+                    const uint32_t prefix_lanes = __ballot_sync(0xffffffffu, ((w >> 32) & 3ull) == kFlagPrefix);
+                    const uint32_t upto = prefix_lanes ? (uint32_t)__ffs((int)prefix_lanes) - 1u : 31u;
+                    const uint32_t part = __reduce_add_sync(0xffffffffu, lane <= upto ? (uint32_t)w : 0u);
+                    if (lane == 0) {
+                        sm.lb_sum[warp] = part;
+                        sm.lb_has_prefix[warp] = prefix_lanes != 0u;
                     }
-                }
-                if (lane == 0) {
-                    st_status(status, tag | (kFlagPrefix << 32) | (excl + tile_dead));
-                    sm.excl_dead = excl;
-                    if (tile_first + kTile >= n_update) stp->dead = excl + tile_dead; // last tile of the stream
+                    __syncthreads();
+                    bool found = false;
+#pragma unroll
+                    for (uint32_t w8 = 0; w8 < kUpdateThreads / 32; w8++) {
+                        if (!found) {
+                            excl += sm.lb_sum[w8];
+                            found = sm.lb_has_prefix[w8] != 0u;
+                        }
+                    }
+                    if (found) break;
+                    __syncthreads(); // the warp slots are rewritten by the next round
                 }
             }
-            __syncthreads();
+            if (tid == 0) {
+                st_status(status, tag | (kFlagPrefix << 32) | (excl + tile_dead));
+                if (tile_first + kTile >= n_update) stp->dead = excl + tile_dead; // last tile of the stream
+            }
+            FW_DBG(3)
             const uint32_t alive_before = before + __popc(alive_mask & ((1u << lane) - 1u));
-            dslot = wrap(head + tile_first - sm.excl_dead + alive_before, d.capacity);
+            dslot = wrap(head + tile_first - excl + alive_before, d.capacity);
             if (capture) { // destroyed particles, in Vec order, into the side block
-                const uint32_t di = sm.excl_dead + (tid - alive_before);
+                const uint32_t di = excl + (tid - alive_before);
                 const StreamArrays b = stream_arrays(d.destroyed_base, d.capacity);
                 b.m0[di] = M0;
                 b.m1[di] = M1;
@@ -859,8 +929,40 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
             st_pack(a.o1 + dslot, c1);
             st_pack(a.o2 + dslot, scale);
         }
+
+        // ---- per-stream AABB of position -/+ scale (reference src/render.rs:681-692), after the
+        // stores so that nothing on the way to them waits for it. One axis per lane, bounds
+        // pre-checked through L1 (stale but cheap; reading them from L2 first cost 10 %,
+        // profiles/r1_tuning.md)
+        {
+            uint32_t mn[3], mx[3];
+            mn[0] = alive ? enc_f32(M0.x - scale) : 0xFFFFFFFFu;
+            mn[1] = alive ? enc_f32(M0.y - scale) : 0xFFFFFFFFu;
+            mn[2] = alive ? enc_f32(M0.z - scale) : 0xFFFFFFFFu;
+            mx[0] = alive ? enc_f32(M0.x + scale) : 0u;
+            mx[1] = alive ? enc_f32(M0.y + scale) : 0u;
+            mx[2] = alive ? enc_f32(M0.z + scale) : 0u;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
+                mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
+            }
+            if (lane < 3u) {
+                const uint32_t lo_inv = ~(lane == 0 ? mn[0] : (lane == 1 ? mn[1] : mn[2]));
+                const uint32_t hi = lane == 0 ? mx[0] : (lane == 1 ? mx[1] : mx[2]);
+                if (lo_inv > stp->aabb_min_inv[lane]) atomicMax(&stp->aabb_min_inv[lane], lo_inv);
+                if (hi > stp->aabb_max[lane]) atomicMax(&stp->aabb_max[lane], hi);
+            }
+        }
+        FW_DBG(4)
         __syncthreads(); // settings / tile-ref buffers are reused by the next iterations
+        FW_DBG(5)
     }
+#ifdef FW_DEBUG_TIMING
+    if (COMPACT && (tid == 0 || tid == 200) && (blockIdx.x == 5 || blockIdx.x == 400) && f.header->epoch % 50u == 0u)
+        printf("cta %u tid %u iters %u | loads+agg %lld math %lld spin %lld lbbar %lld stores+aabb %lld endbar %lld\n", blockIdx.x, tid, it,
+               dbg[0] / it, dbg[1] / it, dbg[2] / it, dbg[3] / it, dbg[4] / it, dbg[5] / it);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1030,17 +1132,18 @@ cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uin
     nested_spawn_kernel<<<dim3(gx, n_cmds), 256, 0, s>>>(t, f, phase);
     return cudaGetLastError();
 }
-cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, cudaStream_t s) {
+cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, int team_size, cudaStream_t s) {
+    const uint32_t ts = (uint32_t)team_size;
     switch (variant) {
-    case kFifo: update_kernel<false, false><<<grid, kUpdateThreads, 0, s>>>(t, f, variant); break;
-    case kCompact: update_kernel<true, false><<<grid, kUpdateThreads, 0, s>>>(t, f, variant); break;
-    case kFifoCollide: update_kernel<false, true><<<grid, kUpdateThreads, 0, s>>>(t, f, variant); break;
-    case kCompactCollide: update_kernel<true, true><<<grid, kUpdateThreads, 0, s>>>(t, f, variant); break;
+    case kFifo: update_kernel<false, false><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
+    case kCompact: update_kernel<true, false><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
+    case kFifoCollide: update_kernel<false, true><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
+    case kCompactCollide: update_kernel<true, true><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
-cudaError_t update_grid_size(int device, int *grids) {
+cudaError_t update_grid_size(int device, int *grids, int *team_size) {
     int sms = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
@@ -1056,6 +1159,7 @@ cudaError_t update_grid_size(int device, int *grids) {
     // persistent grids: every CTA must be resident (the look-back of the compact variants
     // spins on lower-numbered tiles)
     for (int v = 0; v < (int)kNumVariants; v++) grids[v] = sms * (occ[v] > 0 ? occ[v] : 1);
+    *team_size = sms; // one CTA slot of every SM (see update_kernel)
     return cudaSuccess;
 }
 cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, const PackDst &dst,
