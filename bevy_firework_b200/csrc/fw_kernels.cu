@@ -818,7 +818,8 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
                 scale = a.o2[slot];
                 sink ^= __float_as_uint(c0.w) ^ __float_as_uint(c1.w) ^ __float_as_uint(scale);
             }
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sm.sink[warp])), "r"(sink) : "memory");
+            sink = __reduce_xor_sync(0xffffffffu, sink); // (the REDUX itself reads every lane's registers)
+            if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sm.sink[warp])), "r"(sink) : "memory");
             publish_aggregate(alive_early);
             FW_DBG(0)
             prepare_next();
