@@ -188,6 +188,22 @@ pub struct fw_context {
     _private: [u8; 0],
 }
 
+/// how another context / process maps a rank's gather buffer (include/firework_b200.h)
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct fw_gather_handle {
+    pub ipc: [u8; 64],
+    pub address: u64,
+    pub bytes: u64,
+    pub device: i32,
+    pub pid: i32,
+}
+impl Default for fw_gather_handle {
+    fn default() -> Self {
+        Self { ipc: [0; 64], address: 0, bytes: 0, device: 0, pid: 0 }
+    }
+}
+
 extern "C" {
     pub fn fw_last_global_error() -> *const c_char;
     pub fn fw_last_error(ctx: *const fw_context) -> *const c_char;
@@ -218,4 +234,11 @@ extern "C" {
     pub fn fw_read_aabb(ctx: *mut fw_context, spawner_key: u32, out_min: *mut [f32; 3], out_max: *mut [f32; 3], empty: *mut u32) -> c_int;
     pub fn fw_extract_instances(ctx: *mut fw_context, host_dst: *mut c_void, cap_rows: u64, n_rows: *mut u64) -> c_int;
     pub fn fw_total_live(ctx: *mut fw_context, out: *mut u64) -> c_int;
+    pub fn fw_pack_instances_device(ctx: *mut fw_context, device_dst: *mut c_void, cap_rows: u64, n_rows: *mut u64) -> c_int;
+    // multi-GPU render extract over NVLink peer memory (one context per GPU)
+    pub fn fw_gather_create(ctx: *mut fw_context, n_ranks: u32, my_rank: u32, cap_rows_per_rank: u64, out: *mut fw_gather_handle) -> c_int;
+    pub fn fw_gather_connect(ctx: *mut fw_context, handles: *const fw_gather_handle, n_handles: u32) -> c_int;
+    pub fn fw_gather_instances(ctx: *mut fw_context) -> c_int;
+    pub fn fw_gather_result(ctx: *mut fw_context, device_rows: *mut *mut c_void, rows_per_rank: *mut u64, n_ranks: u32, region_stride_rows: *mut u64) -> c_int;
+    pub fn fw_gather_destroy(ctx: *mut fw_context) -> c_int;
 }

@@ -421,3 +421,65 @@ def test_graph_replay_and_concurrent_spawn_match_plain_launches():
         assert r[0].tobytes() == results[0][0].tobytes()
         assert r[1].tobytes() == results[0][1].tobytes()
         assert r[2:] == results[0][2:]
+
+
+def test_compaction_large_stream_many_tiles(engine, oracle):
+    """one compacting stream of ~1100 tiles: the look-back needs several rounds of 256
+    predecessors, deaths are scattered over the whole Vec; bit-exact state against the oracle."""
+    n = 280_000
+    sp = _idle_spawner(lifetime=RandF32(0.5, 3.0), linear_drag=0.3)
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 1, sp)
+    rng = np.random.default_rng(23)
+    rows = random_rows(rng, n)
+    # long runs of survivors and long runs of deaths, so that whole tiles publish 0 or 256
+    rows["age"][50_000:120_000] = rows["lifetime"][50_000:120_000] * 0.1
+    rows["age"][200_000:230_000] = rows["lifetime"][200_000:230_000] * np.float32(0.9999)
+    engine.write_particles(1, 0, rows)
+    w.write_particles(1, 0, rows)
+    for k in range(12):
+        engine.frame(DT, [])
+        w.frame(DT, [])
+        assert engine.counts(1) == w.counts(1), f"frame {k}"
+    assert 0 < engine.counts(1)[0] < n
+    assert_rows_match(engine.read_particles(1, 0), w.read_particles(1, 0), exact=NO_TRIG)
+
+
+def test_collision_bvh_many_mixed_colliders(engine, oracle):
+    """the BVH broad phase against the oracle's test-every-collider loop: 600 cuboids and spheres
+    of very different sizes (one of them enclosing the whole scene), overlapping boxes, a layer
+    filter that hides a third of them, and a collider with a NaN transform that must never cull."""
+    rng = np.random.default_rng(101)
+    cols = [cuboid((40, 1, 40), (0, -0.5, 0))]
+    for i in range(599):
+        pos = rng.uniform(-6, 6, 3)
+        pos[1] = rng.uniform(0.0, 5.0)
+        layers = 1 if i % 3 else 2
+        if i % 2:
+            q = rng.normal(size=4)
+            q /= np.linalg.norm(q)
+            cols.append(cuboid(rng.uniform(0.05, 1.5, 3), pos, tuple(q), layers=layers))
+        else:
+            cols.append(sphere(float(rng.uniform(0.05, 0.9)), pos, layers=layers))
+    cols.append(sphere(30.0, (0.0, 0.0, 0.0), layers=1))           # everything starts inside it
+    cols.append(cuboid((1, 1, 1), (float("nan"), 0.0, 0.0), layers=1))
+    sp = _idle_spawner(lifetime=RandF32.constant(100.0), linear_drag=0.15,
+                       collision_settings=ParticleCollisionSettings(0.6, 0.2, False, 1))
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 1, sp)
+    engine.set_colliders(cols)
+    w.set_colliders(cols)
+    n = 30000
+    rows = random_rows(rng, n, angular=False)
+    rows["position"] = rng.uniform(-6, 6, (n, 3))
+    rows["position"][:, 1] = rng.uniform(0.0, 5.0, n)
+    rows["velocity"] = rng.uniform(-30, 30, (n, 3))      # up to ~0.9 units per frame: multi-node segments
+    rows["velocity"][::7] = 0.0                          # Dir3 fallback (:758-761)
+    rows["lifetime"] = 100.0
+    rows["age"] = 1.0
+    engine.write_particles(1, 0, rows)
+    w.write_particles(1, 0, rows)
+    for k in range(4):
+        engine.frame(DT, [])
+        w.frame(DT, [])
+        assert_rows_match(engine.read_particles(1, 0), w.read_particles(1, 0), exact=NO_TRIG + ("rotation",), what=f"step {k}")
