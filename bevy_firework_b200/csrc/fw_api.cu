@@ -139,6 +139,11 @@ struct fw_context {
     float4 *d_collider_bounds = nullptr;
     uint32_t n_colliders = 0;
     uint32_t n_bvh_nodes = 0; // 2 float4 per node in d_collider_bounds
+    // pinned staging of (colliders | BVH nodes) for asynchronous re-uploads, a small ring guarded by events
+    uint8_t *h_col_stage[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t col_stage_bytes = 0;
+    cudaEvent_t col_stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t col_stage_next = 0;
     uint32_t *d_tile_prefix = nullptr; // kNumVariants x (slots_cap + 1)
     uint8_t *d_stage = nullptr;        // staging of ParticleData rows (host mirror reads/writes)
     size_t stage_bytes = 0;
@@ -795,6 +800,10 @@ int fw_destroy(fw_context *ctx) {
     cudaFree(ctx->d_emitters);
     cudaFree(ctx->d_colliders);
     cudaFree(ctx->d_collider_bounds);
+    for (auto &h : ctx->h_col_stage)
+        if (h) cudaFreeHost(h);
+    for (auto &ev : ctx->col_stage_ev)
+        if (ev) cudaEventDestroy(ev);
     cudaFree(ctx->d_tile_prefix);
     cudaFree(ctx->d_nested_scratch);
     cudaFree(ctx->d_nested_serial);
@@ -1025,17 +1034,26 @@ int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) 
     if (n && !colliders) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_set_colliders: null");
     for (uint32_t i = 0; i < n; i++)
         if (colliders[i].kind > FW_COLLIDER_SPHERE) return fail(ctx, FW_ERR_UNSUPPORTED, "collider %u: only cuboids and spheres are supported", i);
-    CU(ctx, sync_all(ctx));
-    if (ctx->d_colliders) CU(ctx, cudaFree(ctx->d_colliders));
-    ctx->d_colliders = nullptr;
-    ctx->n_colliders = n;
-    ctx->n_bvh_nodes = 0;
-    topo_changed(ctx);
-    if (ctx->d_collider_bounds) CU(ctx, cudaFree(ctx->d_collider_bounds));
-    ctx->d_collider_bounds = nullptr;
+    // Same collider count as before (moving colliders, re-sent every physics step): same buffers,
+    // same kernel arguments, the copies below are ordered on the context's stream between the
+    // frames around them -- no synchronisation, captured frame graphs stay valid. A different
+    // count reallocates.
+    const bool same_shape = n == ctx->n_colliders && (n == 0 || (ctx->d_colliders && ctx->d_collider_bounds));
+    if (!same_shape) {
+        CU(ctx, sync_all(ctx));
+        if (ctx->d_colliders) CU(ctx, cudaFree(ctx->d_colliders));
+        ctx->d_colliders = nullptr;
+        if (ctx->d_collider_bounds) CU(ctx, cudaFree(ctx->d_collider_bounds));
+        ctx->d_collider_bounds = nullptr;
+        ctx->n_colliders = n;
+        ctx->n_bvh_nodes = 0;
+        topo_changed(ctx);
+        if (n) {
+            CU(ctx, cudaMalloc((void **)&ctx->d_colliders, sizeof(fw_collider) * n));
+            CU(ctx, cudaMalloc((void **)&ctx->d_collider_bounds, sizeof(float4) * 2 * (2 * (size_t)n - 1)));
+        }
+    }
     if (n) {
-        CU(ctx, cudaMalloc((void **)&ctx->d_colliders, sizeof(fw_collider) * n));
-        CU(ctx, cudaMemcpy(ctx->d_colliders, colliders, sizeof(fw_collider) * n, cudaMemcpyHostToDevice));
         // broad phase: world AABB of every collider, inflated well beyond fp32 rounding, under a
         // binary BVH (median split of the centroids along the widest axis, one collider per leaf)
         // stored in depth-first order with skip links, so the kernel walks it without a stack
@@ -1062,9 +1080,28 @@ int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) 
         std::vector<uint32_t> layers(n);
         for (uint32_t i = 0; i < n; i++) layers[i] = colliders[i].layers;
         build_bvh(nodes, order, lo, hi, layers, 0, n);
-        ctx->n_bvh_nodes = (uint32_t)(nodes.size() / 2);
-        CU(ctx, cudaMalloc((void **)&ctx->d_collider_bounds, sizeof(float4) * nodes.size()));
-        CU(ctx, cudaMemcpy(ctx->d_collider_bounds, nodes.data(), sizeof(float4) * nodes.size(), cudaMemcpyHostToDevice));
+        ctx->n_bvh_nodes = (uint32_t)(nodes.size() / 2); // always 2n - 1: one collider per leaf
+        // both arrays through a pinned staging slot: the caller's array is free on return and the
+        // host never waits for the stream (a pageable source would)
+        const size_t col_bytes = sizeof(fw_collider) * n, node_bytes = sizeof(float4) * nodes.size();
+        const size_t node_off = (col_bytes + 15) & ~(size_t)15;
+        if (node_off + node_bytes > ctx->col_stage_bytes) {
+            CU(ctx, sync_all(ctx));
+            for (auto &h : ctx->h_col_stage) {
+                if (h) CU(ctx, cudaFreeHost(h));
+                h = nullptr;
+            }
+            ctx->col_stage_bytes = (node_off + node_bytes) * 2;
+            for (auto &h : ctx->h_col_stage) CU(ctx, cudaMallocHost((void **)&h, ctx->col_stage_bytes));
+        }
+        const uint32_t k = ctx->col_stage_next++ % 4u;
+        if (!ctx->col_stage_ev[k]) CU(ctx, cudaEventCreateWithFlags(&ctx->col_stage_ev[k], cudaEventDisableTiming));
+        else CU(ctx, cudaEventSynchronize(ctx->col_stage_ev[k])); // the copy that last used this slot
+        memcpy(ctx->h_col_stage[k], colliders, col_bytes);
+        memcpy(ctx->h_col_stage[k] + node_off, nodes.data(), node_bytes);
+        CU(ctx, cudaMemcpyAsync(ctx->d_colliders, ctx->h_col_stage[k], col_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->d_collider_bounds, ctx->h_col_stage[k] + node_off, node_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaEventRecord(ctx->col_stage_ev[k], ctx->stream));
     }
     return FW_OK;
 }

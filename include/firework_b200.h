@@ -258,7 +258,10 @@ int fw_spawner_reset(fw_context *ctx, uint32_t spawner_key,
 /* entity despawned */
 int fw_spawner_remove(fw_context *ctx, uint32_t spawner_key);
 
-/* replace the collider set of the spatial query (static scene; avian keeps its own) */
+/* replace the collider set of the spatial query that particle_collision casts rays against
+ * (SpatialQuery::cast_ray, src/core.rs:756-765): the world transforms of avian's colliders as of
+ * the last physics step. Re-sending a set of the same size (moving colliders) is asynchronous --
+ * an upload and a BVH rebuild ordered between the frames around it; another size reallocates. */
 int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n);
 
 /* one tick of (spawn_particles ; update_particles) over every spawner of the context.
