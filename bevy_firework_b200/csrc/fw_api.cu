@@ -136,9 +136,8 @@ struct fw_context {
     fw_emission_settings *d_emitters = nullptr;
     std::vector<fw_emission_settings> h_emitters; // host copy, indexed like d_emitters
     fw_collider *d_colliders = nullptr;
-    float4 *d_collider_bounds = nullptr;
+    uint8_t *d_broadphase = nullptr; // BroadPhaseHeader blob, broadphase_bytes(n_colliders)
     uint32_t n_colliders = 0;
-    uint32_t n_bvh_nodes = 0; // 2 float4 per node in d_collider_bounds
     // pinned staging of (colliders | BVH nodes) for asynchronous re-uploads, a small ring guarded by events
     uint8_t *h_col_stage[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t col_stage_bytes = 0;
@@ -799,7 +798,7 @@ int fw_destroy(fw_context *ctx) {
     cudaFree(ctx->d_settings);
     cudaFree(ctx->d_emitters);
     cudaFree(ctx->d_colliders);
-    cudaFree(ctx->d_collider_bounds);
+    cudaFree(ctx->d_broadphase);
     for (auto &h : ctx->h_col_stage)
         if (h) cudaFreeHost(h);
     for (auto &ev : ctx->col_stage_ev)
@@ -1029,6 +1028,152 @@ static void build_bvh(std::vector<float4> &nodes, std::vector<uint32_t> &order, 
     memcpy(&nodes[me + 1].w, &leaf, 4);
 }
 
+// The whole broad phase of a collider set as one blob (layout: BroadPhaseHeader, fw_internal.h).
+static void build_broadphase(const fw_collider *colliders, uint32_t n, std::vector<uint8_t> &blob) {
+    // world AABB of every collider, inflated well beyond fp32 rounding of the exact ray tests
+    std::vector<float> lo(3 * (size_t)n), hi(3 * (size_t)n);
+    std::vector<uint32_t> layers(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const fw_collider &c = colliders[i];
+        layers[i] = c.layers;
+        const double x = c.rotation[0], y = c.rotation[1], z = c.rotation[2], w = c.rotation[3];
+        const double R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)},
+                                {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
+                                {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
+        for (int a = 0; a < 3; a++) {
+            double ext = c.kind == FW_COLLIDER_SPHERE
+                             ? std::fabs((double)c.half_extents[0])
+                             : std::fabs(R[a][0] * c.half_extents[0]) + std::fabs(R[a][1] * c.half_extents[1]) + std::fabs(R[a][2] * c.half_extents[2]);
+            const double margin = 1e-3 + 1e-3 * (std::fabs((double)c.translation[a]) + ext);
+            // a non-finite bound (NaN transform) becomes the whole line: it never culls
+            lo[3 * i + a] = bvh_sane((float)(c.translation[a] - ext - margin), -FLT_MAX);
+            hi[3 * i + a] = bvh_sane((float)(c.translation[a] + ext + margin), FLT_MAX);
+        }
+    }
+    // BVH: median split of the centroids along the widest axis, one collider per leaf, depth-first
+    // order with skip links, so that the kernel walks it without a stack
+    std::vector<float4> nodes;
+    nodes.reserve(4 * (size_t)n);
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; i++) order[i] = i;
+    build_bvh(nodes, order, lo, hi, layers, 0, n);
+
+    // uniform grid over the colliders that are small against the scene; the others ("big": the
+    // ground slab, anything unbounded) are tested for every ray
+    float glo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, ghi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    std::vector<double> diag(n);
+    for (uint32_t i = 0; i < n; i++) {
+        double d2 = 0;
+        for (int a = 0; a < 3; a++) d2 += ((double)hi[3 * i + a] - lo[3 * i + a]) * ((double)hi[3 * i + a] - lo[3 * i + a]);
+        diag[i] = std::sqrt(d2);
+    }
+    std::vector<double> sorted_diag(diag);
+    std::sort(sorted_diag.begin(), sorted_diag.end());
+    const double median_diag = sorted_diag[n / 2];
+    std::vector<uint32_t> big, small;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!(diag[i] <= 8.0 * median_diag) || !std::isfinite(diag[i])) big.push_back(i);
+        else small.push_back(i);
+    }
+    for (uint32_t i : small)
+        for (int a = 0; a < 3; a++) {
+            glo[a] = std::min(glo[a], lo[3 * i + a]);
+            ghi[a] = std::max(ghi[a], hi[3 * i + a]);
+        }
+    BroadPhaseHeader h{};
+    std::vector<uint32_t> cell_start, items;
+    bool use_grid = small.size() >= 8 && big.size() <= 16;
+    float inv_cell[3] = {0, 0, 0};
+    if (use_grid) {
+        // cells about as large as a typical collider box, at most cells_cap of them
+        double edge = std::max(median_diag / std::sqrt(3.0), 1e-6);
+        const size_t cells_cap = broadphase_cells_cap(n), items_cap = broadphase_items_cap(n);
+        for (int attempt = 0; attempt < 24; attempt++, edge *= 1.3) {
+            size_t cells = 1;
+            for (int a = 0; a < 3; a++) {
+                const double ext = std::max((double)ghi[a] - glo[a], 1e-6);
+                h.dim[a] = (uint32_t)std::min<double>(kGridMaxDim, std::max(1.0, std::ceil(ext / edge)));
+                inv_cell[a] = (float)(h.dim[a] / ext);
+                cells *= h.dim[a];
+            }
+            if (cells > cells_cap) continue;
+            // count, then fill (CSR). Cell coordinates in fp32 with the kernel's own expression.
+            auto cell_of = [&](float v, int a) {
+                const float f = std::floor((v - glo[a]) * inv_cell[a]);
+                return (int)std::min<float>(std::max<float>(f, 0.0f), (float)(h.dim[a] - 1));
+            };
+            cell_start.assign(cells + 1, 0);
+            size_t total = 0;
+            for (int pass = 0; pass < 2 && total <= items_cap; pass++) {
+                if (pass == 1) {
+                    uint32_t run = 0;
+                    for (size_t c = 0; c < cells; c++) {
+                        const uint32_t cnt = cell_start[c];
+                        cell_start[c] = run;
+                        run += cnt;
+                    }
+                    cell_start[cells] = run;
+                    items.assign(run, 0);
+                }
+                std::vector<uint32_t> fill(pass == 1 ? cells : 0, 0);
+                for (uint32_t i : small) {
+                    int c0[3], c1[3];
+                    for (int a = 0; a < 3; a++) {
+                        c0[a] = cell_of(lo[3 * i + a], a);
+                        c1[a] = cell_of(hi[3 * i + a], a);
+                    }
+                    for (int z = c0[2]; z <= c1[2]; z++)
+                        for (int y = c0[1]; y <= c1[1]; y++)
+                            for (int x = c0[0]; x <= c1[0]; x++) {
+                                const size_t c = ((size_t)z * h.dim[1] + y) * h.dim[0] + x;
+                                if (pass == 0) {
+                                    cell_start[c]++;
+                                    total++;
+                                } else {
+                                    items[cell_start[c] + fill[c]++] = i;
+                                }
+                            }
+                }
+            }
+            if (total <= items_cap) break;
+            cell_start.clear();
+        }
+        use_grid = !cell_start.empty();
+    }
+    if (!use_grid) {
+        cell_start.assign(2, 0);
+        items.clear();
+        big.clear();
+        h.dim[0] = h.dim[1] = h.dim[2] = 1;
+    }
+    auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    h.n_nodes = (uint32_t)(nodes.size() / 2);
+    h.leaf_off = (uint32_t)sizeof(BroadPhaseHeader);
+    h.nodes_off = (uint32_t)(h.leaf_off + 32 * (size_t)n);
+    h.big_off = (uint32_t)(h.nodes_off + 16 * nodes.size());
+    h.n_big = (uint32_t)big.size();
+    h.cell_off = (uint32_t)align16(h.big_off + 4 * big.size());
+    h.items_off = (uint32_t)align16(h.cell_off + 4 * cell_start.size());
+    h.use_grid = use_grid ? 1u : 0u;
+    for (int a = 0; a < 3; a++) {
+        h.lo[a] = use_grid ? glo[a] : 0.f;
+        h.inv_cell[a] = inv_cell[a];
+    }
+    blob.assign(align16(h.items_off + 4 * items.size()), 0);
+    memcpy(blob.data(), &h, sizeof(h));
+    float4 *leaf = (float4 *)(blob.data() + h.leaf_off);
+    for (uint32_t i = 0; i < n; i++) {
+        float lb;
+        memcpy(&lb, &layers[i], 4);
+        leaf[2 * i] = make_float4(lo[3 * i], lo[3 * i + 1], lo[3 * i + 2], lb);
+        leaf[2 * i + 1] = make_float4(hi[3 * i], hi[3 * i + 1], hi[3 * i + 2], 0.f);
+    }
+    memcpy(blob.data() + h.nodes_off, nodes.data(), 16 * nodes.size());
+    if (!big.empty()) memcpy(blob.data() + h.big_off, big.data(), 4 * big.size());
+    memcpy(blob.data() + h.cell_off, cell_start.data(), 4 * cell_start.size());
+    if (!items.empty()) memcpy(blob.data() + h.items_off, items.data(), 4 * items.size());
+}
+
 int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) {
     ENTER(ctx);
     if (n && !colliders) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_set_colliders: null");
@@ -1038,69 +1183,43 @@ int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) 
     // same kernel arguments, the copies below are ordered on the context's stream between the
     // frames around them -- no synchronisation, captured frame graphs stay valid. A different
     // count reallocates.
-    const bool same_shape = n == ctx->n_colliders && (n == 0 || (ctx->d_colliders && ctx->d_collider_bounds));
+    const bool same_shape = n == ctx->n_colliders && (n == 0 || (ctx->d_colliders && ctx->d_broadphase));
     if (!same_shape) {
         CU(ctx, sync_all(ctx));
         if (ctx->d_colliders) CU(ctx, cudaFree(ctx->d_colliders));
         ctx->d_colliders = nullptr;
-        if (ctx->d_collider_bounds) CU(ctx, cudaFree(ctx->d_collider_bounds));
-        ctx->d_collider_bounds = nullptr;
+        if (ctx->d_broadphase) CU(ctx, cudaFree(ctx->d_broadphase));
+        ctx->d_broadphase = nullptr;
         ctx->n_colliders = n;
-        ctx->n_bvh_nodes = 0;
         topo_changed(ctx);
         if (n) {
             CU(ctx, cudaMalloc((void **)&ctx->d_colliders, sizeof(fw_collider) * n));
-            CU(ctx, cudaMalloc((void **)&ctx->d_collider_bounds, sizeof(float4) * 2 * (2 * (size_t)n - 1)));
+            CU(ctx, cudaMalloc((void **)&ctx->d_broadphase, broadphase_bytes(n)));
         }
     }
     if (n) {
-        // broad phase: world AABB of every collider, inflated well beyond fp32 rounding, under a
-        // binary BVH (median split of the centroids along the widest axis, one collider per leaf)
-        // stored in depth-first order with skip links, so the kernel walks it without a stack
-        std::vector<float> lo(3 * (size_t)n), hi(3 * (size_t)n);
-        for (uint32_t i = 0; i < n; i++) {
-            const fw_collider &c = colliders[i];
-            const double x = c.rotation[0], y = c.rotation[1], z = c.rotation[2], w = c.rotation[3];
-            const double R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)},
-                                    {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
-                                    {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
-            for (int a = 0; a < 3; a++) {
-                double ext = c.kind == FW_COLLIDER_SPHERE
-                                 ? std::fabs((double)c.half_extents[0])
-                                 : std::fabs(R[a][0] * c.half_extents[0]) + std::fabs(R[a][1] * c.half_extents[1]) + std::fabs(R[a][2] * c.half_extents[2]);
-                const double margin = 1e-3 + 1e-3 * (std::fabs((double)c.translation[a]) + ext);
-                lo[3 * i + a] = (float)(c.translation[a] - ext - margin);
-                hi[3 * i + a] = (float)(c.translation[a] + ext + margin);
-            }
-        }
-        std::vector<float4> nodes;
-        nodes.reserve(4 * (size_t)n);
-        std::vector<uint32_t> order(n);
-        for (uint32_t i = 0; i < n; i++) order[i] = i;
-        std::vector<uint32_t> layers(n);
-        for (uint32_t i = 0; i < n; i++) layers[i] = colliders[i].layers;
-        build_bvh(nodes, order, lo, hi, layers, 0, n);
-        ctx->n_bvh_nodes = (uint32_t)(nodes.size() / 2); // always 2n - 1: one collider per leaf
+        std::vector<uint8_t> blob;
+        build_broadphase(colliders, n, blob);
         // both arrays through a pinned staging slot: the caller's array is free on return and the
         // host never waits for the stream (a pageable source would)
-        const size_t col_bytes = sizeof(fw_collider) * n, node_bytes = sizeof(float4) * nodes.size();
-        const size_t node_off = (col_bytes + 15) & ~(size_t)15;
-        if (node_off + node_bytes > ctx->col_stage_bytes) {
+        const size_t col_bytes = sizeof(fw_collider) * n;
+        const size_t blob_off = (col_bytes + 15) & ~(size_t)15;
+        if (blob_off + blob.size() > ctx->col_stage_bytes) {
             CU(ctx, sync_all(ctx));
-            for (auto &h : ctx->h_col_stage) {
-                if (h) CU(ctx, cudaFreeHost(h));
-                h = nullptr;
+            for (auto &hp : ctx->h_col_stage) {
+                if (hp) CU(ctx, cudaFreeHost(hp));
+                hp = nullptr;
             }
-            ctx->col_stage_bytes = (node_off + node_bytes) * 2;
-            for (auto &h : ctx->h_col_stage) CU(ctx, cudaMallocHost((void **)&h, ctx->col_stage_bytes));
+            ctx->col_stage_bytes = blob_off + broadphase_bytes(n);
+            for (auto &hp : ctx->h_col_stage) CU(ctx, cudaMallocHost((void **)&hp, ctx->col_stage_bytes));
         }
         const uint32_t k = ctx->col_stage_next++ % 4u;
         if (!ctx->col_stage_ev[k]) CU(ctx, cudaEventCreateWithFlags(&ctx->col_stage_ev[k], cudaEventDisableTiming));
         else CU(ctx, cudaEventSynchronize(ctx->col_stage_ev[k])); // the copy that last used this slot
         memcpy(ctx->h_col_stage[k], colliders, col_bytes);
-        memcpy(ctx->h_col_stage[k] + node_off, nodes.data(), node_bytes);
+        memcpy(ctx->h_col_stage[k] + blob_off, blob.data(), blob.size());
         CU(ctx, cudaMemcpyAsync(ctx->d_colliders, ctx->h_col_stage[k], col_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(ctx->d_collider_bounds, ctx->h_col_stage[k] + node_off, node_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->d_broadphase, ctx->h_col_stage[k] + blob_off, blob.size(), cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaEventRecord(ctx->col_stage_ev[k], ctx->stream));
     }
     return FW_OK;
@@ -1374,9 +1493,8 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     t.settings = ctx->d_settings;
     t.emitters = ctx->d_emitters;
     t.colliders = ctx->d_colliders;
-    t.collider_bounds = ctx->d_collider_bounds;
+    t.broadphase = ctx->d_broadphase;
     t.n_colliders = ctx->n_colliders;
-    t.n_bvh_nodes = ctx->n_bvh_nodes;
     t.tile_prefix = ctx->d_tile_prefix;
     t.slots_cap = ctx->slots_cap;
     t.lookback_capacity = ctx->tiles_cap;

@@ -120,6 +120,31 @@ __host__ __device__ inline StreamArrays stream_arrays(uint8_t *base, uint32_t ca
     return a;
 }
 
+// Broad phase of the collision sweep, one device blob rebuilt by fw_set_colliders:
+//   leaf[2i], leaf[2i+1]  inflated world AABB of collider i: (min.xyz | layers bits), (max.xyz | -)
+//   nodes                 BVH over those boxes in depth-first order, 2 float4 per node:
+//                         (min.xyz | skip link, leaf: layers bits), (max.xyz | collider index or ~0)
+//   big                   colliders too large for the grid: tested for every ray
+//   cell_start, items     uniform grid over the other colliders (CSR): a ray segment no longer than a
+//                         cell per axis looks at <= 8 cells instead of walking the BVH
+struct BroadPhaseHeader {
+    uint32_t n_nodes, nodes_off, leaf_off; // offsets in bytes from the blob's start
+    uint32_t n_big, big_off;
+    uint32_t use_grid, cell_off, items_off;
+    uint32_t dim[3];
+    float lo[3], inv_cell[3];
+    uint32_t pad[3];
+};
+static_assert(sizeof(BroadPhaseHeader) == 80, "16-byte multiple: the arrays behind it hold float4");
+constexpr uint32_t kGridMaxDim = 64;
+// deterministic capacity of the blob for n colliders (same n => same buffer => same kernel arguments)
+inline size_t broadphase_cells_cap(uint32_t n) { return (size_t)(8u * n < 64u ? 64u : (8u * n > kGridMaxDim * kGridMaxDim * kGridMaxDim ? kGridMaxDim * kGridMaxDim * kGridMaxDim : 8u * n)); }
+inline size_t broadphase_items_cap(uint32_t n) { return 32u * (size_t)n; }
+inline size_t broadphase_bytes(uint32_t n) {
+    return sizeof(BroadPhaseHeader) + 32u * (size_t)n /*leaf*/ + 32u * (2u * (size_t)n) /*nodes*/ + 4u * (size_t)n /*big*/ +
+           4u * (broadphase_cells_cap(n) + 1u) + 4u * broadphase_items_cap(n) + 64u;
+}
+
 // Stream states are double-buffered: frame f reads the buffer frame f-1 wrote and writes the
 // other one (zeroed by a memset node first), so every kernel can DERIVE the state it needs --
 // head after last frame's deaths, count after this frame's spawns -- functionally from the old
@@ -219,9 +244,8 @@ struct DeviceTables {
     const DevParticleSettings *settings; // indexed by stream slot
     const fw_emission_settings *emitters;
     const fw_collider *colliders;
-    const float4 *collider_bounds; // collider BVH, 2 float4 per node (see cast_ray in fw_math.cuh)
+    const uint8_t *broadphase; // BroadPhaseHeader + its arrays (see cast_ray in fw_math.cuh)
     uint32_t n_colliders;
-    uint32_t n_bvh_nodes;
     // tile_prefix[v * slots_cap + s] = number of update tiles of variant v in slots < s
     uint32_t *tile_prefix;
     uint32_t slots_cap;

@@ -301,7 +301,7 @@ __device__ __forceinline__ bool step_particle(const DeviceTables &t, const DevPa
     V3 pos = v3(M0.x, M0.y, M0.z), vel = v3(M2.x, M2.y, M2.z);
     bool should_destroy = false;
     if (COLLIDE) // :608-617, hoisted out of the branch so that the warp stays converged inside
-        particle_collision(t.colliders, t.collider_bounds, t.n_bvh_nodes, ps.collision, alive, pos, vel, dt, cand_queue, should_destroy);
+        particle_collision(t.colliders, t.broadphase, ps.collision, alive, pos, vel, dt, cand_queue, should_destroy);
     if (alive) {
         const float age_percent = age / lifetime;                   // :601
         scale = iscale * sample_curve(ps.scale_curve, age_percent); // :602-605

@@ -281,25 +281,39 @@ __device__ __forceinline__ bool ray_ball_local(float radius, V3 o, V3 d, float m
     normal = n;
     return true;
 }
-// Broad phase: a BVH over the colliders' world AABBs (built by fw_set_colliders; node k =
-// bvh[2k] = min.xyz | skip link (leaf: layers bits), bvh[2k+1] = max.xyz | collider index or
-// 0xFFFFFFFF for an inner node), walked in depth-first order without a stack: a node whose box
-// misses the ray segment's box jumps to its skip link (a leaf's is k + 1). The boxes are inflated
-// on the host by far more than any fp32 rounding of the exact test, so a collider is skipped only
+// Broad phase (blob layout: BroadPhaseHeader in fw_internal.h). Every candidate passes a box test
+// of the ray segment's AABB against the collider's inflated world AABB; the boxes are inflated on
+// the host by far more than any fp32 rounding of the exact test, so a collider is skipped only
 // when the exact test below could not report a hit within max_distance: the result is identical
 // to testing every collider in index order (the CPU oracle does exactly that; equal distances
-// resolve to the lowest collider index). NaN never culls.
+// resolve to the lowest collider index). NaN never culls. Two ways to enumerate candidates:
+//   * grid: a segment that spans at most 2 cells per axis (the usual case: |v| dt is a fraction of
+//     a collider) reads the CSR lists of its <= 8 cells plus the short list of "big" colliders;
+//     a collider listed in several of those cells is taken in the first one its box overlaps;
+//   * BVH: anything else (long segments, non-finite input, grid disabled) walks the BVH in
+//     depth-first order without a stack: a node whose box misses the segment's box jumps to its
+//     skip link (a leaf's is k + 1).
 //
 // Warp-synchronous: ALL 32 lanes of the warp must call (lanes without a ray pass act = false).
-// The lanes of a warp walk different paths, so the walk only collects candidate leaves into a
-// small per-lane queue in shared memory (queue[j * kUpdateThreads], j < kCandQueue); the long
-// exact test then runs over the queues with the warp converged: a warp pays
-// max-over-lanes(candidates) exact tests instead of one per divergent loop trip (ncu on C5 before
-// the split: 2.7 active lanes per instruction in the exact test, profiles/r1_tuning.md).
+// The lanes of a warp see different candidates, so enumeration only collects them into a small
+// per-lane queue in shared memory (queue[j * kUpdateThreads], j < kCandQueue); the long exact
+// test then runs over the queues with the warp converged: a warp pays max-over-lanes(candidates)
+// exact tests instead of one per divergent loop trip (ncu on C5 before the split: 2.7 active
+// lanes per instruction in the exact test, profiles/r1_tuning.md).
 constexpr uint32_t kCandQueue = 4;
-__device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ colliders, const float4 *__restrict__ bvh,
-                                         uint32_t n_nodes, uint32_t filter_mask, bool act, V3 o, V3 d, float max_distance,
-                                         uint32_t *queue, float &distance, V3 &normal) {
+__device__ __forceinline__ float grid_coord(float x, float lo, float inv_cell) { return floorf((x - lo) * inv_cell); }
+__device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ colliders, const uint8_t *__restrict__ bp,
+                                         uint32_t filter_mask, bool act, V3 o, V3 d, float max_distance, uint32_t *queue,
+                                         float &distance, V3 &normal) {
+    if (bp == nullptr) { // no collider set was ever uploaded
+        distance = 0.0f;
+        normal = v3(0.0f, 0.0f, 0.0f);
+        return false;
+    }
+    const BroadPhaseHeader &h = *reinterpret_cast<const BroadPhaseHeader *>(bp);
+    const float4 *__restrict__ bvh = reinterpret_cast<const float4 *>(bp + h.nodes_off);
+    const float4 *__restrict__ leaf = reinterpret_cast<const float4 *>(bp + h.leaf_off);
+    const uint32_t n_nodes = h.n_nodes;
     bool found = false;
     float best = 0.0f;
     uint32_t best_i = 0xFFFFFFFFu;
@@ -308,17 +322,82 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
     const V3 slo = v3(fminf(o.x, e.x), fminf(o.y, e.y), fminf(o.z, e.z));
     const V3 shi = v3(fmaxf(o.x, e.x), fmaxf(o.y, e.y), fmaxf(o.z, e.z));
     const bool cull_ok = isfinite(e.x) && isfinite(e.y) && isfinite(e.z) && isfinite(o.x) && isfinite(o.y) && isfinite(o.z);
-    uint32_t k = act ? 0u : n_nodes;
+
+    // ---- which enumeration; grid state: base cell (8 bits per axis) | span bits << 24
+    bool use_grid = false;
+    uint32_t base = 0, sub = 8u /* next cell sub-index, 8 = no more cells */, cur_sub = 0, big_i = 0, p = 0, p_end = 0;
+    if (act && cull_ok && h.use_grid != 0u) {
+        const float dx = (float)h.dim[0], dy = (float)h.dim[1], dz = (float)h.dim[2];
+        // cell coordinates as floats, clamped to [-1, dim] so that the int conversion is safe
+        const float ax = fminf(fmaxf(grid_coord(slo.x, h.lo[0], h.inv_cell[0]), -1.0f), dx), bx = fminf(fmaxf(grid_coord(shi.x, h.lo[0], h.inv_cell[0]), -1.0f), dx);
+        const float ay = fminf(fmaxf(grid_coord(slo.y, h.lo[1], h.inv_cell[1]), -1.0f), dy), by = fminf(fmaxf(grid_coord(shi.y, h.lo[1], h.inv_cell[1]), -1.0f), dy);
+        const float az = fminf(fmaxf(grid_coord(slo.z, h.lo[2], h.inv_cell[2]), -1.0f), dz), bz = fminf(fmaxf(grid_coord(shi.z, h.lo[2], h.inv_cell[2]), -1.0f), dz);
+        const int x0 = max((int)ax, 0), x1 = min((int)bx, (int)h.dim[0] - 1);
+        const int y0 = max((int)ay, 0), y1 = min((int)by, (int)h.dim[1] - 1);
+        const int z0 = max((int)az, 0), z1 = min((int)bz, (int)h.dim[2] - 1);
+        if (x1 - x0 <= 1 && y1 - y0 <= 1 && z1 - z0 <= 1) {
+            use_grid = true;
+            if (x1 >= x0 && y1 >= y0 && z1 >= z0) { // else: the segment misses the grid, only the big list
+                base = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)z0 << 16) |
+                       ((uint32_t)(x1 - x0) << 24) | ((uint32_t)(y1 - y0) << 25) | ((uint32_t)(z1 - z0) << 26);
+                sub = 0u;
+            }
+        }
+    }
+    const uint32_t *__restrict__ big = reinterpret_cast<const uint32_t *>(bp + h.big_off);
+    const uint32_t *__restrict__ cell_start = reinterpret_cast<const uint32_t *>(bp + h.cell_off);
+    const uint32_t *__restrict__ items = reinterpret_cast<const uint32_t *>(bp + h.items_off);
+    const uint32_t n_big = h.n_big, span = base >> 24;
+    uint32_t k = (act && !use_grid) ? 0u : n_nodes;
+    bool more;
     do {
         uint32_t cnt = 0;
-        while (k < n_nodes && cnt < kCandQueue) {
-            const float4 blo = __ldg(bvh + 2u * k), bhi = __ldg(bvh + 2u * k + 1u);
-            const uint32_t leaf = __float_as_uint(bhi.w), link = __float_as_uint(blo.w);
-            // (bitwise, not short-circuit: one predicate chain instead of six branches)
-            const bool disjoint = cull_ok & ((shi.x < blo.x) | (slo.x > bhi.x) | (shi.y < blo.y) | (slo.y > bhi.y) | (shi.z < blo.z) | (slo.z > bhi.z));
-            const bool inner = leaf == 0xFFFFFFFFu;
-            k = (inner & disjoint) ? link : k + 1u;
-            if (!inner & !disjoint & ((link & filter_mask) != 0u)) queue[(cnt++) * kUpdateThreads] = leaf;
+        if (use_grid) {
+            while (cnt < kCandQueue) {
+                uint32_t cand;
+                bool from_cell = false;
+                if (big_i < n_big) {
+                    cand = __ldg(big + big_i++);
+                } else if (p < p_end) {
+                    cand = __ldg(items + p++);
+                    from_cell = true;
+                } else if (sub < 8u) {
+                    const uint32_t cx = (base & 255u) + (sub & 1u), cy = ((base >> 8) & 255u) + ((sub >> 1) & 1u),
+                                   cz = ((base >> 16) & 255u) + (sub >> 2);
+                    const uint32_t cell = (cz * h.dim[1] + cy) * h.dim[0] + cx;
+                    p = __ldg(cell_start + cell);
+                    p_end = __ldg(cell_start + cell + 1u);
+                    cur_sub = sub;
+                    sub = (sub - span) & span; // next subset of the span bits; back at 0 = all cells seen
+                    if (sub == 0u) sub = 8u;
+                    continue;
+                } else {
+                    break;
+                }
+                const float4 blo = __ldg(leaf + 2u * cand), bhi = __ldg(leaf + 2u * cand + 1u);
+                const bool disjoint = (shi.x < blo.x) | (slo.x > bhi.x) | (shi.y < blo.y) | (slo.y > bhi.y) | (shi.z < blo.z) | (slo.z > bhi.z);
+                if (disjoint | ((__float_as_uint(blo.w) & filter_mask) == 0u)) continue;
+                if (from_cell && span != 0u) {
+                    // listed in several of our cells: take it in the first one its box overlaps
+                    const uint32_t fx = grid_coord(blo.x, h.lo[0], h.inv_cell[0]) > (float)(base & 255u) ? 1u : 0u;
+                    const uint32_t fy = grid_coord(blo.y, h.lo[1], h.inv_cell[1]) > (float)((base >> 8) & 255u) ? 1u : 0u;
+                    const uint32_t fz = grid_coord(blo.z, h.lo[2], h.inv_cell[2]) > (float)((base >> 16) & 255u) ? 1u : 0u;
+                    if (((fx | (fy << 1) | (fz << 2)) & span) != cur_sub) continue;
+                }
+                queue[(cnt++) * kUpdateThreads] = cand;
+            }
+            more = (big_i < n_big) | (p < p_end) | (sub < 8u);
+        } else {
+            while (k < n_nodes && cnt < kCandQueue) {
+                const float4 blo = __ldg(bvh + 2u * k), bhi = __ldg(bvh + 2u * k + 1u);
+                const uint32_t leaf_i = __float_as_uint(bhi.w), link = __float_as_uint(blo.w);
+                // (bitwise, not short-circuit: one predicate chain instead of six branches)
+                const bool disjoint = cull_ok & ((shi.x < blo.x) | (slo.x > bhi.x) | (shi.y < blo.y) | (slo.y > bhi.y) | (shi.z < blo.z) | (slo.z > bhi.z));
+                const bool inner = leaf_i == 0xFFFFFFFFu;
+                k = (inner & disjoint) ? link : k + 1u;
+                if (!inner & !disjoint & ((link & filter_mask) != 0u)) queue[(cnt++) * kUpdateThreads] = leaf_i;
+            }
+            more = k < n_nodes;
         }
         const uint32_t rounds = __reduce_max_sync(0xffffffffu, cnt);
         for (uint32_t j = 0; j < rounds; j++) {
@@ -344,7 +423,7 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
             }
             __syncwarp();
         }
-    } while (__any_sync(0xffffffffu, k < n_nodes));
+    } while (__any_sync(0xffffffffu, more));
     distance = best;
     normal = best_n;
     return found;
@@ -352,8 +431,8 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
 
 // reference src/core.rs:744-800 particle_collision. Warp-synchronous like cast_ray: every lane of
 // the warp calls, lanes without a live particle pass active = false (their pos / vel stay untouched).
-__device__ __forceinline__ void particle_collision(const fw_collider *__restrict__ colliders, const float4 *__restrict__ bvh,
-                                                   uint32_t n_bvh_nodes, const fw_collision_settings &cs, bool active, V3 &pos,
+__device__ __forceinline__ void particle_collision(const fw_collider *__restrict__ colliders, const uint8_t *__restrict__ broadphase,
+                                                   const fw_collision_settings &cs, bool active, V3 &pos,
                                                    V3 &vel, float delta, uint32_t *queue, bool &should_destroy) {
     const float orig_delta = delta;
     int n_steps = 0;
@@ -364,7 +443,7 @@ __device__ __forceinline__ void particle_collision(const fw_collider *__restrict
         V3 dir = (isfinite(len) && len > 0.0f) ? vel / len : v3(0.0f, 1.0f, 0.0f);
         float distance;
         V3 hit_normal;
-        const bool hit = cast_ray(colliders, bvh, n_bvh_nodes, cs.filter_mask, go, pos, dir, length(vel) * delta, queue, distance, hit_normal);
+        const bool hit = cast_ray(colliders, broadphase, cs.filter_mask, go, pos, dir, length(vel) * delta, queue, distance, hit_normal);
         if (go) {
             if (hit) {
                 if (distance == 0.0f) {
