@@ -10,6 +10,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 60 --csv --lo
 ncu --set full --clock-control none --import-source on -k regex:update_kernel -s 110 -c 1 -o $O/c3r python bench.py --workload c3r --steps 5 --warmup 3 --no-cpu-baseline --no-graphs > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:update_kernel -s 80 -c 1 -o $O/c3 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu-baseline --no-graphs > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:update_kernel -s 140 -c 1 -o $O/c5 python bench.py --workload c5 --steps 5 --warmup 3 --no-cpu-baseline --no-graphs > /dev/null 2>&1
-(timeout 600 compute-sanitizer --tool racecheck python -m pytest tests -m gpu -x -q -k "compact or nested or destroy or random or collision" 2>&1 | tail -6) > $O/racecheck.log
-(timeout 600 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -x -q -k "compact or nested or destroy or random or collision or edge" 2>&1 | tail -6) > $O/memcheck.log
+(timeout 900 compute-sanitizer --tool racecheck python -m pytest tests -m gpu -x -q -k "compaction or nested or destroyed or collision_destroy or collision_single or (randomized_mixed_scene and 1)" 2>&1 | tail -6) > $O/racecheck.log
+(timeout 600 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -x -q -k "compaction or nested or destroyed or random or collision or edge" 2>&1 | tail -6) > $O/memcheck.log
 cat $O/pytest_gpu.log; tail -2 $O/racecheck.log; tail -2 $O/memcheck.log
