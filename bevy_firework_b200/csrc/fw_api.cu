@@ -282,6 +282,20 @@ inline void compute_emission_count(float time_passed_in_cycle, float last_emissi
 }
 
 inline bool is_fifo(uint32_t v) { return v == kFifo || v == kFifoCollide; }
+// A compacting ring compacts out of place inside its own ring (fw_kernels.cu: usable_capacity,
+// live_first): it may only be half full, and after a frame its live particles start at
+// head + count (a FIFO ring's: at head + dead).
+inline uint64_t usable_capacity(uint32_t variant, uint64_t capacity) { return is_fifo(variant) ? capacity : capacity / 2; }
+inline uint32_t live_first(uint32_t variant, const StreamState &s, uint32_t capacity) {
+    return (uint32_t)(((uint64_t)s.head + (is_fifo(variant) ? s.dead : s.count)) % std::max(1u, capacity));
+}
+// the state to inject for `live` particles that sit at the start of the block
+inline StreamState injected_state(uint32_t variant, uint32_t live, uint32_t capacity) {
+    StreamState ns{};
+    ns.count = live;
+    ns.head = is_fifo(variant) || live == 0 ? 0u : (capacity - live % capacity) % capacity; // head + count == 0 (mod capacity)
+    return ns;
+}
 
 inline uint32_t round_capacity(uint64_t want) {
     // round up so that freed blocks are reusable: multiples of 1024 up to 64 Ki, then 1/8-octave
@@ -555,9 +569,10 @@ int grow_stream(fw_context *ctx, Stream &st, uint64_t need) {
     // exact state is in ctx->snapshot (refresh_exact was just called)
     const StreamState s = ctx->snapshot[st.slot];
     const uint32_t live = s.count - s.dead;
-    const uint32_t first = (s.head + (is_fifo(st.variant) ? s.dead : 0u)) % std::max(1u, st.block.capacity);
-    const uint32_t ncap = round_capacity(std::max<uint64_t>(need + need / 4, (uint64_t)st.block.capacity * 2));
-    if ((uint64_t)ncap < need) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "stream would exceed 2^32 particles");
+    const uint32_t first = live_first(st.variant, s, st.block.capacity);
+    const uint64_t slots = is_fifo(st.variant) ? need : 2 * need;
+    const uint32_t ncap = round_capacity(std::max<uint64_t>(slots + slots / 4, (uint64_t)st.block.capacity * 2));
+    if ((uint64_t)ncap < slots) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "stream would exceed 2^32 particles");
     Block nb;
     int rc = alloc_block(ctx, ncap, st.n_lea, nb);
     if (rc) return rc;
@@ -569,7 +584,8 @@ int grow_stream(fw_context *ctx, Stream &st, uint64_t need) {
     ctx->readback_is_current = false;
     CU(ctx, launch_ring_copy(block_desc(st.block, st.variant), first, live, block_desc(nb, st.variant), ctx->stream));
     StreamState ns = s;
-    ns.head = 0;
+    const StreamState inj = injected_state(st.variant, live, ncap);
+    ns.head = inj.head;
     ns.count = live;
     ns.dead = 0;
     CU(ctx, cudaMemcpyAsync(cur_states(ctx) + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, ctx->stream));
@@ -684,7 +700,7 @@ int ensure_stage(fw_context *ctx, size_t bytes) {
 inline void live_range(const fw_context *ctx, const Stream &st, uint32_t &first, uint32_t &live) {
     const StreamState s = ctx->snapshot[st.slot];
     live = s.count - s.dead;
-    first = (s.head + (is_fifo(st.variant) ? s.dead : 0u)) % std::max(1u, st.block.capacity);
+    first = live_first(st.variant, s, st.block.capacity);
 }
 
 inline float dec_f32(uint32_t u) {
@@ -931,7 +947,7 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
                 if (rc) return rc;
                 st.slot = ctx->n_slots++;
             }
-            int rc = alloc_block(ctx, round_capacity(estimate_capacity(*sp, t)), st.n_lea, st.block);
+            int rc = alloc_block(ctx, round_capacity(estimate_capacity(*sp, t) * (is_fifo(st.variant) ? 1 : 2)), st.n_lea, st.block);
             if (rc) {
                 ctx->free_slots.push_back(st.slot);
                 return rc;
@@ -1358,7 +1374,9 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     uint64_t scratch_need = plan_bounds();
     auto any_overflow = [&]() {
         for (uint32_t s = 0; s < n_slots; s++)
-            if (add[s] && ctx->slot_owner[s] && ctx->slot_owner[s]->n_hi + add[s] > ctx->slot_owner[s]->block.capacity) return true;
+            if (add[s] && ctx->slot_owner[s] &&
+                ctx->slot_owner[s]->n_hi + add[s] > usable_capacity(ctx->slot_owner[s]->variant, ctx->slot_owner[s]->block.capacity))
+                return true;
         return false;
     };
     if (any_overflow()) {
@@ -1370,7 +1388,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
             if (!st || !add[s]) continue;
             const uint64_t need = st->n_hi + add[s];
             if (need > 0xFFFFFF00ull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "a stream would exceed 2^32 particles");
-            if (need > st->block.capacity && (rc = grow_stream(ctx, *st, need))) return rc;
+            if (need > usable_capacity(st->variant, st->block.capacity) && (rc = grow_stream(ctx, *st, need))) return rc;
         }
     }
     if (scratch_need > 0xFFFFFF00ull) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "nested emission scratch too large");
@@ -1452,7 +1470,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
                         // upper bound of the particles the update kernel covers in this stream
                         const uint64_t covered = step_in_spawn ? st->n_hi - std::min<uint64_t>(st->n_hi, add[s]) : st->n_hi;
                         // (FIFO tiles are aligned to physical slots: up to 31 idle lanes in front, see update_kernel)
-                        const uint64_t lead = (v == kFifo || v == kFifoCollide) ? 31 : 0;
+                        const uint64_t lead = 31;
                         if (covered) run += (uint32_t)((std::min<uint64_t>(covered, st->block.capacity) + lead + kTile - 1) / kTile);
                     }
                 }
@@ -1567,6 +1585,10 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
             launches++;
         }
         if (prof) CU(ctx, cudaEventRecord(fs.ev[2], ctx->stream));
+        if (ctx->variant_streams[kCompact]) { // death counts + per-stream prefixes for the compacting update (timed with it)
+            CU(ctx, launch_count_scan(t, f, kCompact, n_slots, ctx->stream));
+            launches += 2;
+        }
         for (uint32_t v = 0; v < kNumVariants; v++) {
             if (!ctx->variant_streams[v]) continue;
             CU(ctx, launch_update(t, f, v, ctx->grids[v], ctx->team_size, ctx->stream));
@@ -1758,12 +1780,6 @@ int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_pa
     Stream &st = sp->streams[type];
     int rc = refresh_exact(ctx);
     if (rc) return rc;
-    if (n > st.block.capacity) {
-        ctx->snapshot[st.slot].count = 0;
-        ctx->snapshot[st.slot].dead = 0;
-        if ((rc = grow_stream(ctx, st, n))) return rc;
-        if ((rc = ensure_tiles(ctx))) return rc;
-    }
     // The FIFO variant relies on "deaths are a prefix of the Vec": every lifetime equals the
     // type's constant lifetime and ages do not increase along the Vec. Host-written state that
     // breaks this moves the stream to the compacting variant for good.
@@ -1779,13 +1795,18 @@ int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_pa
             if ((rc = upload_desc(ctx, st))) return rc;
         }
     }
+    if (n > usable_capacity(st.variant, st.block.capacity)) {
+        ctx->snapshot[st.slot].count = 0;
+        ctx->snapshot[st.slot].dead = 0;
+        if ((rc = grow_stream(ctx, st, n))) return rc;
+        if ((rc = ensure_tiles(ctx))) return rc;
+    }
     if (n) {
         if ((rc = ensure_stage(ctx, (size_t)n * sizeof(fw_particle_data)))) return rc;
         CU(ctx, cudaMemcpyAsync(ctx->d_stage, in, (size_t)n * sizeof(fw_particle_data), cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, launch_scatter_particles(block_desc(st.block, st.variant), (uint32_t)n, (const fw_particle_data *)ctx->d_stage, ctx->stream));
     }
-    StreamState ns{};
-    ns.count = (uint32_t)n;
+    const StreamState ns = injected_state(st.variant, (uint32_t)n, st.block.capacity);
     CU(ctx, cudaMemcpyAsync(cur_states(ctx) + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, sync_all(ctx));
     st.n_hi = n;

@@ -305,6 +305,8 @@ cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint
 // the nested emitters of a phase: count per parent, scan + append, spawn the children
 cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t n_cmds, cudaStream_t s);
 cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, int team_size, cudaStream_t s);
+// compaction without collisions: per-tile death counts and their per-stream exclusive prefixes (before launch_update)
+cudaError_t launch_count_scan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, uint32_t n_slots, cudaStream_t s);
 cudaError_t update_grid_size(int device, int *grids /*[kNumVariants]*/, int *team_size);
 // live ParticleInstance rows of the streams [slot_begin, slot_end) -> contiguous 64-byte rows
 cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, float4 *dst,

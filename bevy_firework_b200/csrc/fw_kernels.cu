@@ -63,6 +63,14 @@ __device__ __forceinline__ void st_pack(T *p, T v) {
 }
 
 __device__ __forceinline__ uint32_t wrap(uint32_t x, uint32_t cap) { return x >= cap ? x - cap : x; }
+__device__ __forceinline__ bool is_fifo(uint32_t variant) { return variant == kFifo || variant == kFifoCollide; }
+// A compacting ring compacts OUT OF PLACE inside its own ring: frame f reads [head, head + n) and
+// writes the survivors behind it, to [head + n, ...), so it may only ever be half full. After the
+// frame its live particles start at head + count (a FIFO ring's: at head + dead).
+__device__ __forceinline__ uint32_t usable_capacity(const StreamDesc &d) { return is_fifo(d.variant) ? d.capacity : d.capacity / 2u; }
+__device__ __forceinline__ uint32_t live_first(const StreamDesc &d, const StreamState &st) {
+    return wrap(st.head + (is_fifo(d.variant) ? st.dead : st.count), d.capacity);
+}
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 constexpr float kF32Min = -3.402823466e+38f; // f32::MIN, initial last_emitted_age (src/core.rs:467)
 
@@ -109,8 +117,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
             if (d.capacity == 0u) continue;
             StreamState st = (what & kPlanDeaths) ? t.states_prev[s] : t.states[s];
             if (what & kPlanDeaths) { // last frame's buffer -> this frame's buffer
-                const bool fifo = (d.variant == kFifo || d.variant == kFifoCollide);
-                if (fifo) st.head = wrap(st.head + st.dead, d.capacity);
+                st.head = live_first(d, st);
                 st.count -= st.dead;
                 st.dead = 0u;
                 st.aabb_min_inv[0] = st.aabb_min_inv[1] = st.aabb_min_inv[2] = 0u;
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
             }
             if (what & kPlanAppend) {
                 uint32_t spawn = spawn_per_slot[s];
-                const uint32_t room = d.capacity - st.count;
+                const uint32_t room = usable_capacity(d) - st.count;
                 if (spawn > room) {
                     st.overflow += spawn - room;
                     spawn = room;
@@ -144,8 +151,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
                     const StreamDesc d = t.descs[s];
                     if (d.capacity != 0u && d.variant == v) {
                         const uint32_t n = t.states[s].count;
-                        const bool fifo = (v == kFifo || v == kFifoCollide); // slot-aligned tiles, see update_kernel
-                        tiles = n ? (n + (fifo ? (t.states[s].head & 31u) : 0u) + kTile - 1u) / kTile : 0u;
+                        tiles = n ? (n + (t.states[s].head & 31u) + kTile - 1u) / kTile : 0u; // slot-aligned tiles, see update_kernel
                         my_total += n;
                     }
                 }
@@ -181,10 +187,9 @@ struct Derived {
 };
 __device__ __forceinline__ Derived derive_state(const StreamState &old, const StreamDesc &d, uint32_t spawn) {
     Derived r;
-    const bool fifo = (d.variant == kFifo || d.variant == kFifoCollide);
-    r.head = fifo ? wrap(old.head + old.dead, d.capacity) : old.head;
+    r.head = live_first(d, old);
     r.c0 = old.count - old.dead;
-    const uint32_t room = d.capacity - r.c0;
+    const uint32_t room = usable_capacity(d) - r.c0;
     r.dropped = spawn > room ? spawn - room : 0u;
     r.n_update = r.c0 + (spawn - r.dropped);
     return r;
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(1024) nested_scan_kernel(DeviceTables t, Frame
         const StreamDesc cd = t.descs[cmd.child_stream];
         StreamState *cs = &t.states[cmd.child_stream];
         uint32_t total = carry;
-        const uint32_t room = cd.capacity - cs->count;
+        const uint32_t room = usable_capacity(cd) - cs->count;
         if (total > room) {
             cs->overflow += total - room;
             total = room;
@@ -620,32 +625,108 @@ __device__ __forceinline__ TileRef find_tile(const uint32_t *__restrict__ prefix
     }
     return TileRef{lo, tile - prefix[lo], 0u, 0u};
 }
-// thread 0 of a CTA: everything the CTA needs to know about an upcoming tile. On the derive
-// path the first tile of a stream also publishes the stream's state for this frame.
-__device__ __forceinline__ TileRef prepare_tile(const DeviceTables &t, const FrameDeviceInputs &f, const uint32_t *prefix,
-                                                uint32_t n_slots, uint32_t tile, bool derive) {
+// the stream, ring head and particle count behind update tile `tile` (no side effects)
+__device__ __forceinline__ TileRef resolve_tile(const DeviceTables &t, const FrameDeviceInputs &f, const uint32_t *prefix,
+                                                uint32_t n_slots, uint32_t tile, bool derive, Derived *dv_out = nullptr) {
     TileRef r = find_tile(prefix, n_slots, tile);
-    StreamState *stp = &t.states[r.stream];
     if (derive) {
-        const StreamState old = t.states_prev[r.stream];
-        const Derived dv = derive_state(old, t.descs[r.stream], f.spawn_per_slot[r.stream]);
+        const Derived dv = derive_state(t.states_prev[r.stream], t.descs[r.stream], f.spawn_per_slot[r.stream]);
         r.head = dv.head;
         // concurrent spawn+step (header.step_in_spawn): this frame's new particles get their first
         // update inside the spawn kernel, the update kernel only covers the older ones
         r.n_update = f.header->step_in_spawn ? dv.c0 : dv.n_update;
-        if (r.tile == 0u) {
-            stp->head = dv.head;
-            stp->count = dv.n_update;
-            stp->spawn_base = dv.c0;
-            stp->overflow = old.overflow + dv.dropped;
-            atomicAdd(&t.plan->total_update, dv.n_update);
-            if (dv.dropped) atomicOr(&t.plan->error_flags, kErrOverflow);
-        }
+        if (dv_out) *dv_out = dv;
     } else {
-        r.head = stp->head;
-        r.n_update = stp->count;
+        r.head = t.states[r.stream].head;
+        r.n_update = t.states[r.stream].count;
     }
     return r;
+}
+// thread 0 of a CTA: everything the CTA needs to know about an upcoming tile. On the derive
+// path the first tile of a stream also publishes the stream's state for this frame.
+__device__ __forceinline__ TileRef prepare_tile(const DeviceTables &t, const FrameDeviceInputs &f, const uint32_t *prefix,
+                                                uint32_t n_slots, uint32_t tile, bool derive) {
+    Derived dv;
+    const TileRef r = resolve_tile(t, f, prefix, n_slots, tile, derive, &dv);
+    if (derive && r.tile == 0u) {
+        StreamState *stp = &t.states[r.stream];
+        stp->head = dv.head;
+        stp->count = dv.n_update;
+        stp->spawn_base = dv.c0;
+        stp->overflow = t.states_prev[r.stream].overflow + dv.dropped;
+        atomicAdd(&t.plan->total_update, dv.n_update);
+        if (dv.dropped) atomicOr(&t.plan->error_flags, kErrOverflow);
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Compaction without collisions, pass 1 and 2. A particle dies this frame iff age + dt >=
+// lifetime (src/core.rs:594-599), which only needs the `m0` and `k` packs: count_kernel writes
+// every tile's death count (one warp per tile, 24 B per particle), scan_kernel turns the counts
+// of each stream into exclusive prefixes (one warp per stream) and publishes the stream's total.
+// The update kernel then knows where its survivors go before it has loaded anything: no tile
+// waits for another one (the one-pass look-back version was bound by exactly that wait: load ->
+// aggregate -> poll per tile, profiles/r1_tuning.md section j).
+__global__ void __launch_bounds__(256) count_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant) {
+    const bool derive = f.header->derive != 0u;
+    const uint32_t n_tiles = derive ? f.header->host_n_tiles[variant] : t.plan->n_tiles[variant];
+    const uint32_t tile_base = derive ? f.header->host_tile_base[variant] : t.plan->tile_base[variant];
+    const uint32_t n_slots = f.header->n_slots;
+    const uint32_t *prefix = derive ? f.host_tile_prefix + (size_t)variant * (n_slots + 1u)
+                                    : t.tile_prefix + (size_t)variant * (t.slots_cap + 1u);
+    const float dt = f.header->dt;
+    const uint32_t lane = lane_id(), warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
+        TileRef e{};
+        if (lane == 0) e = resolve_tile(t, f, prefix, n_slots, tile, derive);
+        e.stream = __shfl_sync(0xffffffffu, e.stream, 0);
+        e.tile = __shfl_sync(0xffffffffu, e.tile, 0);
+        e.head = __shfl_sync(0xffffffffu, e.head, 0);
+        e.n_update = __shfl_sync(0xffffffffu, e.n_update, 0);
+        const StreamDesc d = t.descs[e.stream];
+        const StreamArrays a = stream_arrays(d.base, d.capacity);
+        const uint32_t shift = e.head & 31u, tile_first = e.tile * kTile;
+        uint32_t dead = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < (uint32_t)kTile / 32u; j++) {
+            const uint32_t p = tile_first + j * 32u + lane, i = p - shift;
+            const bool valid = p >= shift && i < e.n_update;
+            bool dies = false;
+            if (valid) {
+                const uint32_t slot = wrap(e.head + i, d.capacity);
+                dies = a.m0[slot].w + dt >= a.k[slot].x;
+            }
+            dead += __popc(__ballot_sync(0xffffffffu, dies));
+        }
+        if (lane == 0) t.lookback[tile_base + tile] = dead;
+    }
+}
+__global__ void __launch_bounds__(256) scan_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant) {
+    const bool derive = f.header->derive != 0u;
+    const uint32_t tile_base = derive ? f.header->host_tile_base[variant] : t.plan->tile_base[variant];
+    const uint32_t n_slots = f.header->n_slots;
+    const uint32_t *prefix = derive ? f.host_tile_prefix + (size_t)variant * (n_slots + 1u)
+                                    : t.tile_prefix + (size_t)variant * (t.slots_cap + 1u);
+    const uint32_t lane = lane_id(), warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slots; s += warps) {
+        const uint32_t begin = prefix[s], end = prefix[s + 1u];
+        if (begin == end) continue; // not a stream of this variant, or nothing to update
+        uint32_t carry = 0;
+        for (uint32_t k = begin; k < end; k += 32u) {
+            unsigned long long *w = t.lookback + tile_base + k + lane;
+            const uint32_t v = k + lane < end ? (uint32_t)*w : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += n;
+            }
+            if (k + lane < end) *w = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) t.states[s].dead = carry;
+    }
 }
 
 struct alignas(16) UpdateSmem {
@@ -653,7 +734,6 @@ struct alignas(16) UpdateSmem {
     uint64_t bar[2];
     TileRef ref[2];
     uint32_t warp_alive[kUpdateThreads / 32];
-    uint32_t sink[kUpdateThreads / 32];          // see consume-before-publish in update_kernel
     uint32_t team_cut[16];                       // first tile of every team's share (compact variants)
     uint32_t lb_sum[kUpdateThreads / 32];        // look-back partial sums, one per warp
     uint32_t lb_has_prefix[kUpdateThreads / 32]; // that warp's 32 predecessors include an inclusive prefix
@@ -680,7 +760,8 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const bool derive = f.header->derive != 0u;
     const uint32_t all_tiles = derive ? f.header->host_n_tiles[variant] : t.plan->n_tiles[variant];
-    // Tile order. FIFO tiles are independent: CTA b takes tiles b, b + grid, ... A compacting tile
+    // Tile order. Independent tiles (FIFO; compaction with precounted deaths): CTA b takes tiles b,
+    // b + grid, ... With collisions a compacting tile
     // waits for the aggregates of the preceding tiles of its stream, which couples the CTAs that
     // share a stream; with one global round robin the stream boundaries shift every round and the
     // whole grid falls into lock-step (everybody loads, then everybody computes, then everybody
@@ -695,7 +776,7 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
     const uint32_t *prefix = derive ? f.host_tile_prefix + (size_t)variant * (n_slots + 1u)
                                     : t.tile_prefix + (size_t)variant * (t.slots_cap + 1u);
     uint32_t tile_begin = blockIdx.x, tile_stride = gridDim.x, n_tiles = all_tiles;
-    if (COMPACT && team_size != 0u && gridDim.x >= 2u * team_size && all_tiles != 0u) {
+    if (COMPACT && COLLIDE && team_size != 0u && gridDim.x >= 2u * team_size && all_tiles != 0u) {
         const uint32_t n_teams = min(gridDim.x / team_size, 15u);
         if (tid <= n_teams) {
             uint32_t cut = (uint32_t)((uint64_t)all_tiles * tid / n_teams);
@@ -742,12 +823,21 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         // FIFO rings: tiles are aligned to the ring's physical slots, not to the logical index --
         // the head moves by an arbitrary count every frame, and a warp whose 32 slots start at a
         // multiple of 32 touches 4 full 128-byte lines per float4 pack instead of straddling 5
-        // (the first `shift` lanes of a stream's tile 0 idle). Compacting rings keep head % 32 == 0.
-        const uint32_t shift = COMPACT ? 0u : (head & 31u);
+        // (the first `shift` lanes of a stream's tile 0 idle).
+        const uint32_t shift = head & 31u;
         const uint32_t tile_first = e.tile * kTile;
         const uint32_t i = tile_first + tid - shift;
         const bool valid = tile_first + tid >= shift && i < n_update;
         const uint32_t slot = wrap(head + (valid ? i : 0u), d.capacity);
+        // compacting rings: logical index of the tile's first particle; the survivors go OUT OF
+        // PLACE, behind the particles this frame reads (usable_capacity keeps the ring half empty)
+        const uint32_t first_logical = tile_first > shift ? tile_first - shift : 0u;
+        const uint32_t dst_base = wrap(head + n_update, d.capacity);
+        // without collisions the death counts were taken by count_kernel / scan_kernel: dead
+        // particles of the stream before this tile
+        constexpr bool PRECOUNT = COMPACT && !COLLIDE;
+        uint32_t pre_excl = 0;
+        if (PRECOUNT) pre_excl = (uint32_t)t.lookback[tile_base + tile];
 
         // ---- loads: 64 B per particle, five independent coalesced requests per thread
         float4 M0 = make_float4(0.f, 0.f, 0.f, 0.f), M1 = M0, M2 = M0;
@@ -766,9 +856,10 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         }
         // next tile: stream lookup + settings prefetch into the other buffer (every thread left
         // that buffer at the __syncthreads closing the previous iteration). ~2.5k cycles of
-        // dependent loads for one thread: on thread 0, unless the tile's aggregate waits for warp 0
-        // (compacting variants: the last warp does it, after the aggregate is out)
-        const uint32_t prep_tid = COMPACT ? kUpdateThreads - 32u : 0u;
+        // dependent loads for one thread: on thread 0, except where the tile's look-back aggregate
+        // waits for warp 0 (compaction with collisions: the last warp does it, after the aggregate)
+        constexpr bool LOOKBACK = COMPACT && COLLIDE;
+        const uint32_t prep_tid = LOOKBACK ? kUpdateThreads - 32u : 0u;
         auto prepare_next = [&]() {
             if (tid == prep_tid && tile + tile_stride < n_tiles) {
                 const TileRef r = prepare_tile(t, f, prefix, n_slots, tile + tile_stride, derive);
@@ -776,129 +867,101 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
                 bulk_load(&sm.settings[buf ^ 1u], &t.settings[r.stream], sizeof(DevParticleSettings), &sm.bar[buf ^ 1u]);
             }
         };
-        if (!COMPACT) prepare_next();
+        if (!LOOKBACK) prepare_next();
+        mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
+        const DevParticleSettings &ps = sm.settings[buf];
 
-        // ---- compacting variants, part 1: this tile's death count (its look-back aggregate) goes
-        // out as early as possible -- every later tile of the stream waits for it. Without
-        // collisions a particle dies iff age + dt >= lifetime (:594-599), known as soon as the
-        // loads are back; destroy_on_collision is only known after the step (EARLY == false).
-        constexpr bool EARLY = COMPACT && !COLLIDE;
+        // ---- reference src/core.rs:591-658
         float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
         float scale = 0.f, age;
-        uint32_t alive_mask = 0, before = 0, tile_dead = 0;
-        unsigned long long *status = t.lookback + tile_base + tile;
-        const unsigned long long tag = (unsigned long long)epoch << 34;
-        auto publish_aggregate = [&](bool alive_now) {
-            alive_mask = __ballot_sync(0xffffffffu, alive_now);
+        bool destroyed_by_collision;
+        bool alive = step_particle<COLLIDE>(t, ps, dt, valid, M0, M1, M2, M3, K, c0, c1, scale, age, destroyed_by_collision,
+                                            COLLIDE ? cq.q + tid : nullptr);
+        // destroyed-particle stream (:588,597,637): the record the handler receives keeps the old
+        // colours (and the old scale unless a collision destroyed it)
+        const bool capture = COMPACT && d.destroyed_base != nullptr && valid && !alive;
+        if (capture) {
+            c0 = a.o0[slot];
+            c1 = a.o1[slot];
+            if (!destroyed_by_collision) {
+                scale = a.o2[slot];
+                M0.w = age; // age is bumped before the lifetime test (:594-598)
+            }
+        }
+        FW_DBG(0)
+        const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
+        const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
+
+        // ---- destination slot of a survivor
+        uint32_t dslot = slot;
+        if (COMPACT) {
+            // rank of this particle among the survivors of its tile: warp ballot + popc, then the
+            // warps' counts through shared memory
             if (lane == 0) sm.warp_alive[warp] = __popc(alive_mask);
-            __syncthreads(); // every load of this tile has returned by now (see consume_loads)
-            uint32_t tile_alive = 0;
+            __syncthreads();
+            uint32_t before = 0, tile_alive = 0;
 #pragma unroll
             for (uint32_t w = 0; w < kUpdateThreads / 32; w++) {
                 const uint32_t n = sm.warp_alive[w];
                 if (w < warp) before += n;
                 tile_alive += n;
             }
-            // (the host's tile table holds upper bounds: a tile may lie entirely past the count)
-            const uint32_t tile_valid = tile_first < n_update ? min(n_update - tile_first, (uint32_t)kTile) : 0u;
-            tile_dead = tile_valid - tile_alive;
-            if (tid == 0 && e.tile != 0u) st_status(status, tag | (kFlagAgg << 32) | tile_dead);
-        };
-        if (EARLY) {
-            // In place is safe because the aggregate is published after a barrier that follows the
-            // RETURN of every load of the tile: a real instruction consumes each loaded register
-            // (the math that uses them for good only comes after the barrier)
-            const bool alive_early = valid && !(M0.w + dt >= K.x);
-            uint32_t sink = __float_as_uint(M1.w) ^ __float_as_uint(M2.w) ^ __float_as_uint(M3.y);
-#pragma unroll
-            for (uint32_t j = 0; j < kMaxLea; j++) sink ^= __float_as_uint(lea_v[j]);
-            if (d.destroyed_base != nullptr && valid && !alive_early) { // destroyed-particle record, see below
-                c0 = a.o0[slot];
-                c1 = a.o1[slot];
-                scale = a.o2[slot];
-                sink ^= __float_as_uint(c0.w) ^ __float_as_uint(c1.w) ^ __float_as_uint(scale);
-            }
-            sink = __reduce_xor_sync(0xffffffffu, sink); // (the REDUX itself reads every lane's registers)
-            if (lane == 0) asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(&sm.sink[warp])), "r"(sink) : "memory");
-            publish_aggregate(alive_early);
-            FW_DBG(0)
-            prepare_next();
-        }
-        mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
-        const DevParticleSettings &ps = sm.settings[buf];
-
-        // ---- reference src/core.rs:591-658
-        bool destroyed_by_collision;
-        bool alive = step_particle<COLLIDE>(t, ps, dt, valid, M0, M1, M2, M3, K, c0, c1, scale, age, destroyed_by_collision,
-                                            COLLIDE ? cq.q + tid : nullptr);
-        // destroyed-particle stream (:588,597,637): the record the handler receives keeps the old
-        // colours (and the old scale unless a collision destroyed it); read them before this
-        // tile publishes its prefix, i.e. before later tiles may compact over these slots
-        // (EARLY read them above, before the aggregate went out)
-        const bool capture = COMPACT && d.destroyed_base != nullptr && valid && !alive;
-        if (capture) {
-            if (!EARLY) {
-                c0 = a.o0[slot];
-                c1 = a.o1[slot];
-                if (!destroyed_by_collision) scale = a.o2[slot];
-            }
-            if (!destroyed_by_collision) M0.w = age; // age is bumped before the lifetime test (:594-598)
-        }
-        FW_DBG(1)
-        if (COMPACT && !EARLY) {
-            publish_aggregate(alive);
-            prepare_next();
-        }
-        if (!COMPACT) alive_mask = __ballot_sync(0xffffffffu, alive);
-        const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
-
-        // ---- destination slot of a survivor
-        uint32_t dslot = slot;
-        if (COMPACT) {
-            // part 2: decoupled look-back over the preceding tiles of the same stream, 256 at a
-            // time: one THREAD per predecessor, so a stream of up to 256 tiles needs a single round
-            // of status loads (a serial walk by one thread cost ~0.35 us per step, a walk by one
-            // warp up to three dependent rounds at C3r's 77 tiles; profiles/r1_tuning.md)
-            uint32_t excl = 0;
-            if (e.tile != 0u) {
-                for (uint32_t nearest = e.tile - 1u;; nearest -= (uint32_t)kTile) {
-                    const bool in_stream = tid <= nearest; // predecessor nearest - tid exists
-                    unsigned long long w;
-                    bool ready;
-                    do {
-                        w = in_stream ? ld_status(status - 1 - tid - (e.tile - 1u - nearest)) : (tag | (kFlagPrefix << 32));
-                        ready = (w >> 34) == (unsigned long long)epoch && ((w >> 32) & 3ull) != 0ull;
-                    } while (!__all_sync(0xffffffffu, ready));
-                    FW_DBG(2)
-                    const uint32_t prefix_lanes = __ballot_sync(0xffffffffu, ((w >> 32) & 3ull) == kFlagPrefix);
-                    const uint32_t upto = prefix_lanes ? (uint32_t)__ffs((int)prefix_lanes) - 1u : 31u;
-                    const uint32_t part = __reduce_add_sync(0xffffffffu, lane <= upto ? (uint32_t)w : 0u);
-                    if (lane == 0) {
-                        sm.lb_sum[warp] = part;
-                        sm.lb_has_prefix[warp] = prefix_lanes != 0u;
-                    }
-                    __syncthreads();
-                    bool found = false;
-#pragma unroll
-                    for (uint32_t w8 = 0; w8 < kUpdateThreads / 32; w8++) {
-                        if (!found) {
-                            excl += sm.lb_sum[w8];
-                            found = sm.lb_has_prefix[w8] != 0u;
+            FW_DBG(1)
+            uint32_t excl = pre_excl; // dead particles of the stream before this tile
+            if (LOOKBACK) {
+                // destroy_on_collision: deaths are only known now, so the tiles of a stream chain
+                // through a decoupled look-back. One status word per tile (epoch | flag | count).
+                // (the host's tile table holds upper bounds: a tile may lie entirely past the count)
+                const uint32_t tile_end = min(n_update, tile_first + (uint32_t)kTile - shift);
+                const uint32_t tile_dead = (tile_end > first_logical ? tile_end - first_logical : 0u) - tile_alive;
+                unsigned long long *status = t.lookback + tile_base + tile;
+                const unsigned long long tag = (unsigned long long)epoch << 34;
+                if (tid == 0 && e.tile != 0u) st_status(status, tag | (kFlagAgg << 32) | tile_dead);
+                prepare_next();
+                // 256 predecessors at a time, one THREAD per predecessor, so a stream of up to 256
+                // tiles needs a single round of status loads (a serial walk by one thread cost
+                // ~0.35 us per step; profiles/r1_tuning.md)
+                excl = 0;
+                if (e.tile != 0u) {
+                    for (uint32_t nearest = e.tile - 1u;; nearest -= (uint32_t)kTile) {
+                        const bool in_stream = tid <= nearest; // predecessor nearest - tid exists
+                        unsigned long long w;
+                        bool ready;
+                        do {
+                            w = in_stream ? ld_status(status - 1 - tid - (e.tile - 1u - nearest)) : (tag | (kFlagPrefix << 32));
+                            ready = (w >> 34) == (unsigned long long)epoch && ((w >> 32) & 3ull) != 0ull;
+                        } while (!__all_sync(0xffffffffu, ready));
+                        FW_DBG(2)
+                        const uint32_t prefix_lanes = __ballot_sync(0xffffffffu, ((w >> 32) & 3ull) == kFlagPrefix);
+                        const uint32_t upto = prefix_lanes ? (uint32_t)__ffs((int)prefix_lanes) - 1u : 31u;
+                        const uint32_t part = __reduce_add_sync(0xffffffffu, lane <= upto ? (uint32_t)w : 0u);
+                        if (lane == 0) {
+                            sm.lb_sum[warp] = part;
+                            sm.lb_has_prefix[warp] = prefix_lanes != 0u;
                         }
+                        __syncthreads();
+                        bool found = false;
+#pragma unroll
+                        for (uint32_t w8 = 0; w8 < kUpdateThreads / 32; w8++) {
+                            if (!found) {
+                                excl += sm.lb_sum[w8];
+                                found = sm.lb_has_prefix[w8] != 0u;
+                            }
+                        }
+                        if (found) break;
+                        __syncthreads(); // the warp slots are rewritten by the next round
                     }
-                    if (found) break;
-                    __syncthreads(); // the warp slots are rewritten by the next round
                 }
-            }
-            if (tid == 0) {
-                st_status(status, tag | (kFlagPrefix << 32) | (excl + tile_dead));
-                if (tile_first + kTile >= n_update) stp->dead = excl + tile_dead; // last tile of the stream
+                if (tid == 0) {
+                    st_status(status, tag | (kFlagPrefix << 32) | (excl + tile_dead));
+                    if (tile_first + kTile - shift >= n_update) stp->dead = excl + tile_dead; // last tile of the stream
+                }
             }
             FW_DBG(3)
             const uint32_t alive_before = before + __popc(alive_mask & ((1u << lane) - 1u));
-            dslot = wrap(head + tile_first - excl + alive_before, d.capacity);
+            dslot = wrap(dst_base + (first_logical - excl) + alive_before, d.capacity);
             if (capture) { // destroyed particles, in Vec order, into the side block
-                const uint32_t di = excl + (tid - alive_before);
+                const uint32_t di = excl + ((i - first_logical) - alive_before);
                 const StreamArrays b = stream_arrays(d.destroyed_base, d.capacity);
                 b.m0[di] = M0;
                 b.m1[di] = M1;
@@ -961,7 +1024,7 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
     }
 #ifdef FW_DEBUG_TIMING
     if (COMPACT && (tid == 0 || tid == 200) && (blockIdx.x == 5 || blockIdx.x == 400) && f.header->epoch % 50u == 0u)
-        printf("cta %u tid %u iters %u | loads+agg %lld math %lld spin %lld lbbar %lld stores+aabb %lld endbar %lld\n", blockIdx.x, tid, it,
+        printf("cta %u tid %u iters %u | loads+math %lld ranks %lld spin %lld lookback %lld stores+aabb %lld endbar %lld\n", blockIdx.x, tid, it,
                dbg[0] / it, dbg[1] / it, dbg[2] / it, dbg[3] / it, dbg[4] / it, dbg[5] / it);
 #endif
 }
@@ -989,9 +1052,8 @@ __global__ void __launch_bounds__(256) pack_copy_kernel(DeviceTables t, uint32_t
     const StreamDesc d = t.descs[s];
     if (d.capacity == 0u) return;
     const StreamState st = t.states[s];
-    const bool fifo = (d.variant == kFifo || d.variant == kFifoCollide);
     const uint32_t live = st.count - st.dead;
-    const uint32_t first = wrap(st.head + (fifo ? st.dead : 0u), d.capacity);
+    const uint32_t first = live_first(d, st);
     const unsigned long long off = offsets[1 + blockIdx.y];
     const StreamArrays a = stream_arrays(d.base, d.capacity);
     // one 16-byte chunk of a row per thread: fully coalesced 64-byte row writes
@@ -1142,6 +1204,11 @@ cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uin
     case kCompactCollide: update_kernel<true, true><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
     default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+cudaError_t launch_count_scan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, uint32_t n_slots, cudaStream_t s) {
+    count_kernel<<<148 * 8, 256, 0, s>>>(t, f, variant); // one warp per tile, grid-stride: 64 warps per SM
+    scan_kernel<<<std::max(1u, std::min(148u * 8u, (n_slots + 7u) / 8u)), 256, 0, s>>>(t, f, variant); // one warp per stream
     return cudaGetLastError();
 }
 cudaError_t update_grid_size(int device, int *grids, int *team_size) {
