@@ -410,8 +410,10 @@ int ensure_tiles(fw_context *ctx) {
     CU(ctx, sync_all(ctx));
     if (ctx->d_lookback) CU(ctx, cudaFree(ctx->d_lookback));
     ctx->d_lookback = nullptr;
-    CU(ctx, cudaMalloc((void **)&ctx->d_lookback, sizeof(unsigned long long) * ncap));
-    CU(ctx, cudaMemsetAsync(ctx->d_lookback, 0, sizeof(unsigned long long) * ncap, ctx->stream));
+    // two words per tile: [0, ncap) look-back status / precounted exclusive prefix, [ncap, 2 ncap)
+    // precounted per-warp death counts (count_kernel)
+    CU(ctx, cudaMalloc((void **)&ctx->d_lookback, sizeof(unsigned long long) * ncap * 2));
+    CU(ctx, cudaMemsetAsync(ctx->d_lookback, 0, sizeof(unsigned long long) * ncap * 2, ctx->stream));
     ctx->tiles_cap = (uint32_t)ncap;
     topo_changed(ctx);
     return FW_OK;

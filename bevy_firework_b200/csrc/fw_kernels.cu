@@ -26,7 +26,7 @@
 #define FW_MINB 5
 #endif
 #ifndef FW_MINB_COMPACT
-#define FW_MINB_COMPACT 5 // 48 registers, no spills; C3r: 4 CTAs/SM 0.667 ms, 5 0.601 ms, 6 (40 regs) 0.591 ms
+#define FW_MINB_COMPACT 4 // 64 registers; C3r (precounted path): 4 CTAs/SM 0.412 ms, 5 (48 regs, spills) 0.421 ms, 6 0.468 ms
 #endif
 #ifndef FW_MINB_COLLIDE
 #define FW_MINB_COLLIDE 3 // the collision variants are compute-bound and need ~80 registers
@@ -663,8 +663,9 @@ __device__ __forceinline__ TileRef prepare_tile(const DeviceTables &t, const Fra
 // ------------------------------------------------------------------------------------------
 // Compaction without collisions, pass 1 and 2. A particle dies this frame iff age + dt >=
 // lifetime (src/core.rs:594-599), which only needs the `m0` and `k` packs: count_kernel writes
-// every tile's death count (one warp per tile, 24 B per particle), scan_kernel turns the counts
-// of each stream into exclusive prefixes (one warp per stream) and publishes the stream's total.
+// every tile's death count and the running count in front of each of its 8 warps (one warp per
+// tile, 24 B per particle), scan_kernel turns the tile counts of each stream into exclusive
+// prefixes (one warp per stream) and publishes the stream's total.
 // The update kernel then knows where its survivors go before it has loaded anything: no tile
 // waits for another one (the one-pass look-back version was bound by exactly that wait: load ->
 // aggregate -> poll per tile, profiles/r1_tuning.md section j).
@@ -688,8 +689,11 @@ __global__ void __launch_bounds__(256) count_kernel(DeviceTables t, FrameDeviceI
         const StreamArrays a = stream_arrays(d.base, d.capacity);
         const uint32_t shift = e.head & 31u, tile_first = e.tile * kTile;
         uint32_t dead = 0;
+        unsigned long long before_warp = 0; // dead particles of the tile in front of warp j, 8 bits each (j = 1..7)
+        static_assert(kTile == 256, "the per-warp death counts of a tile are packed as 7 x 8 bits");
 #pragma unroll
         for (uint32_t j = 0; j < (uint32_t)kTile / 32u; j++) {
+            if (j) before_warp |= (unsigned long long)dead << (8u * (j - 1u));
             const uint32_t p = tile_first + j * 32u + lane, i = p - shift;
             const bool valid = p >= shift && i < e.n_update;
             bool dies = false;
@@ -699,7 +703,10 @@ __global__ void __launch_bounds__(256) count_kernel(DeviceTables t, FrameDeviceI
             }
             dead += __popc(__ballot_sync(0xffffffffu, dies));
         }
-        if (lane == 0) t.lookback[tile_base + tile] = dead;
+        if (lane == 0) {
+            t.lookback[tile_base + tile] = dead;
+            t.lookback[t.lookback_capacity + tile_base + tile] = before_warp;
+        }
     }
 }
 __global__ void __launch_bounds__(256) scan_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant) {
@@ -837,7 +844,10 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         // particles of the stream before this tile
         constexpr bool PRECOUNT = COMPACT && !COLLIDE;
         uint32_t pre_excl = 0;
-        if (PRECOUNT) pre_excl = (uint32_t)t.lookback[tile_base + tile];
+        if (PRECOUNT) { // ... plus the dead ones of this tile in front of this warp
+            const unsigned long long in_tile = t.lookback[t.lookback_capacity + tile_base + tile];
+            pre_excl = (uint32_t)t.lookback[tile_base + tile] + (warp ? (uint32_t)(in_tile >> (8u * (warp - 1u))) & 255u : 0u);
+        }
 
         // ---- loads: 64 B per particle, five independent coalesced requests per thread
         float4 M0 = make_float4(0.f, 0.f, 0.f, 0.f), M1 = M0, M2 = M0;
@@ -895,19 +905,22 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         // ---- destination slot of a survivor
         uint32_t dslot = slot;
         if (COMPACT) {
-            // rank of this particle among the survivors of its tile: warp ballot + popc, then the
-            // warps' counts through shared memory
-            if (lane == 0) sm.warp_alive[warp] = __popc(alive_mask);
-            __syncthreads();
+            // LOOKBACK: rank of this particle among the survivors of its tile: warp ballot + popc,
+            // then the warps' counts through shared memory. PRECOUNT knows the dead in front of
+            // its warp already and needs neither shared memory nor a barrier.
             uint32_t before = 0, tile_alive = 0;
+            if (LOOKBACK) {
+                if (lane == 0) sm.warp_alive[warp] = __popc(alive_mask);
+                __syncthreads();
 #pragma unroll
-            for (uint32_t w = 0; w < kUpdateThreads / 32; w++) {
-                const uint32_t n = sm.warp_alive[w];
-                if (w < warp) before += n;
-                tile_alive += n;
+                for (uint32_t w = 0; w < kUpdateThreads / 32; w++) {
+                    const uint32_t n = sm.warp_alive[w];
+                    if (w < warp) before += n;
+                    tile_alive += n;
+                }
             }
             FW_DBG(1)
-            uint32_t excl = pre_excl; // dead particles of the stream before this tile
+            uint32_t excl = pre_excl; // dead particles of the stream before this tile (PRECOUNT: before this warp)
             if (LOOKBACK) {
                 // destroy_on_collision: deaths are only known now, so the tiles of a stream chain
                 // through a decoupled look-back. One status word per tile (epoch | flag | count).
@@ -958,10 +971,13 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
                 }
             }
             FW_DBG(3)
-            const uint32_t alive_before = before + __popc(alive_mask & ((1u << lane) - 1u));
-            dslot = wrap(dst_base + (first_logical - excl) + alive_before, d.capacity);
+            // dead particles of the stream in front of this one -> its rank among the survivors
+            const uint32_t lanes_lt = (1u << lane) - 1u;
+            const uint32_t dead_before = PRECOUNT ? excl + __popc(valid_mask & ~alive_mask & lanes_lt)
+                                                  : excl + ((i - first_logical) - (before + __popc(alive_mask & lanes_lt)));
+            dslot = wrap(dst_base + (i - dead_before), d.capacity);
             if (capture) { // destroyed particles, in Vec order, into the side block
-                const uint32_t di = excl + ((i - first_logical) - alive_before);
+                const uint32_t di = dead_before;
                 const StreamArrays b = stream_arrays(d.destroyed_base, d.capacity);
                 b.m0[di] = M0;
                 b.m1[di] = M1;
