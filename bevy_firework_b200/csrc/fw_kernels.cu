@@ -859,11 +859,6 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
             M3 = ld_pack(a.m3 + slot);
             K = ld_pack(a.k + slot);
         }
-        float lea_v[kMaxLea]; // last_emitted_age moves with the particle when compacting
-        if (COMPACT) {
-#pragma unroll
-            for (uint32_t j = 0; j < kMaxLea; j++) lea_v[j] = (valid && j < d.n_lea) ? lea_array(d.base, d.capacity, j)[slot] : 0.f;
-        }
         // next tile: stream lookup + settings prefetch into the other buffer (every thread left
         // that buffer at the __syncthreads closing the previous iteration). ~2.5k cycles of
         // dependent loads for one thread: on thread 0, except where the tile's look-back aggregate
@@ -1001,9 +996,8 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
             st_pack(a.m3 + dslot, M3);
             if (COMPACT) {
                 st_pack(a.k + dslot, K);
-#pragma unroll
-                for (uint32_t j = 0; j < kMaxLea; j++)
-                    if (j < d.n_lea) lea_array(d.base, d.capacity, j)[dslot] = lea_v[j];
+                // last_emitted_age moves with the particle (out of place: the source is still intact)
+                for (uint32_t j = 0; j < d.n_lea; j++) lea_array(d.base, d.capacity, j)[dslot] = lea_array(d.base, d.capacity, j)[slot];
             }
             st_pack(a.o0 + dslot, c0);
             st_pack(a.o1 + dslot, c1);
