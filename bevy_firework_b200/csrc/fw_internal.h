@@ -24,7 +24,8 @@
 // pack/extract kernel, which every render hand-off needs anyway.)
 //
 // Each stream is a ring: logical particle i (the reference's Vec index) lives in slot
-// (head + i) mod capacity. Order inside the ring == the reference's Vec order (survivors keep
+// (first + i) mod capacity, first = live_first(): head + dead for a FIFO ring, head + count for a
+// compacting ring (which writes its survivors behind the particles a frame reads). Order inside the ring == the reference's Vec order (survivors keep
 // their order, spawns are appended), so no per-particle serial is stored.
 #pragma once
 #include <cuda_runtime.h>
@@ -44,7 +45,8 @@ constexpr uint32_t kBytesPerSlot = 100;
 // variants of the update kernel
 enum Variant : uint32_t {
     kFifo = 0,    // constant lifetime, no destroy-on-collision: deaths are a prefix of the Vec
-    kCompact = 1, // anything else: in-place stable compaction (decoupled look-back)
+    kCompact = 1, // anything else: stable compaction, out of place inside the ring (precounted deaths;
+                  // with collisions: decoupled look-back)
     kFifoCollide = 2,
     kCompactCollide = 3,
     kNumVariants = 4
@@ -251,7 +253,8 @@ struct DeviceTables {
     uint32_t slots_cap;
     uint32_t lookback_capacity;
     PlanOut *plan;
-    unsigned long long *lookback; // one status word per tile (compact variants)
+    unsigned long long *lookback; // compact variants, two words per tile: [tile] look-back status or precounted
+                                  // exclusive prefix, [lookback_capacity + tile] precounted per-warp counts
     uint64_t seed;
     // nested emission
     uint32_t *nested_scratch;          // per-parent emission counts -> exclusive offsets
