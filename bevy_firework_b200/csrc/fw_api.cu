@@ -1450,13 +1450,14 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     // table of upper bounds: ceil(n_hi / tile) per stream, n_hi >= the stream's real count.
     const bool derive = n_phases == 1;
     h->derive = derive ? 1u : 0u;
-    // Concurrent spawn+step: when every stream is a plain FIFO ring (no compaction, no collision)
+    // Concurrent spawn+step: when every stream is a FIFO ring (no compaction)
     // the spawn kernel also gives its new particles their first update, so it needs no ordering
     // against the update kernel (which then only covers older particles) and runs on a forked
     // branch. Timed (profiling) frames stay sequential so that kernels are timed in isolation.
-    const bool step_in_spawn = derive && ctx->concurrent_spawn && !ctx->profiling && ctx->variant_streams[kFifo] > 0 &&
-                               ctx->variant_streams[kCompact] == 0 && ctx->variant_streams[kFifoCollide] == 0 &&
-                               ctx->variant_streams[kCompactCollide] == 0;
+    const bool step_in_spawn = derive && ctx->concurrent_spawn && !ctx->profiling &&
+                               ctx->variant_streams[kFifo] + ctx->variant_streams[kFifoCollide] > 0 &&
+                               ctx->variant_streams[kCompact] == 0 && ctx->variant_streams[kCompactCollide] == 0;
+    const bool spawn_collides = ctx->variant_streams[kFifoCollide] > 0;
     h->step_in_spawn = step_in_spawn ? 1u : 0u;
     if (derive) {
         uint32_t *hp = (uint32_t *)(fs.host + off_prefix);
@@ -1572,7 +1573,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
                     CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
                     forked = true;
                 } else {
-                    CU(ctx, launch_spawn(t, f, p, replay ? 0xFFFFFFFFu : (uint32_t)phase_total[p], false, ctx->stream));
+                    CU(ctx, launch_spawn(t, f, p, replay ? 0xFFFFFFFFu : (uint32_t)phase_total[p], false, false, ctx->stream));
                 }
                 launches++;
             }
@@ -1598,7 +1599,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
         }
         if (forked) {
             CU(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-            CU(ctx, launch_spawn(t, f, 0, replay ? 0xFFFFFFFFu : (uint32_t)phase_total[0], true, ctx->side_stream));
+            CU(ctx, launch_spawn(t, f, 0, replay ? 0xFFFFFFFFu : (uint32_t)phase_total[0], true, spawn_collides, ctx->side_stream));
             CU(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
             CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); // join
         }

@@ -302,9 +302,10 @@ constexpr uint32_t kPlanDeaths = 1u, kPlanAppend = 2u, kPlanTiles = 4u;
 cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant_mask, uint32_t what,
                         uint32_t phase, cudaStream_t s);
 // total_spawn: particles of the phase, or 0xFFFFFFFF = unknown at launch time (graph replay)
-// step: the kernel also applies this frame's update to the particles it creates (see spawn_kernel)
+// step: the kernel also applies this frame's update to the particles it creates (see spawn_kernel);
+// collide: ... including the collision sweep of the streams that have one
 cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, bool step,
-                         cudaStream_t s);
+                         bool collide, cudaStream_t s);
 // the nested emitters of a phase: count per parent, scan + append, spawn the children
 cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t n_cmds, cudaStream_t s);
 cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, int team_size, cudaStream_t s);

@@ -297,7 +297,8 @@ __device__ __forceinline__ void emit_particle(const DeviceTables &t, const fw_em
 template <bool COLLIDE>
 __device__ __forceinline__ bool step_particle(const DeviceTables &t, const DevParticleSettings &ps, float dt, bool valid, float4 &M0,
                                               float4 &M1, float4 &M2, float2 &M3, float2 K, float4 &c0, float4 &c1, float &scale,
-                                              float &age_out, bool &destroyed_by_collision, uint32_t *cand_queue = nullptr) {
+                                              float &age_out, bool &destroyed_by_collision, uint32_t *cand_queue = nullptr,
+                                              bool sweeps = true) {
     const float lifetime = K.x, iscale = K.y;
     const float age = M0.w + dt;              // :594
     bool alive = valid && !(age >= lifetime); // :596-599
@@ -306,11 +307,11 @@ __device__ __forceinline__ bool step_particle(const DeviceTables &t, const DevPa
     V3 pos = v3(M0.x, M0.y, M0.z), vel = v3(M2.x, M2.y, M2.z);
     bool should_destroy = false;
     if (COLLIDE) // :608-617, hoisted out of the branch so that the warp stays converged inside
-        particle_collision(t.colliders, t.broadphase, ps.collision, alive, pos, vel, dt, cand_queue, should_destroy);
+        particle_collision(t.colliders, t.broadphase, ps.collision, alive && sweeps, pos, vel, dt, cand_queue, should_destroy);
     if (alive) {
         const float age_percent = age / lifetime;                   // :601
         scale = iscale * sample_curve(ps.scale_curve, age_percent); // :602-605
-        if (!COLLIDE) pos = pos + vel * dt;                         // :619-623
+        if (!COLLIDE || !sweeps) pos = pos + vel * dt;              // :619-623
         if (should_destroy) {
             alive = false;                              // :636-639: position, velocity and scale
             destroyed_by_collision = true;              // are already updated
@@ -375,9 +376,21 @@ __device__ __forceinline__ uint32_t find_cmd(const FrameDeviceInputs &f, uint32_
 // STEP: the kernel also applies this frame's update (src/core.rs:591-658) to the particles it
 // creates, so that it can run CONCURRENTLY with update_kernel, which then only touches older
 // particles (FIFO streams without collision only; the host decides, header.step_in_spawn).
-template <bool STEP>
-__global__ void __launch_bounds__(256, 5) spawn_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t phase) {
+template <bool COLLIDE>
+struct CandQueue { // broad-phase candidates of cast_ray, one column per thread
+    uint32_t q[kCandQueue * kUpdateThreads];
+};
+template <>
+struct CandQueue<false> {
+    uint32_t q[1];
+};
+// COLLIDE (only with STEP): some of the streams sweep their particles against the colliders
+// (src/core.rs:608-617), so the first step does too (warp-synchronous, see cast_ray).
+template <bool STEP, bool COLLIDE>
+__global__ void __launch_bounds__(256, COLLIDE ? FW_MINB_COLLIDE : 5) spawn_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t phase) {
+    static_assert(kUpdateThreads == 256, "the candidate queue is laid out for 256-thread CTAs");
     __shared__ uint32_t s_cmd;
+    __shared__ CandQueue<STEP && COLLIDE> cq;
     const PhaseInfo ph = f.header->phase[phase];
     const float dt = f.header->dt;
     const uint32_t n_slots = f.header->n_slots;
@@ -442,8 +455,15 @@ __global__ void __launch_bounds__(256, 5) spawn_kernel(DeviceTables t, FrameDevi
             // first update step of the new particle, then one store of the final state
             float age;
             bool by_collision;
-            const bool alive = step_particle<false>(t, t.settings[have ? stream : 0u], dt, have, p.m0, p.m1, p.m2, p.m3, p.k, p.o0, p.o1,
-                                                    p.o2, age, by_collision);
+            const DevParticleSettings &ps = t.settings[have ? stream : 0u];
+            bool alive;
+            if (COLLIDE) { // per lane: only the streams with collision settings sweep
+                const bool sweeps = have && d.variant == kFifoCollide;
+                alive = step_particle<true>(t, ps, dt, have, p.m0, p.m1, p.m2, p.m3, p.k, p.o0, p.o1, p.o2, age, by_collision,
+                                            cq.q + threadIdx.x, sweeps);
+            } else {
+                alive = step_particle<false>(t, ps, dt, have, p.m0, p.m1, p.m2, p.m3, p.k, p.o0, p.o1, p.o2, age, by_collision);
+            }
             if (alive) store_particle(d, slot, p, true);
             // AABB and death count per stream: lanes of a warp may belong to different streams
             const uint32_t group = __match_any_sync(0xffffffffu, stream);
@@ -627,7 +647,7 @@ __device__ __forceinline__ TileRef find_tile(const uint32_t *__restrict__ prefix
 }
 // the stream, ring head and particle count behind update tile `tile` (no side effects)
 __device__ __forceinline__ TileRef resolve_tile(const DeviceTables &t, const FrameDeviceInputs &f, const uint32_t *prefix,
-                                                uint32_t n_slots, uint32_t tile, bool derive, Derived *dv_out = nullptr) {
+                                                uint32_t n_slots, uint32_t tile, bool derive) {
     TileRef r = find_tile(prefix, n_slots, tile);
     if (derive) {
         const Derived dv = derive_state(t.states_prev[r.stream], t.descs[r.stream], f.spawn_per_slot[r.stream]);
@@ -635,7 +655,6 @@ __device__ __forceinline__ TileRef resolve_tile(const DeviceTables &t, const Fra
         // concurrent spawn+step (header.step_in_spawn): this frame's new particles get their first
         // update inside the spawn kernel, the update kernel only covers the older ones
         r.n_update = f.header->step_in_spawn ? dv.c0 : dv.n_update;
-        if (dv_out) *dv_out = dv;
     } else {
         r.head = t.states[r.stream].head;
         r.n_update = t.states[r.stream].count;
@@ -646,16 +665,24 @@ __device__ __forceinline__ TileRef resolve_tile(const DeviceTables &t, const Fra
 // path the first tile of a stream also publishes the stream's state for this frame.
 __device__ __forceinline__ TileRef prepare_tile(const DeviceTables &t, const FrameDeviceInputs &f, const uint32_t *prefix,
                                                 uint32_t n_slots, uint32_t tile, bool derive) {
-    Derived dv;
-    const TileRef r = resolve_tile(t, f, prefix, n_slots, tile, derive, &dv);
-    if (derive && r.tile == 0u) {
-        StreamState *stp = &t.states[r.stream];
-        stp->head = dv.head;
-        stp->count = dv.n_update;
-        stp->spawn_base = dv.c0;
-        stp->overflow = t.states_prev[r.stream].overflow + dv.dropped;
-        atomicAdd(&t.plan->total_update, dv.n_update);
-        if (dv.dropped) atomicOr(&t.plan->error_flags, kErrOverflow);
+    TileRef r = find_tile(prefix, n_slots, tile);
+    StreamState *stp = &t.states[r.stream];
+    if (derive) {
+        const StreamState old = t.states_prev[r.stream];
+        const Derived dv = derive_state(old, t.descs[r.stream], f.spawn_per_slot[r.stream]);
+        r.head = dv.head;
+        r.n_update = f.header->step_in_spawn ? dv.c0 : dv.n_update; // (see resolve_tile)
+        if (r.tile == 0u) {
+            stp->head = dv.head;
+            stp->count = dv.n_update;
+            stp->spawn_base = dv.c0;
+            stp->overflow = old.overflow + dv.dropped;
+            atomicAdd(&t.plan->total_update, dv.n_update);
+            if (dv.dropped) atomicOr(&t.plan->error_flags, kErrOverflow);
+        }
+    } else {
+        r.head = stp->head;
+        r.n_update = stp->count;
     }
     return r;
 }
@@ -744,14 +771,6 @@ struct alignas(16) UpdateSmem {
     uint32_t team_cut[16];                       // first tile of every team's share (compact variants)
     uint32_t lb_sum[kUpdateThreads / 32];        // look-back partial sums, one per warp
     uint32_t lb_has_prefix[kUpdateThreads / 32]; // that warp's 32 predecessors include an inclusive prefix
-};
-template <bool COLLIDE>
-struct CandQueue { // broad-phase candidates of cast_ray, one column per thread
-    uint32_t q[kCandQueue * kUpdateThreads];
-};
-template <>
-struct CandQueue<false> {
-    uint32_t q[1];
 };
 
 // The fused per-frame update. One CTA processes whole tiles of 256 consecutive particles of one
@@ -1188,12 +1207,14 @@ cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint3
     plan_kernel<<<1, 1024, 0, s>>>(t, f, variant_mask, what, phase);
     return cudaGetLastError();
 }
-cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, bool step, cudaStream_t s) {
+cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, bool step, bool collide,
+                         cudaStream_t s) {
     if (total_spawn == 0) return cudaSuccess;
     const uint32_t fixed = 148u * 5u; // one resident wave; larger counts stride
     const uint32_t blocks = total_spawn == 0xFFFFFFFFu ? fixed : std::min(fixed, (total_spawn + 255u) / 256u);
-    if (step) spawn_kernel<true><<<blocks, 256, 0, s>>>(t, f, phase);
-    else spawn_kernel<false><<<blocks, 256, 0, s>>>(t, f, phase);
+    if (step && collide) spawn_kernel<true, true><<<blocks, 256, 0, s>>>(t, f, phase);
+    else if (step) spawn_kernel<true, false><<<blocks, 256, 0, s>>>(t, f, phase);
+    else spawn_kernel<false, false><<<blocks, 256, 0, s>>>(t, f, phase);
     return cudaGetLastError();
 }
 cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t n_cmds, cudaStream_t s) {
