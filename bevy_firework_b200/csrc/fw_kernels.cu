@@ -6,7 +6,8 @@
 //                   new particle, Philox4x32-10 counter-based draws
 //   nested_*        reference src/core.rs:471-546: per-parent emission counts, scan, children
 //   update_kernel   reference src/core.rs:591-658 (+ :744-800 when COLLIDE), fused with death
-//                   handling (FIFO ring advance or in-place stable compaction), the destroyed-
+//                   handling (FIFO ring advance, or stable compaction out of place inside the ring
+//                   with deaths precounted by count_kernel / scan_kernel), the destroyed-
 //                   particle stream (:588,597,637) and the per-stream AABB (src/render.rs:677-703)
 //   pack kernels    assemble the 64-byte ParticleInstance rows (src/render.rs:95-115) of the
 //                   live particles into one contiguous buffer (render extract / all-gather)
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
 // ------------------------------------------------------------------------------------------
 // The state of a stream for THIS frame as a pure function of last frame's buffer and this
 // frame's spawn count (the fast path has no plan kernel): deaths of the last update advance the
-// head of a FIFO ring (a compacting ring already moved its survivors to the front), spawns are
+// head of a FIFO ring (a compacting ring wrote its survivors behind the particles it read), spawns are
 // appended, clamped to the ring's room (the host grows rings before that can happen).
 struct Derived {
     uint32_t head, c0, n_update, dropped;
@@ -616,10 +617,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
 // look-back status word of a tile: epoch<<34 | flag<<32 | value. The whole message is this one
 // 64-bit word, so relaxed gpu-scope accesses are enough (as in CUB's single-word tile status): a
 // release store would first drain the CTA's previous tile of particle stores, an acquire load
-// invalidates L1 -- measured on C3r as 16 % + 38 % of the kernel (profiles/r1_tuning.md). The
-// in-place hazard (a later tile storing over slots this tile read) is covered by construction:
-// the word is written after a __syncthreads() that follows the USE of every loaded value, i.e.
-// when this tile's loads have long returned.
+// invalidates L1 -- measured on C3r as 16 % + 38 % of the kernel (profiles/r1_tuning.md). No
+// other data is ordered through it: survivors are written out of place, where no tile reads.
 constexpr unsigned long long kFlagAgg = 1ull, kFlagPrefix = 2ull;
 __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
