@@ -1192,6 +1192,29 @@ static void build_broadphase(const fw_collider *colliders, uint32_t n, std::vect
     if (!items.empty()) memcpy(blob.data() + h.items_off, items.data(), 4 * items.size());
 }
 
+int fw_host_emission_count(float time_passed_in_cycle, float last_emission, float cycle_duration, float offset_start,
+                           float offset_end, float particles_per_cycle, uint64_t *times, float *next_last_emission) {
+    uint64_t n = 0;
+    float next = 0.f;
+    compute_emission_count(time_passed_in_cycle, last_emission, cycle_duration, offset_start, offset_end, particles_per_cycle, n, next);
+    if (times) *times = n;
+    if (next_last_emission) *next_last_emission = next;
+    return FW_OK;
+}
+
+int fw_host_build_broadphase(const fw_collider *colliders, uint32_t n, void *out, uint64_t cap_bytes, uint64_t *n_bytes) {
+    if (n && !colliders) return FW_ERR_INVALID_ARGUMENT;
+    for (uint32_t i = 0; i < n; i++)
+        if (colliders[i].kind > FW_COLLIDER_SPHERE) return FW_ERR_UNSUPPORTED;
+    std::vector<uint8_t> blob;
+    if (n) build_broadphase(colliders, n, blob);
+    if (n_bytes) *n_bytes = blob.size();
+    if (blob.size() > broadphase_bytes(n)) return FW_ERR_INTERNAL; // the device buffer is sized by this bound
+    if (!out || cap_bytes < blob.size()) return blob.empty() ? FW_OK : FW_ERR_BUFFER_TOO_SMALL;
+    if (!blob.empty()) memcpy(out, blob.data(), blob.size());
+    return FW_OK;
+}
+
 int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) {
     ENTER(ctx);
     if (n && !colliders) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_set_colliders: null");

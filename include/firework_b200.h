@@ -245,6 +245,20 @@ uint32_t fw_abi_version(void);
  * Lets a binding verify its layout against the compiled library. */
 uint32_t fw_abi_sizeof(const char *struct_name);
 
+/* ---- host-side logic of the path, callable without a device (pinned by the `-m "not gpu"` tests) */
+/* compute_emission_count (src/core.rs:553-575) exactly as fw_frame evaluates it on the host:
+ * *times = particles to emit (`as usize`: NaN / negative -> 0), *next_last_emission = the emitter's
+ * (or, for a nested emitter, the parent particle's) new last_emission */
+int fw_host_emission_count(float time_passed_in_cycle, float last_emission, float cycle_duration,
+                           float offset_start, float offset_end, float particles_per_cycle,
+                           uint64_t *times, float *next_last_emission);
+/* the broad phase fw_set_colliders builds for a collider set (what SpatialQuery::cast_ray's BVH
+ * is to the reference, src/core.rs:756-765): inflated world AABBs, stackless BVH, uniform grid;
+ * layout in DESIGN.md section 3 / BroadPhaseHeader. *n_bytes = size of the blob; it is written to
+ * `out` if cap_bytes suffices (FW_ERR_BUFFER_TOO_SMALL otherwise; out may be NULL to ask). */
+int fw_host_build_broadphase(const fw_collider *colliders, uint32_t n, void *out, uint64_t cap_bytes,
+                             uint64_t *n_bytes);
+
 int fw_create(const fw_config *cfg, fw_context **out_ctx);
 int fw_destroy(fw_context *ctx);
 

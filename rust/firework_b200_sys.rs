@@ -209,6 +209,10 @@ extern "C" {
     pub fn fw_last_error(ctx: *const fw_context) -> *const c_char;
     pub fn fw_abi_version() -> u32;
     pub fn fw_abi_sizeof(struct_name: *const c_char) -> u32;
+    // host-side logic, callable without a device
+    pub fn fw_host_emission_count(time_passed_in_cycle: f32, last_emission: f32, cycle_duration: f32, offset_start: f32,
+        offset_end: f32, particles_per_cycle: f32, times: *mut u64, next_last_emission: *mut f32) -> c_int;
+    pub fn fw_host_build_broadphase(colliders: *const fw_collider, n: u32, out: *mut c_void, cap_bytes: u64, n_bytes: *mut u64) -> c_int;
     pub fn fw_create(cfg: *const fw_config, out_ctx: *mut *mut fw_context) -> c_int;
     pub fn fw_destroy(ctx: *mut fw_context) -> c_int;
     pub fn fw_spawner_reset(
