@@ -79,9 +79,11 @@ def make_workload(name: str, rank: int):
 class Scene:
     """Drives either backend (Engine or OracleWorld: same method names) through the schedule."""
 
-    def __init__(self, backend, workload, rank, shard=None):
+    def __init__(self, backend, workload, rank, shard=None, max_spawners=None):
         self.b = backend
         self.label, self.spawners, colliders, self.fill_frames, self.bursts = make_workload(workload, rank)
+        if max_spawners is not None and len(self.spawners) > max_spawners:  # CPU arm: a bounded sample
+            self.spawners = self.spawners[:max_spawners]
         if shard is not None:  # strong scaling: this rank simulates only its block of the spawners
             world, r = shard
             from bevy_firework_b200.distributed import shard_range
@@ -204,15 +206,27 @@ def measured_peak_gbs():
 
 
 # ------------------------------------------------------------------------------ CPU arm
-def run_cpu(workload: str, steps: int, warmup: int, threads: int):
-    """the reference's CPU path: the C oracle (reference-faithful AoS loop, task per spawner)."""
+def run_cpu(workload: str, steps: int, warmup: int, threads: int, budget_s: float = 0.0):
+    """the reference's CPU path: the C oracle (reference-faithful AoS loop, task per spawner).
+    budget_s > 0: every step is a bounded sample of the workload -- the first spawners of it, as
+    many as keep fill + warm-up + `steps` frames within about budget_s seconds (the loop costs
+    ~1.8e-8 s per particle update on these hosts; throughput does not depend on the sample size
+    as long as every thread has spawners)."""
     from oracle import oracle as O
 
     class Backend(O.OracleWorld, OracleBackendTag):
         pass
 
     b = Backend(seed=W.SEED, n_threads=threads)
-    sc = Scene(b, workload, 0)
+    max_spawners = None
+    if budget_s > 0.0:
+        n_all = len(make_workload(workload, 0)[1])
+        fill = make_workload(workload, 0)[3]
+        if n_all:
+            per_spawner_frame_s = {"c5": 8.0e-3}.get(workload, 0.175 / 512.0 * (16.0 / max(threads, 1)))
+            fit = int(budget_s / ((fill + warmup + steps) * per_spawner_frame_s))
+            max_spawners = max(min(n_all, threads), min(n_all, fit - fit % max(threads, 1)))
+    sc = Scene(b, workload, 0, max_spawners=max_spawners)
     for _ in range(sc.fill_frames + warmup):
         sc.step()
     sc.updated = 0
@@ -223,7 +237,9 @@ def run_cpu(workload: str, steps: int, warmup: int, threads: int):
     updated = sc.updated
     live = b.total_live()
     b.close()
-    return updated / dt, dt / steps * 1e3, live, sc.label
+    sample = "full workload" if max_spawners is None or max_spawners >= len(make_workload(workload, 0)[1]) else \
+        f"the first {max_spawners} spawners of the workload"
+    return updated / dt, dt / steps * 1e3, live, sc.label, sample
 
 
 # ------------------------------------------------------------------------------ main
@@ -236,6 +252,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c3r", "c4", "c5"])
     ap.add_argument("--cpu-steps", type=int, default=8, help="timed frames of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=120.0,
+                    help="--impl reference: bound of the whole CPU run in seconds (the sample shrinks for large --steps)")
     ap.add_argument("--extract", action="store_true", help="also time the full instance-row extract (D2H)")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernel by kernel instead of replaying frame graphs")
     ap.add_argument("--no-concurrent-spawn", action="store_true", help="run the spawn kernel before the update kernel")
@@ -254,14 +272,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        v, ms, live, label = run_cpu(args.workload, args.steps, args.warmup, cores)
+        v, ms, live, label, sample = run_cpu(args.workload, args.steps, args.warmup, cores, budget_s=args.ref_budget_s)
         line = {
             "impl": "reference", "metric": "particles updated/sec (fused step)", "value": v, "unit": "particles/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": label, "dt": "fl32(1/60)", "live_particles": live},
             "cpu_baseline": {"value": v, "unit": "particles/s", "cores": cores, "kind": "port",
-                             "sample": f"full workload, {args.steps} frames after {args.warmup} warm-up frames; "
+                             "sample": f"{sample} ({live} live particles), {args.steps} frames after {args.warmup} warm-up frames; "
                                        "C restatement of the reference loop (no Rust toolchain in the image), "
                                        f"one task per spawner on {cores} threads, sequential spawn"},
             "e2e": {"value": v, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -410,7 +428,7 @@ def main():
             line["e2e_extract"] = extract
         if world == 1 and not args.no_cpu_baseline:
             eng.close()
-            v, cms, clive, _ = run_cpu(args.workload, args.cpu_steps, 1, cores)
+            v, cms, clive, _, _ = run_cpu(args.workload, args.cpu_steps, 1, cores)
             # Bevy's default compute pool does not get every core: 4-thread figure too
             v4 = run_cpu(args.workload, max(2, args.cpu_steps // 2), 1, 4)[0] if cores > 4 else v
             line["cpu_baseline"] = {
