@@ -37,7 +37,7 @@ from bevy_firework_b200 import workloads as W  # noqa: E402
 ALGO_BYTES_PER_PARTICLE = 156  # 64 B read + 92 B written
 # dominant kernel and its algorithmic bytes per particle, per workload: the
 # compacting variant also moves the two constants (lifetime, initial_scale) with the particle
-KERNEL_OF = {"c3r": ("fw::update_kernel<true,false>", 164), "c5": ("fw::update_kernel<false,true>", 156)}
+KERNEL_OF = {"c3r": ("fw::update_kernel<true,0>", 164), "c5": ("fw::update_kernel<false,1>", 156)}
 DT = float(np.float32(1.0) / np.float32(60.0))
 
 
@@ -396,7 +396,7 @@ def main():
         peak, peak_src = measured_peak_gbs()
         upd_kernel_ms = kprof.update_ms / args.steps
         per_launch_particles = int(kprof.particles_updated) / args.steps
-        kernel_name, algo_bytes = KERNEL_OF.get(args.workload, ("fw::update_kernel<false,false>", ALGO_BYTES_PER_PARTICLE))
+        kernel_name, algo_bytes = KERNEL_OF.get(args.workload, ("fw::update_kernel<false,0>", ALGO_BYTES_PER_PARTICLE))
         achieved = algo_bytes * per_launch_particles / (upd_kernel_ms * 1e-3) / 1e9
         line = {
             "metric": "particles updated/sec (fused step)", "value": updated_all / (ms_all * 1e-3), "unit": "particles/s",

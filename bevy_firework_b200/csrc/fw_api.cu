@@ -137,6 +137,7 @@ struct fw_context {
     std::vector<fw_emission_settings> h_emitters; // host copy, indexed like d_emitters
     fw_collider *d_colliders = nullptr;
     uint8_t *d_broadphase = nullptr; // BroadPhaseHeader blob, broadphase_bytes(n_colliders)
+    bool colliders_revolved = false; // the set contains cylinders / cones: kernels built with their exact test
     uint32_t n_colliders = 0;
     // pinned staging of (colliders | BVH nodes) for asynchronous re-uploads, a small ring guarded by events
     uint8_t *h_col_stage[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1059,9 +1060,11 @@ static void build_broadphase(const fw_collider *colliders, uint32_t n, std::vect
                                 {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
                                 {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
         for (int a = 0; a < 3; a++) {
+            // local half extents: cylinder / cone = (r, h, r)
+            const double hz = (c.kind == FW_COLLIDER_CYLINDER || c.kind == FW_COLLIDER_CONE) ? c.half_extents[0] : c.half_extents[2];
             double ext = c.kind == FW_COLLIDER_SPHERE
                              ? std::fabs((double)c.half_extents[0])
-                             : std::fabs(R[a][0] * c.half_extents[0]) + std::fabs(R[a][1] * c.half_extents[1]) + std::fabs(R[a][2] * c.half_extents[2]);
+                             : std::fabs(R[a][0] * c.half_extents[0]) + std::fabs(R[a][1] * c.half_extents[1]) + std::fabs(R[a][2] * hz);
             const double margin = 1e-3 + 1e-3 * (std::fabs((double)c.translation[a]) + ext);
             // a non-finite bound (NaN transform) becomes the whole line: it never culls
             lo[3 * i + a] = bvh_sane((float)(c.translation[a] - ext - margin), -FLT_MAX);
@@ -1205,7 +1208,7 @@ int fw_host_emission_count(float time_passed_in_cycle, float last_emission, floa
 int fw_host_build_broadphase(const fw_collider *colliders, uint32_t n, void *out, uint64_t cap_bytes, uint64_t *n_bytes) {
     if (n && !colliders) return FW_ERR_INVALID_ARGUMENT;
     for (uint32_t i = 0; i < n; i++)
-        if (colliders[i].kind > FW_COLLIDER_SPHERE) return FW_ERR_UNSUPPORTED;
+        if (colliders[i].kind > FW_COLLIDER_CONE) return FW_ERR_UNSUPPORTED;
     std::vector<uint8_t> blob;
     if (n) build_broadphase(colliders, n, blob);
     if (n_bytes) *n_bytes = blob.size();
@@ -1219,11 +1222,17 @@ int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) 
     ENTER(ctx);
     if (n && !colliders) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_set_colliders: null");
     for (uint32_t i = 0; i < n; i++)
-        if (colliders[i].kind > FW_COLLIDER_SPHERE) return fail(ctx, FW_ERR_UNSUPPORTED, "collider %u: only cuboids and spheres are supported", i);
+        if (colliders[i].kind > FW_COLLIDER_CONE) return fail(ctx, FW_ERR_UNSUPPORTED, "collider %u: only cuboids, spheres, cylinders and cones are supported", i);
     // Same collider count as before (moving colliders, re-sent every physics step): same buffers,
     // same kernel arguments, the copies below are ordered on the context's stream between the
     // frames around them -- no synchronisation, captured frame graphs stay valid. A different
     // count reallocates.
+    bool revolved = false;
+    for (uint32_t i = 0; i < n; i++) revolved = revolved || colliders[i].kind >= FW_COLLIDER_CYLINDER;
+    if (revolved != ctx->colliders_revolved) { // other kernels from the next frame on: captured graphs are stale
+        ctx->colliders_revolved = revolved;
+        topo_changed(ctx);
+    }
     const bool same_shape = n == ctx->n_colliders && (n == 0 || (ctx->d_colliders && ctx->d_broadphase));
     if (!same_shape) {
         CU(ctx, sync_all(ctx));
@@ -1480,7 +1489,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     const bool step_in_spawn = derive && ctx->concurrent_spawn && !ctx->profiling &&
                                ctx->variant_streams[kFifo] + ctx->variant_streams[kFifoCollide] > 0 &&
                                ctx->variant_streams[kCompact] == 0 && ctx->variant_streams[kCompactCollide] == 0;
-    const bool spawn_collides = ctx->variant_streams[kFifoCollide] > 0;
+    const int spawn_collides = ctx->variant_streams[kFifoCollide] > 0 ? (ctx->colliders_revolved ? 2 : 1) : 0;
     h->step_in_spawn = step_in_spawn ? 1u : 0u;
     if (derive) {
         uint32_t *hp = (uint32_t *)(fs.host + off_prefix);
@@ -1596,7 +1605,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
                     CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
                     forked = true;
                 } else {
-                    CU(ctx, launch_spawn(t, f, p, replay ? 0xFFFFFFFFu : (uint32_t)phase_total[p], false, false, ctx->stream));
+                    CU(ctx, launch_spawn(t, f, p, replay ? 0xFFFFFFFFu : (uint32_t)phase_total[p], false, 0, ctx->stream));
                 }
                 launches++;
             }
@@ -1617,7 +1626,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
         }
         for (uint32_t v = 0; v < kNumVariants; v++) {
             if (!ctx->variant_streams[v]) continue;
-            CU(ctx, launch_update(t, f, v, ctx->grids[v], ctx->team_size, ctx->stream));
+            CU(ctx, launch_update(t, f, v, ctx->grids[v], ctx->team_size, ctx->colliders_revolved, ctx->stream));
             launches++;
         }
         if (forked) {

@@ -305,10 +305,12 @@ cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint3
 // step: the kernel also applies this frame's update to the particles it creates (see spawn_kernel);
 // collide: ... including the collision sweep of the streams that have one
 cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, bool step,
-                         bool collide, cudaStream_t s);
+                         int collide /* 0 none, 1 cuboids / spheres, 2 + cylinders / cones */, cudaStream_t s);
 // the nested emitters of a phase: count per parent, scan + append, spawn the children
 cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t n_cmds, cudaStream_t s);
-cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, int team_size, cudaStream_t s);
+// revolved: the collider set contains cylinders / cones (selects the kernel build that can test them)
+cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, int team_size, bool revolved,
+                          cudaStream_t s);
 // compaction without collisions: per-tile death counts and their per-stream exclusive prefixes (before launch_update)
 cudaError_t launch_count_scan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, uint32_t n_slots, cudaStream_t s);
 cudaError_t update_grid_size(int device, int *grids /*[kNumVariants]*/, int *team_size);

@@ -293,9 +293,10 @@ __device__ __forceinline__ void emit_particle(const DeviceTables &t, const fw_em
 // ------------------------------------------------------------------------------------------
 // One particle, one frame: reference src/core.rs:591-658 in the reference's order. Returns
 // whether the particle survives; the packs are updated in place, colours / scale are outputs.
-// COLLIDE: warp-synchronous (every lane of the warp must call; cand_queue = this thread's column of
-// the CTA's candidate queue, see cast_ray).
-template <bool COLLIDE>
+// COLLIDE (0 none, 1 cuboid / sphere colliders, 2 + cylinders / cones): warp-synchronous (every
+// lane of the warp must call; cand_queue = this thread's column of the CTA's candidate queue, see
+// cast_ray).
+template <int COLLIDE>
 __device__ __forceinline__ bool step_particle(const DeviceTables &t, const DevParticleSettings &ps, float dt, bool valid, float4 &M0,
                                               float4 &M1, float4 &M2, float2 &M3, float2 K, float4 &c0, float4 &c1, float &scale,
                                               float &age_out, bool &destroyed_by_collision, uint32_t *cand_queue = nullptr,
@@ -308,7 +309,7 @@ __device__ __forceinline__ bool step_particle(const DeviceTables &t, const DevPa
     V3 pos = v3(M0.x, M0.y, M0.z), vel = v3(M2.x, M2.y, M2.z);
     bool should_destroy = false;
     if (COLLIDE) // :608-617, hoisted out of the branch so that the warp stays converged inside
-        particle_collision(t.colliders, t.broadphase, ps.collision, alive && sweeps, pos, vel, dt, cand_queue, should_destroy);
+        particle_collision<(COLLIDE == 2)>(t.colliders, t.broadphase, ps.collision, alive && sweeps, pos, vel, dt, cand_queue, should_destroy);
     if (alive) {
         const float age_percent = age / lifetime;                   // :601
         scale = iscale * sample_curve(ps.scale_curve, age_percent); // :602-605
@@ -387,11 +388,11 @@ struct CandQueue<false> {
 };
 // COLLIDE (only with STEP): some of the streams sweep their particles against the colliders
 // (src/core.rs:608-617), so the first step does too (warp-synchronous, see cast_ray).
-template <bool STEP, bool COLLIDE>
+template <bool STEP, int COLLIDE>
 __global__ void __launch_bounds__(256, COLLIDE ? FW_MINB_COLLIDE : 5) spawn_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t phase) {
     static_assert(kUpdateThreads == 256, "the candidate queue is laid out for 256-thread CTAs");
     __shared__ uint32_t s_cmd;
-    __shared__ CandQueue<STEP && COLLIDE> cq;
+    __shared__ CandQueue<(STEP && COLLIDE != 0)> cq;
     const PhaseInfo ph = f.header->phase[phase];
     const float dt = f.header->dt;
     const uint32_t n_slots = f.header->n_slots;
@@ -460,10 +461,10 @@ __global__ void __launch_bounds__(256, COLLIDE ? FW_MINB_COLLIDE : 5) spawn_kern
             bool alive;
             if (COLLIDE) { // per lane: only the streams with collision settings sweep
                 const bool sweeps = have && d.variant == kFifoCollide;
-                alive = step_particle<true>(t, ps, dt, have, p.m0, p.m1, p.m2, p.m3, p.k, p.o0, p.o1, p.o2, age, by_collision,
-                                            cq.q + threadIdx.x, sweeps);
+                alive = step_particle<COLLIDE>(t, ps, dt, have, p.m0, p.m1, p.m2, p.m3, p.k, p.o0, p.o1, p.o2, age, by_collision,
+                                               cq.q + threadIdx.x, sweeps);
             } else {
-                alive = step_particle<false>(t, ps, dt, have, p.m0, p.m1, p.m2, p.m3, p.k, p.o0, p.o1, p.o2, age, by_collision);
+                alive = step_particle<0>(t, ps, dt, have, p.m0, p.m1, p.m2, p.m3, p.k, p.o0, p.o1, p.o2, age, by_collision);
             }
             if (alive) store_particle(d, slot, p, true);
             // AABB and death count per stream: lanes of a warp may belong to different streams
@@ -777,11 +778,11 @@ struct alignas(16) UpdateSmem {
 // look-back of the compact variants: a tile only ever waits on lower-numbered tiles, and every
 // CTA of the grid is resident). Thread 0 looks up the next tile's stream and prefetches its
 // settings block with a bulk async copy while the CTA works on the current tile.
-template <bool COMPACT, bool COLLIDE>
+template <bool COMPACT, int COLLIDE>
 __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (COMPACT ? FW_MINB_COMPACT : FW_MINB))
     update_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant, uint32_t team_size) {
     __shared__ UpdateSmem sm;
-    __shared__ CandQueue<COLLIDE> cq;
+    __shared__ CandQueue<(COLLIDE != 0)> cq;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const bool derive = f.header->derive != 0u;
     const uint32_t all_tiles = derive ? f.header->host_n_tiles[variant] : t.plan->n_tiles[variant];
@@ -1206,14 +1207,15 @@ cudaError_t launch_plan(const DeviceTables &t, const FrameDeviceInputs &f, uint3
     plan_kernel<<<1, 1024, 0, s>>>(t, f, variant_mask, what, phase);
     return cudaGetLastError();
 }
-cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, bool step, bool collide,
+cudaError_t launch_spawn(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t total_spawn, bool step, int collide,
                          cudaStream_t s) {
     if (total_spawn == 0) return cudaSuccess;
     const uint32_t fixed = 148u * 5u; // one resident wave; larger counts stride
     const uint32_t blocks = total_spawn == 0xFFFFFFFFu ? fixed : std::min(fixed, (total_spawn + 255u) / 256u);
-    if (step && collide) spawn_kernel<true, true><<<blocks, 256, 0, s>>>(t, f, phase);
-    else if (step) spawn_kernel<true, false><<<blocks, 256, 0, s>>>(t, f, phase);
-    else spawn_kernel<false, false><<<blocks, 256, 0, s>>>(t, f, phase);
+    if (step && collide == 2) spawn_kernel<true, 2><<<blocks, 256, 0, s>>>(t, f, phase);
+    else if (step && collide == 1) spawn_kernel<true, 1><<<blocks, 256, 0, s>>>(t, f, phase);
+    else if (step) spawn_kernel<true, 0><<<blocks, 256, 0, s>>>(t, f, phase);
+    else spawn_kernel<false, 0><<<blocks, 256, 0, s>>>(t, f, phase);
     return cudaGetLastError();
 }
 cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t phase, uint32_t n_cmds, cudaStream_t s) {
@@ -1225,13 +1227,20 @@ cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uin
     nested_spawn_kernel<<<dim3(gx, n_cmds), 256, 0, s>>>(t, f, phase);
     return cudaGetLastError();
 }
-cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, int team_size, cudaStream_t s) {
+cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, int team_size, bool revolved,
+                          cudaStream_t s) {
     const uint32_t ts = (uint32_t)team_size;
     switch (variant) {
-    case kFifo: update_kernel<false, false><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
-    case kCompact: update_kernel<true, false><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
-    case kFifoCollide: update_kernel<false, true><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
-    case kCompactCollide: update_kernel<true, true><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
+    case kFifo: update_kernel<false, 0><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
+    case kCompact: update_kernel<true, 0><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
+    case kFifoCollide:
+        if (revolved) update_kernel<false, 2><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
+        else update_kernel<false, 1><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
+        break;
+    case kCompactCollide:
+        if (revolved) update_kernel<true, 2><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
+        else update_kernel<true, 1><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
+        break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -1246,13 +1255,13 @@ cudaError_t update_grid_size(int device, int *grids, int *team_size) {
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
     int occ[kNumVariants] = {0, 0, 0, 0};
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kFifo], update_kernel<false, false>, kUpdateThreads, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kFifo], update_kernel<false, 0>, kUpdateThreads, 0);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kCompact], update_kernel<true, false>, kUpdateThreads, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kCompact], update_kernel<true, 0>, kUpdateThreads, 0);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kFifoCollide], update_kernel<false, true>, kUpdateThreads, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kFifoCollide], update_kernel<false, 2>, kUpdateThreads, 0);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kCompactCollide], update_kernel<true, true>, kUpdateThreads, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kCompactCollide], update_kernel<true, 2>, kUpdateThreads, 0);
     if (e != cudaSuccess) return e;
     // persistent grids: every CTA must be resident (the look-back of the compact variants
     // spins on lower-numbered tiles)

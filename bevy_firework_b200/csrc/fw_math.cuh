@@ -281,6 +281,69 @@ __device__ __forceinline__ bool ray_ball_local(float radius, V3 o, V3 d, float m
     normal = n;
     return true;
 }
+// Cylinder and cone: the analytic solid of revolution about +Y whose radius goes linearly from r0
+// at y = -h to r1 at y = +h (cylinder r0 = r1, cone r1 = 0); defined by this build, see the oracle.
+// (not inlined: the cuboid / sphere scenes should not pay registers for it)
+__device__ __noinline__ bool ray_frustum_local(float r0, float r1, float h, V3 o, V3 d, float max_toi, float &toi, V3 &normal) {
+    const float s = (r1 - r0) / (2.0f * h), c0 = (r0 + r1) * 0.5f;
+    const float ro = c0 + s * o.y;
+    if (o.y >= -h && o.y <= h && ro >= 0.0f && o.x * o.x + o.z * o.z <= ro * ro) {
+        toi = 0.0f;
+        normal = v3(0.0f, 0.0f, 0.0f);
+        return true;
+    }
+    bool found = false;
+    float best = 0.0f;
+    V3 bn = v3(0.0f, 0.0f, 0.0f);
+    if (d.y != 0.0f) {
+        const float inv = 1.0f / d.y;
+#pragma unroll
+        for (int cap = 0; cap < 2; cap++) {
+            const float yc = cap ? h : -h, rc = cap ? r1 : r0;
+            const float t = (yc - o.y) * inv;
+            const float x = o.x + d.x * t, z = o.z + d.z * t;
+            if (rc > 0.0f && t >= 0.0f && x * x + z * z <= rc * rc && (!found || t < best)) {
+                found = true;
+                best = t;
+                bn = v3(0.0f, cap ? 1.0f : -1.0f, 0.0f);
+            }
+        }
+    }
+    const float A = d.x * d.x + d.z * d.z - (s * s) * (d.y * d.y);
+    const float B = o.x * d.x + o.z * d.z - (s * ro) * d.y;
+    const float C = o.x * o.x + o.z * o.z - ro * ro;
+    float roots[2] = {0.0f, 0.0f};
+    int n_roots = 0;
+    if (A != 0.0f) {
+        const float disc = B * B - A * C;
+        if (disc >= 0.0f) {
+            const float q = sqrtf(disc);
+            roots[0] = (-B - q) / A;
+            roots[1] = (-B + q) / A;
+            n_roots = 2;
+        }
+    } else if (B != 0.0f) {
+        roots[0] = -C / (2.0f * B);
+        n_roots = 1;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const float t = roots[k];
+        const float y = o.y + d.y * t, rr = c0 + s * y;
+        if (k < n_roots && t >= 0.0f && y >= -h && y <= h && rr >= 0.0f && (!found || t < best)) {
+            const float x = o.x + d.x * t, z = o.z + d.z * t;
+            const V3 g = v3(x, -(s * rr), z);
+            const float len = length(g);
+            found = true;
+            best = t;
+            bn = len > 0.0f ? g * (1.0f / len) : v3(0.0f, s < 0.0f ? 1.0f : -1.0f, 0.0f);
+        }
+    }
+    if (!found || !(best <= max_toi)) return false;
+    toi = best;
+    normal = bn;
+    return true;
+}
 // Broad phase (blob layout: BroadPhaseHeader in fw_internal.h). Every candidate passes a box test
 // of the ray segment's AABB against the collider's inflated world AABB; the boxes are inflated on
 // the host by far more than any fp32 rounding of the exact test, so a collider is skipped only
@@ -300,8 +363,11 @@ __device__ __forceinline__ bool ray_ball_local(float radius, V3 o, V3 d, float m
 // test then runs over the queues with the warp converged: a warp pays max-over-lanes(candidates)
 // exact tests instead of one per divergent loop trip (ncu on C5 before the split: 2.7 active
 // lanes per instruction in the exact test, profiles/r1_tuning.md).
+// REVOLVED: the collider set contains cylinders / cones (their exact test costs the cuboid /
+// sphere scenes registers, so it is compiled in only when the set needs it: C5 0.123 vs 0.129 ms).
 constexpr uint32_t kCandQueue = 4;
 __device__ __forceinline__ float grid_coord(float x, float lo, float inv_cell) { return floorf((x - lo) * inv_cell); }
+template <bool REVOLVED>
 __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ colliders, const uint8_t *__restrict__ bp,
                                          uint32_t filter_mask, bool act, V3 o, V3 d, float max_distance, uint32_t *queue,
                                          float &distance, V3 &normal) {
@@ -413,6 +479,8 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
                 V3 nl;
                 bool hit;
                 if (c.kind == FW_COLLIDER_SPHERE) hit = ray_ball_local(c.half_extents[0], ol, dl, max_distance, toi, nl);
+                else if (REVOLVED && c.kind == FW_COLLIDER_CYLINDER) hit = ray_frustum_local(c.half_extents[0], c.half_extents[0], c.half_extents[1], ol, dl, max_distance, toi, nl);
+                else if (REVOLVED && c.kind == FW_COLLIDER_CONE) hit = ray_frustum_local(c.half_extents[0], 0.0f, c.half_extents[1], ol, dl, max_distance, toi, nl);
                 else hit = ray_cuboid_local(v3(c.half_extents[0], c.half_extents[1], c.half_extents[2]), ol, dl, max_distance, toi, nl);
                 if (hit && (!found || toi < best || (toi == best && cand < best_i))) {
                     found = true;
@@ -431,6 +499,7 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
 
 // reference src/core.rs:744-800 particle_collision. Warp-synchronous like cast_ray: every lane of
 // the warp calls, lanes without a live particle pass active = false (their pos / vel stay untouched).
+template <bool REVOLVED>
 __device__ __forceinline__ void particle_collision(const fw_collider *__restrict__ colliders, const uint8_t *__restrict__ broadphase,
                                                    const fw_collision_settings &cs, bool active, V3 &pos,
                                                    V3 &vel, float delta, uint32_t *queue, bool &should_destroy) {
@@ -443,7 +512,7 @@ __device__ __forceinline__ void particle_collision(const fw_collider *__restrict
         V3 dir = (isfinite(len) && len > 0.0f) ? vel / len : v3(0.0f, 1.0f, 0.0f);
         float distance;
         V3 hit_normal;
-        const bool hit = cast_ray(colliders, broadphase, cs.filter_mask, go, pos, dir, length(vel) * delta, queue, distance, hit_normal);
+        const bool hit = cast_ray<REVOLVED>(colliders, broadphase, cs.filter_mask, go, pos, dir, length(vel) * delta, queue, distance, hit_normal);
         if (go) {
             if (hit) {
                 if (distance == 0.0f) {

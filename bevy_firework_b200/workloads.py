@@ -161,6 +161,26 @@ def sphere(radius, translation, layers: int = 1) -> _abi.fw_collider:
     return c
 
 
+def _revolved(kind, radius, height, translation, rotation, layers) -> _abi.fw_collider:
+    c = _abi.fw_collider()
+    c.kind = kind
+    c.layers = layers
+    c.half_extents[:] = [float(radius), 0.5 * float(height), 0.0]
+    c.translation[:] = [float(t) for t in translation]
+    c.rotation[:] = [float(r) for r in rotation]
+    return c
+
+
+def cylinder(radius, height, translation, rotation=(0.0, 0.0, 0.0, 1.0), layers: int = 1) -> _abi.fw_collider:
+    """``Collider::cylinder(radius, height)``, axis +Y (examples/textures.rs:195)."""
+    return _revolved(_abi.FW_COLLIDER_CYLINDER, radius, height, translation, rotation, layers)
+
+
+def cone(radius, height, translation, rotation=(0.0, 0.0, 0.0, 1.0), layers: int = 1) -> _abi.fw_collider:
+    """``Collider::cone(radius, height)``, apex towards +Y (examples/textures.rs:211)."""
+    return _revolved(_abi.FW_COLLIDER_CONE, radius, height, translation, rotation, layers)
+
+
 def grid_positions(n: int, spacing: float = 2.0, y: float = 0.1) -> List[Tuple[float, float, float]]:
     """n spawners on a near-square grid (C2: 8x8, C3: 32x16)."""
     cols = int(math.ceil(math.sqrt(n)))

@@ -191,12 +191,18 @@ typedef struct fw_particle_instance {
 } fw_particle_instance;
 
 /* ---- static colliders seen by SpatialQuery::cast_ray (src/core.rs:756-765) */
-enum fw_collider_kind { FW_COLLIDER_CUBOID = 0, FW_COLLIDER_SPHERE = 1 };
+enum fw_collider_kind {
+    FW_COLLIDER_CUBOID = 0,   /* Collider::cuboid(x, y, z): half_extents = (x/2, y/2, z/2) */
+    FW_COLLIDER_SPHERE = 1,   /* Collider::sphere(r): half_extents[0] = r */
+    FW_COLLIDER_CYLINDER = 2, /* Collider::cylinder(r, height), axis +Y: half_extents = (r, height/2, -) */
+    FW_COLLIDER_CONE = 3      /* Collider::cone(r, height), apex at +Y: half_extents = (r, height/2, -)
+                                 (examples/textures.rs:195,211 use both) */
+};
 
 typedef struct fw_collider {
     uint32_t kind;
     uint32_t layers;       /* membership bits tested against fw_collision_settings.filter_mask */
-    float half_extents[3]; /* cuboid; sphere: half_extents[0] = radius */
+    float half_extents[3]; /* see fw_collider_kind */
     float translation[3];
     float rotation[4]; /* Quat x,y,z,w */
 } fw_collider;

@@ -375,6 +375,69 @@ static int ray_ball_local(float radius, v3 o, v3 d, float max_toi, float *toi, v
     *normal = n;
     return 1;
 }
+/* Cylinder and cone (parry: support-map shapes cast with GJK -- not restated; DEFINED BY THIS
+ * BUILD as the analytic solid of revolution about +Y whose radius goes linearly from r0 at
+ * y = -h to r1 at y = +h: cylinder r0 = r1, cone r1 = 0). Solid: an origin inside gives toi 0
+ * and a zero normal, like the cuboid. Candidates in the order bottom cap, top cap, the two side
+ * roots; the first smallest one wins. */
+static int ray_frustum_local(float r0, float r1, float h, v3 o, v3 d, float max_toi, float *toi, v3 *normal) {
+    const float s = (r1 - r0) / (2.0f * h), c0 = (r0 + r1) * 0.5f;
+    const float ro = c0 + s * o.y; /* radius of the solid at the origin's height */
+    if (o.y >= -h && o.y <= h && ro >= 0.0f && o.x * o.x + o.z * o.z <= ro * ro) {
+        *toi = 0.0f;
+        *normal = v3_make(0.0f, 0.0f, 0.0f);
+        return 1;
+    }
+    int found = 0;
+    float best = 0.0f;
+    v3 bn = v3_make(0.0f, 0.0f, 0.0f);
+    if (d.y != 0.0f) {
+        const float inv = 1.0f / d.y;
+        for (int cap = 0; cap < 2; cap++) {
+            const float yc = cap ? h : -h, rc = cap ? r1 : r0;
+            const float t = (yc - o.y) * inv;
+            const float x = o.x + d.x * t, z = o.z + d.z * t;
+            if (rc > 0.0f && t >= 0.0f && x * x + z * z <= rc * rc && (!found || t < best)) {
+                found = 1;
+                best = t;
+                bn = v3_make(0.0f, cap ? 1.0f : -1.0f, 0.0f);
+            }
+        }
+    }
+    const float A = d.x * d.x + d.z * d.z - (s * s) * (d.y * d.y);
+    const float B = o.x * d.x + o.z * d.z - (s * ro) * d.y;
+    const float C = o.x * o.x + o.z * o.z - ro * ro;
+    float roots[2];
+    int n_roots = 0;
+    if (A != 0.0f) {
+        const float disc = B * B - A * C;
+        if (disc >= 0.0f) {
+            const float q = sqrtf(disc);
+            roots[0] = (-B - q) / A;
+            roots[1] = (-B + q) / A;
+            n_roots = 2;
+        }
+    } else if (B != 0.0f) {
+        roots[0] = -C / (2.0f * B);
+        n_roots = 1;
+    }
+    for (int k = 0; k < n_roots; k++) {
+        const float t = roots[k];
+        const float y = o.y + d.y * t, rr = c0 + s * y;
+        if (t >= 0.0f && y >= -h && y <= h && rr >= 0.0f && (!found || t < best)) {
+            const float x = o.x + d.x * t, z = o.z + d.z * t;
+            v3 g = v3_make(x, -(s * rr), z);
+            const float len = v3_length(g);
+            found = 1;
+            best = t;
+            bn = len > 0.0f ? v3_mul(g, 1.0f / len) : v3_make(0.0f, s < 0.0f ? 1.0f : -1.0f, 0.0f);
+        }
+    }
+    if (!found || !(best <= max_toi)) return 0;
+    *toi = best;
+    *normal = bn;
+    return 1;
+}
 int fwo_cast_ray(const fw_collider *c, uint32_t n, uint32_t filter_mask, const float origin[3],
                  const float dir[3], float max_distance, float *distance, float normal[3],
                  uint32_t *index) {
@@ -395,6 +458,10 @@ int fwo_cast_ray(const fw_collider *c, uint32_t n, uint32_t filter_mask, const f
         int hit;
         if (c[i].kind == FW_COLLIDER_SPHERE)
             hit = ray_ball_local(c[i].half_extents[0], ol, dl, max_distance, &toi, &nl);
+        else if (c[i].kind == FW_COLLIDER_CYLINDER)
+            hit = ray_frustum_local(c[i].half_extents[0], c[i].half_extents[0], c[i].half_extents[1], ol, dl, max_distance, &toi, &nl);
+        else if (c[i].kind == FW_COLLIDER_CONE)
+            hit = ray_frustum_local(c[i].half_extents[0], 0.0f, c[i].half_extents[1], ol, dl, max_distance, &toi, &nl);
         else
             hit = ray_cuboid_local(v3_make(c[i].half_extents[0], c[i].half_extents[1], c[i].half_extents[2]),
                                    ol, dl, max_distance, &toi, &nl);

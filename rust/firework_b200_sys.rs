@@ -29,6 +29,8 @@ pub const FW_SHAPE_SPHERE: u32 = 1;
 pub const FW_SHAPE_CIRCLE: u32 = 2;
 pub const FW_COLLIDER_CUBOID: u32 = 0;
 pub const FW_COLLIDER_SPHERE: u32 = 1;
+pub const FW_COLLIDER_CYLINDER: u32 = 2; // half_extents = (radius, height / 2, -), axis +Y
+pub const FW_COLLIDER_CONE: u32 = 3; // half_extents = (radius, height / 2, -), apex at +Y
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]

@@ -15,7 +15,7 @@ import pytest
 
 from bevy_firework_b200 import _abi
 from bevy_firework_b200.build import build_native
-from bevy_firework_b200.workloads import collision_scene_colliders, cuboid, sphere
+from bevy_firework_b200.workloads import collision_scene_colliders, cone, cuboid, cylinder, sphere
 
 f32 = np.float32
 
@@ -151,10 +151,15 @@ def _scene(rng, n, with_big=True, with_nan=False):
         pos = rng.uniform(-8, 8, 3)
         pos[1] = rng.uniform(0, 6)
         layers = 1 if len(cols) % 3 else 2
-        if len(cols) % 2:
-            q = rng.normal(size=4)
-            q /= np.linalg.norm(q)
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        kind = len(cols) % 4
+        if kind == 1:
             cols.append(cuboid(rng.uniform(0.1, 1.6, 3), pos, tuple(q), layers=layers))
+        elif kind == 2:
+            cols.append(cylinder(float(rng.uniform(0.1, 0.8)), float(rng.uniform(0.2, 1.5)), pos, tuple(q), layers=layers))
+        elif kind == 3:
+            cols.append(cone(float(rng.uniform(0.1, 0.8)), float(rng.uniform(0.2, 1.5)), pos, tuple(q), layers=layers))
         else:
             cols.append(sphere(float(rng.uniform(0.1, 0.9)), pos, layers=layers))
     if with_nan:
@@ -173,6 +178,8 @@ def test_broadphase_boxes_contain_the_colliders(lib):
                       [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
                       [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
         he = np.array(c.half_extents[:], dtype=np.float64)
+        if c.kind in (_abi.FW_COLLIDER_CYLINDER, _abi.FW_COLLIDER_CONE):
+            he = np.array([he[0], he[1], he[0]])  # solid of revolution about +Y: (r, h, r)
         ext = np.full(3, abs(he[0])) if c.kind == _abi.FW_COLLIDER_SPHERE else np.abs(R) @ np.abs(he)
         assert (bp.leaf[i, 0, :3] < t - ext).all() and (bp.leaf[i, 1, :3] > t + ext).all()
         assert int(bp.leaf_u[i, 0, 3]) == c.layers

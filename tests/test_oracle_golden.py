@@ -238,3 +238,36 @@ def test_particle_collision_bounce(oracle):
     # miss: plain Euler step (src/core.rs:792-795)
     pos, vel, destroy = oracle.particle_collision([ground], cs, (0.0, 5.0, 0.0), (1.0, 2.0, 3.0), 0.5)
     assert pos == (0.5, 6.0, 1.5) and vel == (1.0, 2.0, 3.0) and not destroy
+
+
+# ------------------------------------------------------------------ cylinder / cone ray casts
+def test_cylinder_and_cone_ray_casts_known_answers(oracle):
+    """the analytic cylinder / cone (defined by this build, parry casts them with GJK): closed-form
+    hits of the two colliders of examples/textures.rs:195,211"""
+    from bevy_firework_b200.workloads import cone, cylinder
+
+    base = [cylinder(4.0, 0.2, (0.0, 0.0, 0.0))]             # circular base: radius 4, height 0.2
+    hit = oracle.cast_ray(base, (1.0, 5.0, 0.0), (0.0, -1.0, 0.0), 10.0)
+    assert hit is not None and abs(hit[0] - 4.9) < 1e-6 and hit[1] == (0.0, 1.0, 0.0)   # top cap
+    hit = oracle.cast_ray(base, (10.0, 0.0, 0.0), (-1.0, 0.0, 0.0), 10.0)
+    assert hit is not None and abs(hit[0] - 6.0) < 1e-6 and hit[1] == (1.0, 0.0, 0.0)   # side
+    assert oracle.cast_ray(base, (10.0, 0.0, 0.0), (-1.0, 0.0, 0.0), 5.9) is None        # max_distance
+    assert oracle.cast_ray(base, (1.0, 5.0, 0.0), (0.0, 1.0, 0.0), 100.0) is None        # pointing away
+    assert oracle.cast_ray(base, (5.0, 5.0, 0.0), (0.0, -1.0, 0.0), 100.0) is None       # past the rim
+    hit = oracle.cast_ray(base, (1.0, 0.05, 1.0), (0.0, 1.0, 0.0), 1.0)                  # inside, solid
+    assert hit is not None and hit[0] == 0.0 and hit[1] == (0.0, 0.0, 0.0)
+
+    pyramid = [cone(0.5, 1.0, (0.0, 0.5, 0.0))]              # apex at y = 1, base radius 0.5 at y = 0
+    hit = oracle.cast_ray(pyramid, (5.0, 0.5, 0.0), (-1.0, 0.0, 0.0), 10.0)              # side at half height: r = 0.25
+    assert hit is not None and abs(hit[0] - 4.75) < 1e-6
+    n = np.array(hit[1])
+    assert np.allclose(n, np.array([2.0, 1.0, 0.0]) / np.sqrt(5.0), atol=1e-6)           # slope 1 : 2
+    hit = oracle.cast_ray(pyramid, (0.0, 5.0, 0.0), (0.0, -1.0, 0.0), 10.0)              # onto the apex
+    assert hit is not None and abs(hit[0] - 4.0) < 1e-6 and hit[1] == (0.0, 1.0, 0.0)
+    hit = oracle.cast_ray(pyramid, (0.2, -3.0, 0.0), (0.0, 1.0, 0.0), 10.0)              # base cap from below
+    assert hit is not None and abs(hit[0] - 3.0) < 1e-6 and hit[1] == (0.0, -1.0, 0.0)
+    assert oracle.cast_ray(pyramid, (0.4, 5.0, 0.0), (0.0, -1.0, 0.0), 4.1) is None      # too short to reach the side
+    hit = oracle.cast_ray(pyramid, (0.4, 5.0, 0.0), (0.0, -1.0, 0.0), 10.0)              # side at r = 0.4: y = 0.2
+    assert hit is not None and abs(hit[0] - 4.8) < 1e-6
+    # the mirrored nappe above the apex is not part of the solid
+    assert oracle.cast_ray(pyramid, (5.0, 1.5, 0.0), (-1.0, 0.0, 0.0), 10.0) is None
