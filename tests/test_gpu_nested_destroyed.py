@@ -184,3 +184,40 @@ def test_destroyed_handler_through_the_plugin():
     for _ in range(25):
         app.update(DT)
     assert sum(seen) == 200 and app.data(e).counts() == [0]
+
+
+def test_textures_example_with_its_colliders(engine, oracle):
+    """examples/textures.rs as a whole: the casings (type 0) bounce off the circular base
+    (Collider::cylinder(4, 0.2), :195) and the cone (:211) with the example's collision settings
+    (:97-102) while they trail nested smoke puffs (type 1)."""
+    from bevy_firework_b200.workloads import cone, cylinder
+
+    sp = textures_spawner(rate=600.0, nested_count=10.0)
+    sp.particle_settings[0].collision_settings = ParticleCollisionSettings(0.4, 0.35, False)
+    cols = [cylinder(4.0, 0.2, (0.0, 0.0, 0.0)), cone(0.5, 1.0, (0.0, 0.5, 0.0))]
+    w = oracle.OracleWorld()
+    engine.set_colliders(cols)
+    w.set_colliders(cols)
+    reset_both(engine, w, 7, sp)
+    q = (0.0, 0.0, -math.sin(math.pi / 4), math.cos(math.pi / 4))  # from_rotation_arc(Y, X)
+    inp = [frame_input(7, (-2.0, 2.0, 0.0), q)]
+    for k in range(200):
+        engine.frame(DT, inp)
+        w.frame(DT, inp)
+        assert engine.counts(7) == w.counts(7), f"frame {k}"
+    got, want = engine.read_particles(7, 0), w.read_particles(7, 0)
+    assert len(got) == len(want) > 1000
+    # the casings are spawned through sinf/cosf and then bounce: the north_star bound on >= 99.5 %
+    # of them (an ulp-different spawn can flip a grazing ray cast); ages exact
+    ok = np.ones(len(got), dtype=bool)
+    for f in ("position", "velocity"):
+        a, b = got[f].astype(np.float64), want[f].astype(np.float64)
+        ok &= (np.abs(a - b) <= 1e-4 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 1.0)).all(axis=1)
+    assert ok.mean() >= 0.995, ok.mean()
+    assert (got["age"] == want["age"]).all()
+    # most casings end up resting on the base (top at y = 0.1), none fell through it inside its radius
+    on_disc = np.hypot(want["position"][:, 0], want["position"][:, 2]) < 3.9
+    assert (want["position"][on_disc, 1] > 0.05).all()
+    puffs, opuffs = engine.read_particles(7, 1), w.read_particles(7, 1)
+    assert len(puffs) == len(opuffs) > 0
+    assert (puffs["age"] == opuffs["age"]).all()
