@@ -302,6 +302,42 @@ pub fn gpu_forget_removed(gpu: ResMut<GpuParticles>, mut removed: RemovedCompone
     }
 }
 
+/// `SpatialQuery::cast_ray` (src/core.rs:756-765) sees avian's colliders as of the last physics
+/// step; the library sees what this system sends. Same count as last time = an asynchronous
+/// re-upload (moving colliders), so sending every frame is cheap. Shapes the library cannot test
+/// (anything but cuboid / ball / cylinder / cone) are skipped with a warning, once.
+#[cfg(feature = "physics_avian")]
+pub fn gpu_sync_colliders(
+    gpu: ResMut<GpuParticles>,
+    q: Query<(&Collider, &GlobalTransform, Option<&CollisionLayers>)>,
+    mut scratch: Local<Vec<fw_collider>>,
+) {
+    use avian3d::parry::shape::TypedShape;
+    scratch.clear();
+    for (collider, transform, layers) in &q {
+        let t = transform.compute_transform();
+        let (kind, half_extents) = match collider.shape_scaled().as_typed_shape() {
+            TypedShape::Cuboid(c) => (FW_COLLIDER_CUBOID, [c.half_extents.x, c.half_extents.y, c.half_extents.z]),
+            TypedShape::Ball(b) => (FW_COLLIDER_SPHERE, [b.radius, 0.0, 0.0]),
+            TypedShape::Cylinder(c) => (FW_COLLIDER_CYLINDER, [c.radius, c.half_height, 0.0]),
+            TypedShape::Cone(c) => (FW_COLLIDER_CONE, [c.radius, c.half_height, 0.0]),
+            _ => {
+                bevy::log::warn_once!("firework_b200: collider shape not supported by the GPU collision sweep, ignored");
+                continue;
+            }
+        };
+        scratch.push(fw_collider {
+            kind,
+            layers: layers.map(|l| l.memberships.0).unwrap_or(1),
+            half_extents,
+            translation: t.translation.to_array(),
+            rotation: t.rotation.to_array(),
+        });
+    }
+    let rc = unsafe { fw_set_colliders(gpu.ctx, scratch.as_ptr(), scratch.len() as u32) };
+    gpu.check(rc, "fw_set_colliders");
+}
+
 /// in `impl Plugin for ParticleSystemPlugin` (src/plugin.rs:35-61) the chain becomes:
 pub fn add_gpu_systems(app: &mut App, schedule: impl bevy::ecs::schedule::ScheduleLabel + Clone) {
     app.insert_resource(GpuParticles::new(0, 0x00F1_2E00).expect("firework_b200: no B200 / library"));
@@ -315,6 +351,8 @@ pub fn add_gpu_systems(app: &mut App, schedule: impl bevy::ecs::schedule::Schedu
             gpu_sync_spawner_data,
             #[cfg(feature = "physics_avian")]
             sync_parent_velocity,
+            #[cfg(feature = "physics_avian")]
+            gpu_sync_colliders,
             gpu_frame,
             gpu_notify_finished,
         )
