@@ -189,6 +189,7 @@ EXPORTS = {
     "fw_abi_sizeof": (u32, [C.c_char_p]),
     "fw_host_emission_count": (C.c_int, [f32, f32, f32, f32, f32, f32, P(u64), P(f32)]),
     "fw_host_build_broadphase": (C.c_int, [P(fw_collider), u32, C.c_void_p, u64, P(u64)]),
+    "fw_device_sincos": (C.c_int, [_ctx, C.c_void_p, u64, C.c_void_p, C.c_void_p]),
     "fw_create": (C.c_int, [P(fw_config), P(_ctx)]),
     "fw_destroy": (C.c_int, [_ctx]),
     "fw_spawner_reset": (C.c_int, [_ctx, u32, P(fw_particle_settings), u32,

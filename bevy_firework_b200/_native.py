@@ -234,6 +234,13 @@ class Engine:
     def gather_destroy(self):
         self._check(self._L.fw_gather_destroy(self._ctx))
 
+    def device_sincos(self, x):
+        """include/fw_sincos.h evaluated on the device -> (sin, cos) float32 arrays"""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        s, c = np.empty_like(x), np.empty_like(x)
+        self._check(self._L.fw_device_sincos(self._ctx, x.ctypes.data, x.size, s.ctypes.data, c.ctypes.data))
+        return s, c
+
     def event_record(self, slot: int):
         self._check(self._L.fw_event_record(self._ctx, slot))
 

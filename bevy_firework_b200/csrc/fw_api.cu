@@ -2103,6 +2103,21 @@ int fw_gather_destroy(fw_context *ctx) {
     return FW_OK;
 }
 
+int fw_device_sincos(fw_context *ctx, const float *x, uint64_t n, float *sin_out, float *cos_out) {
+    ENTER(ctx);
+    if (n && (!x || !sin_out || !cos_out)) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_device_sincos: null");
+    if (!n) return FW_OK;
+    int rc = ensure_stage(ctx, (size_t)n * 12);
+    if (rc) return rc;
+    float *dx = (float *)ctx->d_stage, *ds = dx + n, *dc = ds + n;
+    CU(ctx, cudaMemcpyAsync(dx, x, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, launch_sincos(dx, n, ds, dc, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(sin_out, ds, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(cos_out, dc, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, sync_all(ctx));
+    return FW_OK;
+}
+
 int fw_event_record(fw_context *ctx, uint32_t slot) {
     ENTER(ctx);
     if (slot >= 16) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_event_record: slot %u out of range", slot);

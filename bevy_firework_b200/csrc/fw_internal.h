@@ -325,6 +325,8 @@ cudaError_t launch_gather_signal(const GatherPeers &p, uint32_t which, unsigned 
 cudaError_t launch_gather_particles(uint8_t *base, uint32_t capacity, uint32_t first, uint32_t n, uint32_t pbr,
                                     fw_particle_data *dst, cudaStream_t s);
 cudaError_t launch_scatter_particles(const StreamDesc &d, uint32_t n, const fw_particle_data *src, cudaStream_t s);
+// include/fw_sincos.h evaluated on the device (parity hook)
+cudaError_t launch_sincos(const float *x, uint64_t n, float *s, float *c, cudaStream_t st);
 // ring -> linear copy into a bigger block (growth)
 cudaError_t launch_ring_copy(const StreamDesc &src, uint32_t first, uint32_t n, const StreamDesc &dst, cudaStream_t s);
 

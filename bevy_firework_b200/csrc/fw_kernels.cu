@@ -238,8 +238,10 @@ __device__ __forceinline__ ParticleRegs make_particle(const DeviceTables &t, con
     V3 spawn_offset = v3(0.0f, 0.0f, 0.0f);
     if (es.shape_kind == FW_SHAPE_SPHERE) {
         const float u = u_shape0 * 2.0f * kPi, v = u_shape1 * kPi, r = u_shape2;
-        const float sv = sinf(v);
-        const V3 unit = v3(sv * cosf(u), cosf(v), sv * sinf(u));
+        float su, cu, sv, cv;
+        fw_sincosf(u, &su, &cu);
+        fw_sincosf(v, &sv, &cv);
+        const V3 unit = v3(sv * cu, cv, sv * su);
         spawn_offset = (unit * r) * es.shape_radius;
     } else if (es.shape_kind == FW_SHAPE_CIRCLE) {
         const float u = u_shape0 * 2.0f * kPi, r = u_shape1;
@@ -253,8 +255,10 @@ __device__ __forceinline__ ParticleRegs make_particle(const DeviceTables &t, con
         if (rv.spread > 0.0f) {
             const float a = ua * 2.0f * kPi;
             const float p = ur * rv.spread;
-            const float sp = sinf(p), cp = cosf(p);
-            const V3 local = v3(sp * cosf(a), cp, sp * sinf(a));
+            float sp, cp, sa, ca;
+            fw_sincosf(p, &sp, &cp);
+            fw_sincosf(a, &sa, &ca);
+            const V3 local = v3(sp * ca, cp, sp * sa);
             const Q4 arc = q_from_rotation_arc(v3(0.0f, 1.0f, 0.0f), normalize_or_zero(dir));
             dir = qrot(arc, local);
         }
@@ -1186,6 +1190,10 @@ __global__ void __launch_bounds__(256) scatter_particles_kernel(StreamDesc d, ui
     a.o2[i] = p.scale;
     for (uint32_t j = 0; j < d.n_lea; j++) lea_array(d.base, d.capacity, j)[i] = kF32Min;
 }
+__global__ void __launch_bounds__(256) sincos_kernel(const float *x, uint64_t n, float *s, float *c) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        fw_sincosf(x[i], &s[i], &c[i]);
+}
 __global__ void __launch_bounds__(256) ring_copy_kernel(StreamDesc src, uint32_t first, uint32_t n, StreamDesc dst) {
     const StreamArrays a = stream_arrays(src.base, src.capacity), b = stream_arrays(dst.base, dst.capacity);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1302,6 +1310,11 @@ cudaError_t launch_gather_particles(uint8_t *base, uint32_t capacity, uint32_t f
 cudaError_t launch_scatter_particles(const StreamDesc &d, uint32_t n, const fw_particle_data *src, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     scatter_particles_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(d, n, src);
+    return cudaGetLastError();
+}
+cudaError_t launch_sincos(const float *x, uint64_t n, float *s, float *c, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    sincos_kernel<<<(unsigned)std::min<uint64_t>((n + 255u) / 256u, 148u * 8u), 256, 0, st>>>(x, n, s, c);
     return cudaGetLastError();
 }
 cudaError_t launch_ring_copy(const StreamDesc &src, uint32_t first, uint32_t n, const StreamDesc &dst, cudaStream_t s) {

@@ -3,13 +3,15 @@
 // This translation unit is compiled with -fmad=false: every a*b+c below is two correctly
 // rounded IEEE operations, in the operation order of the reference's Rust expressions
 // (glam 0.32 scalar formulas), so position / velocity / age / scale / colours can be compared
-// bit-for-bit with a CPU evaluation of the same expressions. Only sinf/cosf (rotation, spawn
-// shapes) are library functions whose last ulp may differ from a host libm.
+// bit-for-bit with a CPU evaluation of the same expressions. Sine and cosine (rotation, spawn
+// shapes) are the library's own IEEE-only definition, include/fw_sincos.h, not CUDA's sincosf:
+// a CPU replay that compiles the same header gets the same bits.
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
 #include <stdint.h>
 
+#include "../../include/fw_sincos.h"
 #include "fw_internal.h"
 
 namespace fw {
@@ -69,7 +71,7 @@ __device__ __forceinline__ V3 qrot(Q4 q, V3 v) {
 __device__ __forceinline__ Q4 qconj(Q4 q) { return Q4{-q.x, -q.y, -q.z, q.w}; }
 __device__ __forceinline__ Q4 q_from_axis_angle(V3 axis, float angle) {
     float s, c;
-    sincosf(angle * 0.5f, &s, &c);
+    fw_sincosf(angle * 0.5f, &s, &c);
     return Q4{axis.x * s, axis.y * s, axis.z * s, c};
 }
 // glam Quat::from_scaled_axis (reference src/core.rs:646)
@@ -80,7 +82,7 @@ __device__ __forceinline__ Q4 q_from_scaled_axis(V3 v) {
 }
 __device__ __forceinline__ Q4 q_from_rotation_y(float angle) {
     float s, c;
-    sincosf(angle * 0.5f, &s, &c);
+    fw_sincosf(angle * 0.5f, &s, &c);
     return Q4{0.0f, s, 0.0f, c};
 }
 __device__ __forceinline__ V3 any_orthonormal(V3 n) {

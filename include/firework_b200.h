@@ -265,6 +265,11 @@ int fw_host_emission_count(float time_passed_in_cycle, float last_emission, floa
 int fw_host_build_broadphase(const fw_collider *colliders, uint32_t n, void *out, uint64_t cap_bytes,
                              uint64_t *n_bytes);
 
+/* include/fw_sincos.h as compiled into the kernels (-fmad=false): sine and cosine of n host floats,
+ * evaluated ON THE DEVICE. A CPU replay that compiles the same header must get the same bits; the
+ * parity tests check exactly that (every rotation and every spawned direction passes through it). */
+int fw_device_sincos(fw_context *ctx, const float *x, uint64_t n, float *sin_out, float *cos_out);
+
 int fw_create(const fw_config *cfg, fw_context **out_ctx);
 int fw_destroy(fw_context *ctx);
 

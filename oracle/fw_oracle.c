@@ -13,6 +13,8 @@
  */
 #define _GNU_SOURCE
 #include "fw_oracle.h"
+/* sine / cosine: the library's own IEEE-only definition, compiled into both sides (see the header) */
+#include "../include/fw_sincos.h"
 
 #include <float.h>
 #include <math.h>
@@ -74,7 +76,8 @@ static inline v3 q_mul_v3(q4 q, v3 v) {
 static inline q4 q_conj(q4 q) { q4 r = {-q.x, -q.y, -q.z, q.w}; return r; }
 /* glam Quat::from_axis_angle */
 static inline q4 q_from_axis_angle(v3 axis, float angle) {
-    float s = sinf(angle * 0.5f), c = cosf(angle * 0.5f);
+    float s, c;
+    fw_sincosf(angle * 0.5f, &s, &c);
     q4 r = {axis.x * s, axis.y * s, axis.z * s, c};
     return r;
 }
@@ -85,7 +88,9 @@ static inline q4 q_from_scaled_axis(v3 v) {
     return q_from_axis_angle(v3_div(v, length), length);
 }
 static inline q4 q_from_rotation_y(float angle) {
-    q4 r = {0.0f, sinf(angle * 0.5f), 0.0f, cosf(angle * 0.5f)};
+    float s, c;
+    fw_sincosf(angle * 0.5f, &s, &c);
+    q4 r = {0.0f, s, 0.0f, c};
     return r;
 }
 /* glam Vec3::any_orthonormal_vector (for the 180-degree branch of from_rotation_arc) */
@@ -109,6 +114,10 @@ static inline q4 q_from_rotation_arc(v3 from, v3 to) {
     return q;
 }
 
+void fwo_sincosf(float x, float *s, float *c) { fw_sincosf(x, s, c); }
+void fwo_sincosf_array(const float *x, uint64_t n, float *s, float *c) {
+    for (uint64_t i = 0; i < n; i++) fw_sincosf(x[i], &s[i], &c[i]);
+}
 void fwo_quat_from_scaled_axis(const float v[3], float out[4]) {
     q4 q = q_from_scaled_axis(v3_make(v[0], v[1], v[2]));
     out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
@@ -281,8 +290,10 @@ void fwo_rand_vec3(const fw_rand_vec3 *r, float u_angle, float u_radius, float u
     if (r->spread > 0.0f) {
         float a = u_angle * 2.0f * FW_PI;
         float p = u_radius * r->spread;
-        float sp = sinf(p), cp = cosf(p);
-        v3 local = v3_make(sp * cosf(a), cp, sp * sinf(a));
+        float sp, cp, sa, ca;
+        fw_sincosf(p, &sp, &cp);
+        fw_sincosf(a, &sa, &ca);
+        v3 local = v3_make(sp * ca, cp, sp * sa);
         q4 arc = q_from_rotation_arc(v3_make(0.0f, 1.0f, 0.0f), v3_normalize_or_zero(dir));
         dir = q_mul_v3(arc, local);
     }
@@ -296,8 +307,10 @@ void fwo_generate_point(const fw_emission_settings *e, float u0, float u1, float
     v3 p = v3_make(0.0f, 0.0f, 0.0f);
     if (e->shape_kind == FW_SHAPE_SPHERE) {
         float u = u0 * 2.0f * FW_PI, v = u1 * FW_PI, r = u2; /* :23-25 */
-        float sv = sinf(v);
-        v3 unit = v3_make(sv * cosf(u), cosf(v), sv * sinf(u));
+        float su, cu, sv, cv;
+        fw_sincosf(u, &su, &cu);
+        fw_sincosf(v, &sv, &cv);
+        v3 unit = v3_make(sv * cu, cv, sv * su);
         p = v3_mul(v3_mul(unit, r), e->shape_radius); /* :30 */
     } else if (e->shape_kind == FW_SHAPE_CIRCLE) {
         float u = u0 * 2.0f * FW_PI, r = u1; /* :33 */
@@ -438,16 +451,47 @@ static int ray_frustum_local(float r0, float r1, float h, v3 o, v3 d, float max_
     *normal = bn;
     return 1;
 }
-int fwo_cast_ray(const fw_collider *c, uint32_t n, uint32_t filter_mask, const float origin[3],
-                 const float dir[3], float max_distance, float *distance, float normal[3],
-                 uint32_t *index) {
+/* TEST HELPER (not part of the restatement): conservative boxes that let the full-size collision
+ * parity tests finish in seconds. boxes[6i..6i+5] = min.xyz, max.xyz of collider i's bounding
+ * sphere, inflated far beyond any fp32 rounding of the exact tests below. A collider is skipped
+ * only when the box of the ray segment [o, o + d*max_distance] misses its box -- the exact test
+ * could not have reported a hit within max_distance -- so the result is the brute-force result
+ * (tests/test_oracle_golden.py compares the two on random scenes). Non-finite input never culls. */
+static void collider_cull_box(const fw_collider *c, float box[6]) {
+    float r;
+    if (c->kind == FW_COLLIDER_SPHERE) r = fabsf(c->half_extents[0]);
+    else if (c->kind == FW_COLLIDER_CUBOID)
+        r = sqrtf(c->half_extents[0] * c->half_extents[0] + c->half_extents[1] * c->half_extents[1] + c->half_extents[2] * c->half_extents[2]);
+    else r = sqrtf(c->half_extents[0] * c->half_extents[0] + c->half_extents[1] * c->half_extents[1]);
+    for (int a = 0; a < 3; a++) {
+        const float m = 1e-3f + 1e-3f * (fabsf(c->translation[a]) + r);
+        box[a] = c->translation[a] - r - m;
+        box[3 + a] = c->translation[a] + r + m;
+        if (!isfinite(box[a]) || !isfinite(box[3 + a])) { box[a] = -FLT_MAX; box[3 + a] = FLT_MAX; }
+    }
+}
+static int cast_ray_impl(const fw_collider *c, uint32_t n, const float *boxes, uint32_t filter_mask, const float origin[3],
+                         const float dir[3], float max_distance, float *distance, float normal[3],
+                         uint32_t *index) {
     int found = 0;
     float best = 0.0f;
     v3 best_n = v3_make(0.0f, 0.0f, 0.0f);
     uint32_t best_i = 0;
     v3 o = v3_make(origin[0], origin[1], origin[2]), d = v3_make(dir[0], dir[1], dir[2]);
+    float slo[3], shi[3];
+    int cull = boxes != NULL;
+    for (int a = 0; a < 3 && cull; a++) {
+        const float e = origin[a] + dir[a] * max_distance;
+        if (!isfinite(e) || !isfinite(origin[a])) cull = 0;
+        slo[a] = fminf(origin[a], e);
+        shi[a] = fmaxf(origin[a], e);
+    }
     for (uint32_t i = 0; i < n; i++) {
         if ((c[i].layers & filter_mask) == 0u) continue;
+        if (cull) {
+            const float *b = boxes + 6 * (size_t)i;
+            if (shi[0] < b[0] || slo[0] > b[3] || shi[1] < b[1] || slo[1] > b[4] || shi[2] < b[2] || slo[2] > b[5]) continue;
+        }
         q4 rot = {c[i].rotation[0], c[i].rotation[1], c[i].rotation[2], c[i].rotation[3]};
         q4 inv = q_conj(rot);
         v3 tr = v3_make(c[i].translation[0], c[i].translation[1], c[i].translation[2]);
@@ -478,12 +522,26 @@ int fwo_cast_ray(const fw_collider *c, uint32_t n, uint32_t filter_mask, const f
     if (index) *index = best_i;
     return 1;
 }
+int fwo_cast_ray(const fw_collider *c, uint32_t n, uint32_t filter_mask, const float origin[3],
+                 const float dir[3], float max_distance, float *distance, float normal[3],
+                 uint32_t *index) {
+    return cast_ray_impl(c, n, NULL, filter_mask, origin, dir, max_distance, distance, normal, index);
+}
+int fwo_cast_ray_culled(const fw_collider *c, uint32_t n, uint32_t filter_mask, const float origin[3],
+                        const float dir[3], float max_distance, float *distance, float normal[3],
+                        uint32_t *index) {
+    float *boxes = (float *)malloc(sizeof(float) * 6 * (n ? n : 1));
+    for (uint32_t i = 0; i < n; i++) collider_cull_box(&c[i], boxes + 6 * (size_t)i);
+    const int r = cast_ray_impl(c, n, boxes, filter_mask, origin, dir, max_distance, distance, normal, index);
+    free(boxes);
+    return r;
+}
 
 /* ref src/core.rs:744-800 particle_collision, line by line (including the
  * time-minus-distance subtraction at :786 and the undiminished delta at :766-775). */
-void fwo_particle_collision(const fw_collider *colliders, uint32_t n_colliders,
-                            const fw_collision_settings *cs, float pos_io[3], float vel_io[3],
-                            float delta, uint32_t *should_destroy_out) {
+static void particle_collision_impl(const fw_collider *colliders, uint32_t n_colliders, const float *boxes,
+                                    const fw_collision_settings *cs, float pos_io[3], float vel_io[3],
+                                    float delta, uint32_t *should_destroy_out) {
     v3 pos = v3_make(pos_io[0], pos_io[1], pos_io[2]);
     v3 vel = v3_make(vel_io[0], vel_io[1], vel_io[2]);
     float orig_delta = delta;
@@ -494,8 +552,8 @@ void fwo_particle_collision(const fw_collider *colliders, uint32_t n_colliders,
         float len = v3_length(vel);
         v3 dir = (isfinite(len) && len > 0.0f) ? v3_div(vel, len) : v3_make(0.0f, 1.0f, 0.0f);
         float o[3] = {pos.x, pos.y, pos.z}, d[3] = {dir.x, dir.y, dir.z}, nrm[3], distance;
-        if (fwo_cast_ray(colliders, n_colliders, cs->filter_mask, o, d, v3_length(vel) * delta,
-                         &distance, nrm, NULL)) {
+        if (cast_ray_impl(colliders, n_colliders, boxes, cs->filter_mask, o, d, v3_length(vel) * delta,
+                          &distance, nrm, NULL)) {
             v3 hit_normal = v3_make(nrm[0], nrm[1], nrm[2]);
             if (distance == 0.0f) {
                 v3 normal = hit_normal;
@@ -529,6 +587,11 @@ void fwo_particle_collision(const fw_collider *colliders, uint32_t n_colliders,
     pos_io[0] = pos.x; pos_io[1] = pos.y; pos_io[2] = pos.z;
     vel_io[0] = vel.x; vel_io[1] = vel.y; vel_io[2] = vel.z;
     *should_destroy_out = should_destroy;
+}
+void fwo_particle_collision(const fw_collider *colliders, uint32_t n_colliders,
+                            const fw_collision_settings *cs, float pos_io[3], float vel_io[3],
+                            float delta, uint32_t *should_destroy_out) {
+    particle_collision_impl(colliders, n_colliders, NULL, cs, pos_io, vel_io, delta, should_destroy_out);
 }
 
 /* ------------------------------------------------------------------ world model
@@ -573,6 +636,8 @@ struct fwo_world {
     size_t n_sp, cap_sp;
     fw_collider *colliders;
     uint32_t n_colliders;
+    float *cull_boxes; /* test helper, see collider_cull_box; NULL = brute force */
+    int cull;
 };
 
 static void pvec_push(pvec *v, particle p) {
@@ -602,7 +667,7 @@ static void spawner_free(spawner *s) {
 void fwo_destroy(fwo_world *w) {
     if (!w) return;
     for (size_t i = 0; i < w->n_sp; i++) spawner_free(w->sp[i]);
-    free(w->sp); free(w->colliders); free(w);
+    free(w->sp); free(w->colliders); free(w->cull_boxes); free(w);
 }
 static spawner *find_spawner(const fwo_world *w, uint32_t key) {
     for (size_t i = 0; i < w->n_sp; i++) if (w->sp[i]->key == key) return w->sp[i];
@@ -663,7 +728,15 @@ void fwo_set_colliders(fwo_world *w, const fw_collider *c, uint32_t n) {
     w->colliders = (fw_collider *)malloc(sizeof(*c) * (n ? n : 1));
     memcpy(w->colliders, c, sizeof(*c) * n);
     w->n_colliders = n;
+    free(w->cull_boxes);
+    w->cull_boxes = NULL;
+    if (w->cull) {
+        w->cull_boxes = (float *)malloc(sizeof(float) * 6 * (n ? n : 1));
+        for (uint32_t i = 0; i < n; i++) collider_cull_box(&c[i], w->cull_boxes + 6 * (size_t)i);
+    }
 }
+/* test helper: from the next fwo_set_colliders on, skip colliders whose box the ray segment misses */
+void fwo_set_cull(fwo_world *w, int on) { w->cull = on; }
 
 /* ref src/core.rs:288-302 ParticleSpawnerData::active */
 static int spawner_active(const spawner *s) {
@@ -812,7 +885,7 @@ static void update_spawner(const fwo_world *w, spawner *s, float dt) {
             uint32_t should_destroy = 0;
             if (ps->collision.enabled) { /* :608-617 */
                 float pp[3] = {pos.x, pos.y, pos.z}, vv[3] = {vel.x, vel.y, vel.z};
-                fwo_particle_collision(w->colliders, w->n_colliders, &ps->collision, pp, vv, dt, &should_destroy);
+                particle_collision_impl(w->colliders, w->n_colliders, w->cull_boxes, &ps->collision, pp, vv, dt, &should_destroy);
                 pos = v3_make(pp[0], pp[1], pp[2]);
                 vel = v3_make(vv[0], vv[1], vv[2]);
             } else { /* :619-623 */

@@ -7,7 +7,10 @@
  * library (bevy_firework_b200/csrc) never includes, links or calls anything in oracle/.
  *
  * It shares ONLY the POD settings structs of the public ABI header, so that the same settings
- * bytes can be handed to the oracle and to the CUDA path.
+ * bytes can be handed to the oracle and to the CUDA path, and include/fw_sincos.h: the sine / cosine
+ * is defined by the library in IEEE operations (a platform libm is not a specification) and both
+ * sides compile that one definition; its accuracy is pinned separately (tests/test_sincos.py,
+ * scripts/sincos_exhaustive.c: correctly rounded against an 80-bit libm for every finite float).
  *
  * PARITY STATUS
  *   pinned by the reference's own tests: compute_emission_count (src/core.rs:806-834) and
@@ -30,6 +33,10 @@ extern "C" {
 
 typedef struct fwo_world fwo_world;
 
+/* the library's sine / cosine (include/fw_sincos.h) as compiled into this oracle */
+void fwo_sincosf(float x, float *s, float *c);
+void fwo_sincosf_array(const float *x, uint64_t n, float *s, float *c);
+
 fwo_world *fwo_create(uint64_t seed);
 void fwo_destroy(fwo_world *w);
 
@@ -37,6 +44,10 @@ int fwo_spawner_reset(fwo_world *w, uint32_t key, const fw_particle_settings *ps
                       const fw_emission_settings *es, uint32_t n_emitters, uint32_t starts_enabled);
 int fwo_spawner_remove(fwo_world *w, uint32_t key);
 void fwo_set_colliders(fwo_world *w, const fw_collider *c, uint32_t n);
+/* TEST HELPER for the full-size collision scenes: skip (with conservative boxes) colliders the ray
+ * segment cannot reach; results equal the brute-force loop (checked in tests/test_oracle_golden.py).
+ * Off by default; the CPU baseline that bench.py times never turns it on. */
+void fwo_set_cull(fwo_world *w, int on);
 
 /* spawn_particles then update_particles; n_threads tasks-per-spawner pool for the update
  * (mirrors Query::par_iter_mut, src/core.rs:583-585); spawn is sequential (:377). */

@@ -26,7 +26,7 @@ def build(force: bool = False) -> str:
     """Compile the oracle with gcc (``oracle/Makefile``)."""
     if force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-        for f in ("fw_oracle.c", "fw_oracle.h")
+        for f in ("fw_oracle.c", "fw_oracle.h", "../include/firework_b200.h", "../include/fw_sincos.h")
     ):
         subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))
     return _LIB_PATH
@@ -66,10 +66,15 @@ def lib():
         "fwo_rand_vec3": (None, [P(_abi.fw_rand_vec3), f32, f32, f32, P(f32 * 3)]),
         "fwo_cast_ray": (C.c_int, [P(_abi.fw_collider), u32, u32, P(f32 * 3), P(f32 * 3), f32,
                                    P(f32), P(f32 * 3), P(u32)]),
+        "fwo_cast_ray_culled": (C.c_int, [P(_abi.fw_collider), u32, u32, P(f32 * 3), P(f32 * 3), f32,
+                                          P(f32), P(f32 * 3), P(u32)]),
+        "fwo_set_cull": (None, [vp, C.c_int]),
         "fwo_particle_collision": (None, [P(_abi.fw_collider), u32, P(_abi.fw_collision_settings),
                                           P(f32 * 3), P(f32 * 3), f32, P(u32)]),
         "fwo_quat_from_scaled_axis": (None, [P(f32 * 3), P(f32 * 4)]),
         "fwo_quat_mul": (None, [P(f32 * 4), P(f32 * 4), P(f32 * 4)]),
+        "fwo_sincosf": (None, [f32, P(f32), P(f32)]),
+        "fwo_sincosf_array": (None, [vp, u64, vp, vp]),
         "fwo_rem_euclid": (f32, [f32, f32]),
         "fwo_div_euclid": (f32, [f32, f32]),
     }
@@ -104,6 +109,18 @@ def philox4x32_10(ctr: Sequence[int], key: Sequence[int]):
     return tuple(o)
 
 
+def sincosf(x):
+    """include/fw_sincos.h as compiled into the oracle: scalar -> (sin, cos); float32 array -> two arrays"""
+    if np.ndim(x) == 0:
+        s, c = C.c_float(), C.c_float()
+        lib().fwo_sincosf(float(x), C.byref(s), C.byref(c))
+        return s.value, c.value
+    xs = np.ascontiguousarray(x, dtype=np.float32)
+    s, c = np.empty_like(xs), np.empty_like(xs)
+    lib().fwo_sincosf_array(xs.ctypes.data, xs.size, s.ctypes.data, c.ctypes.data)
+    return s, c
+
+
 def uniform(seed, spawner_key, emitter, serial, draw) -> float:
     return lib().fwo_uniform(seed, spawner_key, emitter, serial, draw)
 
@@ -127,12 +144,14 @@ def _colliders_array(colliders):
     return arr
 
 
-def cast_ray(colliders, origin, direction, max_distance, filter_mask=0xFFFFFFFF):
-    arr = _colliders_array(colliders)
+def cast_ray(colliders, origin, direction, max_distance, filter_mask=0xFFFFFFFF, culled=False):
+    """culled: through the test helper's conservative boxes (must equal the brute-force loop)"""
+    arr = colliders if isinstance(colliders, C.Array) else _colliders_array(colliders)
     o, d = (C.c_float * 3)(*origin), (C.c_float * 3)(*direction)
     dist, nrm, idx = C.c_float(), (C.c_float * 3)(), C.c_uint32()
-    hit = lib().fwo_cast_ray(arr, len(colliders), filter_mask, C.byref(o), C.byref(d), max_distance,
-                             C.byref(dist), C.byref(nrm), C.byref(idx))
+    fn = lib().fwo_cast_ray_culled if culled else lib().fwo_cast_ray
+    hit = fn(arr, len(colliders), filter_mask, C.byref(o), C.byref(d), max_distance,
+             C.byref(dist), C.byref(nrm), C.byref(idx))
     return (dist.value, tuple(nrm), idx.value) if hit else None
 
 
@@ -154,9 +173,13 @@ def frame_inputs_array(inputs):
 class OracleWorld:
     """The reference's schedule played on the CPU restatement."""
 
-    def __init__(self, seed: int = 0x00F12E00, n_threads: int = 1):
+    def __init__(self, seed: int = 0x00F12E00, n_threads: int = 1, cull: bool = False):
+        """cull: TEST HELPER for the full-size collision scenes (conservative boxes in front of the
+        brute-force ray loop; same results). Never used by the timed CPU baseline."""
         self._L = lib()
         self._w = self._L.fwo_create(seed)
+        if cull:
+            self._L.fwo_set_cull(self._w, 1)
         self.n_threads = n_threads
         self._n_types = {}
 

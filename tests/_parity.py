@@ -1,9 +1,8 @@
 """Shared helpers of the parity tests: drive the CPU oracle and the CUDA path with the same
 settings bytes and the same frame inputs, then compare ``ParticleData`` rows.
 
-Tolerances: counts are exact; every field whose value does not pass
-through sinf/cosf is compared bit-for-bit (``exact`` list); the rest must satisfy
-``abs(a-b) <= tol * max(abs(a), abs(b), 1)`` with tol = 1e-5 (north_star's bound).
+Bar: counts AND every field of every row are equal -- no tolerance anywhere (north_star allows
+1e-5 relative; the build does not need it).
 """
 from __future__ import annotations
 
@@ -11,33 +10,31 @@ import numpy as np
 
 from bevy_firework_b200._native import frame_input
 
-TOL = 1e-5
 ALL_FIELDS = ("position", "velocity", "rotation", "angular_velocity", "initial_scale", "scale", "age",
               "lifetime", "base_color", "emissive_color", "pbr")
 
 
-def close(a, b, tol=TOL):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
-    return np.abs(a - b) <= tol * np.maximum(np.maximum(np.abs(a), np.abs(b)), 1.0)
+def same_bits(g, w):
+    """IEEE equality (so -0 == +0) with NaNs required in the same places"""
+    g = np.asarray(g)
+    w = np.asarray(w)
+    if g.dtype.kind != "f":
+        return g == w
+    return (g == w) | (np.isnan(g) & np.isnan(w))
 
 
-def assert_rows_match(got, want, exact=(), tol=TOL, what=""):
+def assert_rows_match(got, want, what=""):
+    """every field of every ParticleData row equal, no tolerance: the kernels evaluate the
+    reference's expressions in the reference's order with IEEE operations only (-fmad=false; sine and
+    cosine from include/fw_sincos.h on both sides), so nothing may differ"""
     assert len(got) == len(want), f"{what}: count {len(got)} != oracle {len(want)}"
     for f in ALL_FIELDS:
         g, w = got[f], want[f]
-        if f in exact or f == "pbr":
-            bad = ~(g == w)
-            if bad.ndim > 1:
-                bad = bad.any(axis=1)
-            assert not bad.any(), (f"{what}: field {f} not bit-exact at {int(np.argmax(bad))}: "
-                                   f"{g[np.argmax(bad)]} vs {w[np.argmax(bad)]} ({int(bad.sum())} rows)")
-        else:
-            ok = close(g, w, tol)
-            if ok.ndim > 1:
-                ok = ok.all(axis=1)
-            assert ok.all(), (f"{what}: field {f} off at {int(np.argmin(ok))}: "
-                              f"{g[np.argmin(ok)]} vs {w[np.argmin(ok)]} ({int((~ok).sum())} rows)")
+        bad = ~same_bits(g, w)
+        if bad.ndim > 1:
+            bad = bad.any(axis=1)
+        assert not bad.any(), (f"{what}: field {f} differs at row {int(np.argmax(bad))}: "
+                               f"{g[np.argmax(bad)]} vs {w[np.argmax(bad)]} ({int(bad.sum())} of {len(g)} rows)")
 
 
 def reset_both(engine, world, key, spawner):

@@ -50,8 +50,7 @@ def test_zero_dt_and_varying_dt(engine, oracle):
         engine.frame(dt, [frame_input(1, (0.0, 0.1, 0.0))])
         w.frame(dt, [frame_input(1, (0.0, 0.1, 0.0))])
         assert engine.counts(1) == w.counts(1), f"frame {k} dt {dt}"
-    assert_rows_match(engine.read_particles(1, 0), w.read_particles(1, 0),
-                      exact=("age", "lifetime", "initial_scale", "scale", "base_color", "emissive_color"))
+    assert_rows_match(engine.read_particles(1, 0), w.read_particles(1, 0))
 
 
 def test_large_one_shot_burst(engine):
@@ -187,10 +186,8 @@ def test_c3_full_size_properties(oracle):
 def test_randomized_mixed_scene(engine, oracle, seed):
     """a seeded random scene replayed on both sides: spawners of every update variant in one
     context (FIFO, compacting, colliding, colliding + destroy), random shapes / curves / rates,
-    uneven dt, spawners reset and removed on the way. Counts every frame; at the end every field
-    that does not pass through sinf/cosf bit-exact for the streams without collisions, and the
-    north_star bound on >= 99.5 % of the rows of the colliding ones (a last-ulp spawn difference
-    can flip a grazing ray cast)."""
+    uneven dt, spawners reset and removed on the way. Counts every frame; at the end every field of
+    every row of every stream equal."""
     from bevy_firework_b200 import (EmissionShape, FireworkCurve, FireworkGradient, LinearRgba,
                                     ParticleCollisionSettings)
     from bevy_firework_b200.workloads import cuboid, sphere
@@ -268,17 +265,5 @@ def test_randomized_mixed_scene(engine, oracle, seed):
         w.frame(dt, inp)
         for key in spawners:
             assert engine.counts(key) == w.counts(key), f"frame {k} spawner {key} ({spawners[key][0]})"
-    exact = ("age", "lifetime", "initial_scale", "scale", "base_color", "emissive_color")
     for key, (kind, _) in spawners.items():
-        got, want = engine.read_particles(key, 0), w.read_particles(key, 0)
-        assert len(got) == len(want)
-        if kind in ("fifo", "compact"):
-            assert_rows_match(got, want, exact=exact, what=f"spawner {key} ({kind})")
-        elif len(got):
-            ok = np.ones(len(got), dtype=bool)
-            for f in ("position", "velocity"):
-                a, b = got[f].astype(np.float64), want[f].astype(np.float64)
-                ok &= (np.abs(a - b) <= 1e-4 * np.maximum(np.maximum(np.abs(a), np.abs(b)), 1.0)).all(axis=1)
-            assert ok.mean() >= 0.995, (key, kind, ok.mean())
-            for f in ("age", "lifetime", "initial_scale"):
-                assert (got[f] == want[f]).all(), (key, kind, f)
+        assert_rows_match(engine.read_particles(key, 0), w.read_particles(key, 0), what=f"spawner {key} ({kind})")

@@ -271,3 +271,30 @@ def test_cylinder_and_cone_ray_casts_known_answers(oracle):
     assert hit is not None and abs(hit[0] - 4.8) < 1e-6
     # the mirrored nappe above the apex is not part of the solid
     assert oracle.cast_ray(pyramid, (5.0, 1.5, 0.0), (-1.0, 0.0, 0.0), 10.0) is None
+
+
+def test_culled_ray_cast_equals_brute_force(oracle):
+    """the oracle's test helper (conservative boxes, used by the full-size collision scenes) returns
+    exactly what the brute-force loop over every collider returns: hit or not, distance, normal, index"""
+    import ctypes as C
+
+    from bevy_firework_b200 import _abi
+    from bevy_firework_b200.workloads import collision_scene_colliders, cone, cylinder, sphere
+
+    cols = list(collision_scene_colliders(64)) + [sphere(0.5, (1.0, 1.0, 1.0)), cylinder(0.6, 1.0, (-2.0, 1.0, 0.5)),
+                                                  cone(0.5, 1.2, (0.5, 0.6, -2.0))]
+    arr = (_abi.fw_collider * len(cols))(*cols)
+    rng = np.random.default_rng(5)
+    hits = 0
+    for _ in range(4000):
+        o = rng.uniform(-7, 7, 3) * (1.0, 0.4, 1.0) + (0.0, 1.0, 0.0)
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        md = float(rng.choice([0.05, 0.2, 1.0, 30.0]))
+        a = oracle.cast_ray(arr, o, d, md)
+        b = oracle.cast_ray(arr, o, d, md, culled=True)
+        assert a == b, (o, d, md, a, b)
+        hits += a is not None
+    assert hits > 500
+    inf = float("inf")
+    assert oracle.cast_ray(arr, (0, 5, 0), (0, -1, 0), inf) == oracle.cast_ray(arr, (0, 5, 0), (0, -1, 0), inf, culled=True)
