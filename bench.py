@@ -7,8 +7,9 @@
 A "step" is one frame of the hot path (fw_frame = plan + spawn + update kernels) over the whole
 workload at fixed dt = fl32(1/60). Default workload: C3 = examples/stress_test.rs settings,
 512 spawners x rate 19531 => ~10 M live particles PER GPU (1.6 GB of state, >> the 126 MB L2, so
-no L2 flush is needed between steps). With N > 1 every rank owns its own 512 spawners (sharded by
-spawner, no data-path collective): weak scaling.
+no L2 flush is needed between steps). With N > 1 the 512 spawners are split over the ranks (BASELINE
+config 3: shard by spawner, no data-path collective, strong scaling); the same run also measures every
+rank carrying all 512 (weak) and reports it beside the headline.
 
 One JSON line on rank 0 (see the contract in the task statement): value = whole-job particles/s
 with state resident in HBM; e2e = same metric through the C ABI with host input structs and a
@@ -254,12 +255,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=120.0,
                     help="--impl reference: bound of the whole CPU run in seconds (the sample shrinks for large --steps)")
-    ap.add_argument("--extract", action="store_true", help="also time the full instance-row extract (D2H)")
+    ap.add_argument("--no-extract", action="store_true", help="skip the e2e_extract leg (full instance-row extract, D2H)")
+    ap.add_argument("--blocks", type=int, default=10, help="timed blocks of --steps frames each; value = the median block")
+    ap.add_argument("--single-scaling", action="store_true", help="N > 1: do not also measure the other scaling mode")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernel by kernel instead of replaying frame graphs")
     ap.add_argument("--no-concurrent-spawn", action="store_true", help="run the spawn kernel before the update kernel")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: every rank runs the whole workload (default); strong: the workload's spawners are "
-                         "sharded over the ranks (BASELINE config 3: 10 M particles over 1..8 GPUs)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default): the workload's spawners are sharded over the ranks (BASELINE config 3: the "
+                         "10 M-particle scene over 1..8 GPUs); weak: every rank runs the whole workload. With N > 1 the "
+                         "other mode is measured too and reported beside the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -276,8 +280,9 @@ def main():
         line = {
             "impl": "reference", "metric": "particles updated/sec (fused step)", "value": v, "unit": "particles/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": label, "dt": "fl32(1/60)", "live_particles": live},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": label, "dt": "fl32(1/60)", "live_particles": live,
+                       "note": "one CPU workload on rank 0 whatever --gpus is"},
             "cpu_baseline": {"value": v, "unit": "particles/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} ({live} live particles), {args.steps} frames after {args.warmup} warm-up frames; "
                                        "C restatement of the reference loop (no Rust toolchain in the image), "
@@ -299,54 +304,109 @@ def main():
 
     from bevy_firework_b200._native import Engine
 
-    eng = Engine(device=local_rank, seed=W.SEED, profile=False, graphs=not args.no_graphs,
-                 concurrent_spawn=not args.no_concurrent_spawn)  # raises without the CUDA library
-    sc = Scene(eng, args.workload, rank, shard=(world, rank) if args.scaling == "strong" and world > 1 else None)
-    for _ in range(sc.fill_frames):  # reach the stationary live count (lifetime/dt + 2 frames)
-        sc.step()
-    eng.sync()
-    live = eng.total_live()
+    def make_engine():
+        return Engine(device=local_rank, seed=W.SEED, profile=False, graphs=not args.no_graphs,
+                      concurrent_spawn=not args.no_concurrent_spawn)  # raises without the CUDA library
 
-    def barrier():
-        eng.sync()
+    def barrier(e):
+        e.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    sampler = ClockSampler(local_rank)
-    # ---- device-resident throughput: K steps, CUDA events on the launching stream
-    for _ in range(args.warmup):
-        sc.step()
-    barrier()
-    eng.profile_reset()
-    sampler.start()
-    eng.event_record(0)
-    for _ in range(args.steps):
-        sc.step()
-    eng.event_record(1)
-    ms = eng.event_elapsed_ms(0, 1)
-    barrier()
-    prof, n_prof = eng.profile_sum()
-    updated = int(prof.particles_updated)
-    launches = int(prof.kernel_launches)
-    assert n_prof == args.steps, (n_prof, args.steps)
+    def reduce_max(vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def reduce_sum(vals):
+        if world == 1:
+            return [int(v) for v in vals]
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [int(v) for v in t.tolist()]
+
+    def gather_ranks(v):
+        if world == 1:
+            return [v]
+        out = [None] * world
+        dist.all_gather_object(out, v)
+        return out
+
+    sampler = ClockSampler(local_rank, period_s=0.02)
+    sampler.start()  # before the warm-up: the timed region of a 20-step run is a few milliseconds
+
+    def timed_blocks(e, scene, n_blocks):
+        """n_blocks x [barrier + synchronize | EXACTLY `steps` frames between two CUDA events on the
+        launching stream | barrier + synchronize]; per block: max over ranks of the time, sum over
+        ranks of the particles. -> (block ms (max over ranks), particles per block, this rank's ms)"""
+        out_ms, out_upd, mine = [], [], []
+        for _ in range(n_blocks):
+            barrier(e)
+            e.profile_reset()
+            e.event_record(0)
+            for _ in range(args.steps):
+                scene.step()
+            e.event_record(1)
+            ms_b = e.event_elapsed_ms(0, 1)
+            barrier(e)
+            prof_b, n_b = e.profile_sum()
+            assert n_b == args.steps, (n_b, args.steps)
+            out_ms.append(ms_b)
+            out_upd.append(int(prof_b.particles_updated))
+            mine.append(ms_b)
+        launches_b = int(e.profile_sum()[0].kernel_launches)
+        ms_all_b = reduce_max(out_ms)
+        upd_all_b = reduce_sum(out_upd)
+        return ms_all_b, upd_all_b, mine, launches_b
+
+    def run_scene(scaling):
+        e = make_engine()
+        scene = Scene(e, args.workload, rank, shard=(world, rank) if scaling == "strong" and world > 1 else None)
+        for _ in range(scene.fill_frames):  # reach the stationary live count (lifetime/dt + 2 frames)
+            scene.step()
+        e.sync()
+        for _ in range(args.warmup):
+            scene.step()
+        ms_b, upd_b, mine, launches_b = timed_blocks(e, scene, args.blocks)
+        k = int(np.argsort(ms_b)[len(ms_b) // 2])  # the median block
+        return e, scene, {"ms": ms_b[k], "updated": upd_b[k], "block_ms_per_step": [m / args.steps for m in ms_b],
+                          "rank_ms_per_step": gather_ranks(float(np.median(mine)) / args.steps), "launches": launches_b}
+
+    # ---- device-resident throughput. N > 1: BASELINE config 3 is the 10 M / 512-spawner scene SPLIT
+    # over the GPUs (spawner i -> GPU i // (512 / N)), so that is the headline ("strong"); the same
+    # run also measures every GPU carrying the whole scene ("weak") and reports it beside it.
+    eng, sc, main_t = run_scene(args.scaling)
+    live = eng.total_live()
+    # what one update moves per particle of this workload's streams (fw_stream_layout_get: fields the
+    # library proved constant for the stream are not stored), and the kernel instantiation that runs
+    first_key = sc.spawners[0][0] if sc.spawners else sc.live_bursts[-1]
+    lay = eng.stream_layout(first_key, 0)
+    layout_bytes = int(lay.bytes_read + lay.bytes_written)
+    layout_kernel = "fw::update_kernel<%s,%d,%s>" % ("true" if lay.variant & 1 else "false", 1 if lay.variant & 2 else 0,
+                                                     "true" if lay.variant & 4 else "false")
+    layout_info = {"variant": int(lay.variant), "flags": int(lay.flags), "bytes_read": int(lay.bytes_read),
+                   "bytes_written": int(lay.bytes_written), "bytes_count_pass": int(lay.bytes_count_pass),
+                   "generic_bytes_per_particle": ALGO_BYTES_PER_PARTICLE}
 
     # ---- per-kernel durations: K more steps launched kernel by kernel with CUDA events around
     # every kernel (events recorded inside a replayed graph carry no timestamps)
+    barrier(eng)
     eng.profile_reset()
     eng.set_profiling(True)
     for _ in range(args.steps):
         sc.step()
-    barrier()
+    barrier(eng)
     kprof, kn = eng.profile_sum()
     eng.set_profiling(False)
-    clocks = sampler.stop()
     assert kprof.timed_frames == args.steps, (kprof.timed_frames, args.steps)
 
     # ---- end to end through the C ABI: host inputs in, per-frame results (counts, AABBs) out
     keys = [k for k, *_ in sc.spawners]
     eng.profile_reset()
-    barrier()
+    barrier(eng)
     t0 = time.perf_counter()
     eng.event_record(2)
     e2e_steps = max(10, min(args.steps, 200))
@@ -363,50 +423,73 @@ def main():
     updated_e2e = int(prof2.particles_updated)
     h2d = int(prof2.h2d_bytes // max(n2, 1))
     d2h = int(prof2.d2h_bytes // max(n2, 1))  # the frame's own state readback serves fw_counts_all / fw_read_aabb
+    ms_e2e_all = reduce_max([ms_e2e])[0]
+    updated_e2e_all = reduce_sum([updated_e2e])[0]
 
+    # ---- end to end INCLUDING the render hand-off: every frame also brings the 64-byte
+    # ParticleInstance rows of all live particles (what extract_firework_components consumes,
+    # reference src/render.rs:439-461) into pinned host memory. PCIe-bound.
     extract = None
-    if args.extract:
-        cap = eng.total_live() + 4 * 512 * 400
+    if not args.no_extract:
+        x_steps = 10
+        cap = eng.total_live() + 4 * max(len(sc.spawners), 151) * 2048
         host = torch.empty((cap, 16), dtype=torch.float32, pin_memory=True)
         eng.extract_instances(host.data_ptr(), cap)
-        barrier()
+        barrier(eng)
+        upd0 = eng.profile_sum()[0].particles_updated
         t0 = time.perf_counter()
         rows = 0
-        upd0 = eng.profile_sum()[0].particles_updated
-        for _ in range(10):
+        for _ in range(x_steps):
             sc.step()
             rows = eng.extract_instances(host.data_ptr(), cap)
         dt_x = time.perf_counter() - t0
         upd1 = eng.profile_sum()[0].particles_updated
-        extract = {"value": (upd1 - upd0) / dt_x, "unit": "particles/s", "d2h_bytes_per_step": rows * 64,
-                   "ms_per_step": dt_x / 10 * 1e3}
+        dt_x_all = reduce_max([dt_x])[0]
+        upd_x_all = reduce_sum([upd1 - upd0])[0]
+        extract = {"value": upd_x_all / dt_x_all, "unit": "particles/s", "d2h_bytes_per_step": rows * 64,
+                   "ms_per_step": dt_x_all / x_steps * 1e3, "steps": x_steps,
+                   "pcie_gbs": rows * 64 / (dt_x / x_steps) / 1e9,
+                   "what": "fw_frame + fw_extract_instances: all live 64-byte ParticleInstance rows into pinned host memory every step"}
+        del host
 
-    # ---- reduce over ranks: time = max, work = sum
-    if world > 1:
-        tt = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ww = torch.tensor([updated, updated_e2e, live, launches], dtype=torch.float64, device="cuda")
-        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
-        ms_all, ms_e2e_all = tt.tolist()
-        updated_all, updated_e2e_all, live_all, launches_all = [int(x) for x in ww.tolist()]
-    else:
-        ms_all, ms_e2e_all, updated_all, updated_e2e_all, live_all, launches_all = ms, ms_e2e, updated, updated_e2e, live, launches
+    live_all, launches_all = reduce_sum([live, main_t["launches"]])
+    clocks_now = sampler.stop()
+
+    # ---- weak scaling beside the strong headline (N > 1), same run
+    other = None
+    if world > 1 and not args.single_scaling:
+        eng.close()
+        other_kind = "weak" if args.scaling == "strong" else "strong"
+        eng2, sc2, ot = run_scene(other_kind)
+        live2 = reduce_sum([eng2.total_live()])[0]
+        other = {"scaling": other_kind, "value": ot["updated"] / (ot["ms"] * 1e-3), "unit": "particles/s",
+                 "ms_per_step": ot["ms"] / args.steps, "live_particles": live2,
+                 "block_ms_per_step": ot["block_ms_per_step"], "rank_ms_per_step": ot["rank_ms_per_step"]}
+        eng2.close()
+        eng = None
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         upd_kernel_ms = kprof.update_ms / args.steps
         per_launch_particles = int(kprof.particles_updated) / args.steps
-        kernel_name, algo_bytes = KERNEL_OF.get(args.workload, ("fw::update_kernel<false,0>", ALGO_BYTES_PER_PARTICLE))
+        kernel_name, algo_bytes = layout_kernel, layout_bytes
         achieved = algo_bytes * per_launch_particles / (upd_kernel_ms * 1e-3) / 1e9
+        ms_all, updated_all = main_t["ms"], main_t["updated"]
         line = {
             "metric": "particles updated/sec (fused step)", "value": updated_all / (ms_all * 1e-3), "unit": "particles/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": sc.label, "dt": "fl32(1/60)", "live_particles": live_all, "seed": hex(W.SEED),
-                       "streams_per_gpu": len(sc.spawners) or 151, "parallelism": f"shard-by-spawner x{world}",
-                       "l2": "state per GPU (1.6 GB at C3) is larger than the 126 MB L2; no flush between steps",
+                       "streams_per_gpu": len(sc.spawners) or 151,
+                       "parallelism": (f"shard-by-spawner x{world}: the workload's spawners split over the GPUs" if args.scaling == "strong"
+                                       else f"shard-by-spawner x{world}: every GPU carries the whole workload"),
+                       "l2": "state per GPU (0.8 GB at C3 on one GPU) is larger than the 126 MB L2; no flush between steps"
+                             + ("; split over 8 GPUs the 100 MB per GPU fit in L2 -- said here, not hidden" if world > 1 and args.scaling == "strong" else ""),
                        "fill_frames": sc.fill_frames, "cuda_graphs": not args.no_graphs,
-                       "concurrent_spawn": not args.no_concurrent_spawn},
+                       "concurrent_spawn": not args.no_concurrent_spawn,
+                       "timing": f"{args.blocks} blocks of exactly {args.steps} steps, each bracketed by barrier + synchronize and timed with "
+                                 "CUDA events on the launching stream, max over ranks per block; value = the median block"},
+            "block_ms_per_step": main_t["block_ms_per_step"], "rank_ms_per_step": main_t["rank_ms_per_step"],
             "e2e": {"value": updated_e2e_all / (ms_e2e_all * 1e-3), "unit": "particles/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "what": "fw_frame with host input structs + fw_counts_all/fw_read_aabb (sync + D2H) every step"},
@@ -416,18 +499,28 @@ def main():
                          "kernel": kernel_name,
                          "algorithmic_bytes_per_launch": algo_bytes * per_launch_particles,
                          "algorithmic_bytes_per_particle": algo_bytes,
-                         "particles_per_launch": per_launch_particles, "kernel_ms": upd_kernel_ms,
+                         "particles_per_launch": per_launch_particles, "kernel_ms": upd_kernel_ms, "layout": layout_info,
                          "peak_source": peak_src,
+                         "generic_layout": {"algorithmic_bytes_per_particle": ALGO_BYTES_PER_PARTICLE,
+                                            "note": "SURVEY 8d's figure for a stream where every ParticleData field varies; this "
+                                                    "workload's streams keep only the fields that can vary (fw_stream_layout_get)"},
                          "how": f"CUDA events around the kernel, mean of {args.steps} launches in a second timed "
                                 "region of the same run (kernel-by-kernel launches)"},
             "kernel_ms": {"plan": kprof.plan_ms / args.steps, "spawn": kprof.spawn_ms / args.steps,
                           "update": upd_kernel_ms, "frame": kprof.total_ms / args.steps},
-            "clocks": clocks,
+            "clocks": clocks_now,
         }
         if extract:
             line["e2e_extract"] = extract
+        if other:
+            line[other["scaling"]] = other
+        if world > 1:
+            line["reference_arm_note"] = "the --impl reference arm times ONE CPU workload on rank 0 whatever N is"
         if world == 1 and not args.no_cpu_baseline:
-            eng.close()
+            if eng is not None:
+                eng.close()
+                eng = None
+            line["parity_checked"] = parity_check(args.workload, local_rank)
             v, cms, clive, _, _ = run_cpu(args.workload, args.cpu_steps, 1, cores)
             # Bevy's default compute pool does not get every core: 4-thread figure too
             v4 = run_cpu(args.workload, max(2, args.cpu_steps // 2), 1, 4)[0] if cores > 4 else v
@@ -437,10 +530,44 @@ def main():
                           f"frames, {cms:.1f} ms/frame; C restatement of the reference loop (oracle/fw_oracle.c), "
                           f"one task per spawner on {cores} threads, sequential spawn"}
         print(json.dumps(line), flush=True)
+    if eng is not None:
+        eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def parity_check(workload: str, device: int):
+    """the bench workload's first spawners replayed on the CUDA path and on the CPU oracle, every
+    field of every row compared for equality (the tests do this for the whole workload)"""
+    from bevy_firework_b200._native import Engine
+    from oracle import oracle as O
+
+    class Backend(O.OracleWorld, OracleBackendTag):
+        pass
+
+    n = {"c5": 2, "c4": 0}.get(workload, 4)
+    if n == 0:
+        return None
+    e = Engine(device=device, seed=W.SEED)
+    b = Backend(seed=W.SEED, n_threads=4, cull=workload == "c5")
+    se, sb = Scene(e, workload, 0, max_spawners=n), Scene(b, workload, 0, max_spawners=n)
+    frames = {"c5": 130}.get(workload, 70)
+    for _ in range(frames):
+        se.step()
+        sb.step()
+    rows = 0
+    ok = True
+    for key, *_ in se.spawners:
+        g, w = e.read_particles(key, 0), b.read_particles(key, 0)
+        ok = ok and len(g) == len(w) and all((g[f] == w[f]).all() for f in g.dtype.names)
+        rows += len(g)
+    e.close()
+    b.close()
+    if not ok:
+        raise SystemExit("bench.py: the CUDA path and the CPU oracle disagree on the bench workload")
+    return {"spawners": n, "frames": frames, "rows": rows, "equal": True}
 
 
 if __name__ == "__main__":

@@ -154,6 +154,11 @@ class fw_frame_profile(C.Structure):
                 ("h2d_bytes", u64), ("d2h_bytes", u64)]
 
 
+class fw_stream_layout(C.Structure):
+    _fields_ = [("variant", u32), ("flags", u32), ("bytes_read", u32), ("bytes_written", u32),
+                ("bytes_count_pass", u32), ("capacity", u32)]
+
+
 class fw_gather_handle(C.Structure):
     _fields_ = [("ipc", C.c_uint8 * 64), ("address", u64), ("bytes", u64), ("device", C.c_int32), ("pid", C.c_int32)]
 
@@ -179,6 +184,9 @@ def particle_instance_dtype():
     ])
 
 
+FW_LAYOUT_COMPACTING, FW_LAYOUT_COLLIDES, FW_LAYOUT_ROTATES = 1, 2, 4
+FW_STORE_BASE_COLOR, FW_STORE_EMISSIVE_COLOR, FW_STORE_SCALE, FW_STORE_LIFETIME = 1, 2, 4, 8
+
 # every exported symbol of the C ABI: name -> (restype, argtypes)
 P = C.POINTER
 _ctx = C.c_void_p
@@ -202,6 +210,7 @@ EXPORTS = {
     "fw_counts_all": (C.c_int, [_ctx, P(u32), P(u32), P(u32), u32, P(u32)]),
     "fw_spawner_status_get": (C.c_int, [_ctx, u32, P(fw_spawner_status)]),
     "fw_spawner_mark_finished_notified": (C.c_int, [_ctx, u32]),
+    "fw_stream_layout_get": (C.c_int, [_ctx, u32, u32, P(fw_stream_layout)]),
     "fw_read_particles": (C.c_int, [_ctx, u32, u32, C.c_void_p, u64, P(u64)]),
     "fw_write_particles": (C.c_int, [_ctx, u32, u32, C.c_void_p, u64]),
     "fw_read_instances": (C.c_int, [_ctx, u32, u32, C.c_void_p, u64, P(u64)]),
@@ -233,4 +242,5 @@ POD_TYPES = {
     "fw_particle_instance": fw_particle_instance, "fw_collider": fw_collider,
     "fw_config": fw_config, "fw_spawner_status": fw_spawner_status,
     "fw_frame_profile": fw_frame_profile, "fw_gather_handle": fw_gather_handle,
+    "fw_stream_layout": fw_stream_layout,
 }

@@ -167,6 +167,11 @@ class Engine:
         self._check(self._L.fw_spawner_status_get(self._ctx, key, C.byref(st)))
         return st
 
+    def stream_layout(self, key, type_=0) -> _abi.fw_stream_layout:
+        out = _abi.fw_stream_layout()
+        self._check(self._L.fw_stream_layout_get(self._ctx, key, type_, C.byref(out)))
+        return out
+
     def mark_finished_notified(self, key):
         self._check(self._L.fw_spawner_mark_finished_notified(self._ctx, key))
 

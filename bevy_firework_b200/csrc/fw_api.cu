@@ -55,7 +55,10 @@ struct Stream {
     Block destroyed; // particles destroyed by the last update (capture_destroyed types only)
     uint32_t n_lea = 0;     // nested emitters targeting this type
     bool injected = false;  // state was written by the host: nested emitters may catch up at once
+    bool accounted = false; // counted in tiles_needed / variant_streams (a failed reset may stop before that)
     uint32_t variant = kFifo;
+    uint32_t flags = kStoreAll; // kStore*: which derived / constant fields the stream keeps per particle
+    DevParticleSettings dev;    // device form of ps incl. the constants of the packs it does not keep
     uint64_t n_hi = 0;        // host-side upper bound of the live count
     uint64_t born_frame = 0;  // readbacks of older frames do not describe this stream
     fw_particle_settings ps;
@@ -182,9 +185,16 @@ struct fw_context {
     unsigned long long *d_nested_serial = nullptr; // per device emitter
     NestedOut *d_nested_out = nullptr;
     uint32_t nested_out_cap = 0;
-    int grids[kNumVariants] = {0, 0, 0, 0};
+    int grids[kNumVariants] = {0};
     int team_size = 0; // CTAs per team of the compacting update kernels (= SM count)
-    uint32_t variant_streams[kNumVariants] = {0, 0, 0, 0};
+    uint32_t variant_streams[kNumVariants] = {0};
+    float prev_dt = 0.f; // dt of the previous frame (nested emission reads ages that frame advanced)
+    // per-frame scratch of fw_frame, kept between frames so that a steady-state frame allocates nothing
+    std::vector<SpawnCmd> fr_cmds[kMaxPhases];
+    std::vector<NestedCmd> fr_nested[kMaxPhases];
+    std::vector<uint32_t> fr_spawn_per_slot;
+    std::vector<uint64_t> fr_add;
+    std::vector<SpawnerInput> fr_inputs;
 
     // profile accumulators
     fw_frame_profile prof_last{};
@@ -282,7 +292,7 @@ inline void compute_emission_count(float time_passed_in_cycle, float last_emissi
     next_last_emission = next_last_emission_percent * cycle_duration;
 }
 
-inline bool is_fifo(uint32_t v) { return v == kFifo || v == kFifoCollide; }
+inline bool is_fifo(uint32_t v) { return variant_is_fifo(v); }
 // A compacting ring compacts out of place inside its own ring (fw_kernels.cu: usable_capacity,
 // live_first): it may only be half full, and after a frame its live particles start at
 // head + count (a FIFO ring's: at head + dead).
@@ -310,13 +320,14 @@ inline uint32_t round_capacity(uint64_t want) {
     return (uint32_t)r;
 }
 inline size_t block_bytes(uint32_t cap, uint32_t n_lea) { return (size_t)cap * (kBytesPerSlot + 4u * n_lea); }
-inline StreamDesc block_desc(const Block &b, uint32_t variant, const Block *destroyed = nullptr) {
+inline StreamDesc block_desc(const Block &b, uint32_t variant, uint32_t flags, const Block *destroyed = nullptr) {
     StreamDesc d{};
     d.base = (uint8_t *)b.base;
     d.destroyed_base = destroyed ? (uint8_t *)destroyed->base : nullptr;
     d.capacity = b.capacity;
     d.variant = variant;
     d.n_lea = b.n_lea;
+    d.flags = flags;
     return d;
 }
 
@@ -420,14 +431,93 @@ int ensure_tiles(fw_context *ctx) {
     return FW_OK;
 }
 
-uint32_t pick_variant(const fw_particle_settings &ps) {
+inline uint32_t f32_bits(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+// glam Quat::mul_quat with the identity on the left, in the kernels' fp32 operation order (this file
+// is compiled -fmad=false / -ffp-contract=off like them): what src/core.rs:645-647 does to a rotation
+// when the angular velocity is zero
+inline void qmul_identity(const float b[4], float out[4]) {
+    const float ax = 0.0f, ay = 0.0f, az = 0.0f, aw = 1.0f;
+    out[0] = aw * b[0] + ax * b[3] + ay * b[2] - az * b[1];
+    out[1] = aw * b[1] - ax * b[2] + ay * b[3] + az * b[0];
+    out[2] = aw * b[2] + ax * b[1] - ay * b[0] + az * b[3];
+    out[3] = aw * b[3] - ax * b[0] - ay * b[1] - az * b[2];
+}
+// What can be PROVED about a particle type at reset, and therefore need not be stored per particle
+// (layout: fw_internal.h). Every proof is about the reference's arithmetic on these exact settings:
+//  * FIFO (deaths are a prefix of the Vec): every particle gets the same lifetime (ages are monotone
+//    in Vec order) and nothing else can kill a particle;
+//  * static (no kVarRot): every emitter of the type draws angular velocity = direction * 0 = +-0
+//    (RandVec3 with magnitude [0, 0], finite direction / spread) and angular_acceleration is +0 with a
+//    finite drag: src/core.rs:648-650 then gives +0 after the first update, for ever (dt is finite
+//    and >= 0, fw_frame checks), from_scaled_axis(0) is the identity (:645-647) and the rotation is
+//    q = identity * initial_rotation, which must be the same for all emitters and a fixed point;
+//  * constant base / emissive gradient, constant scale curve: :602-605, 652-655 return colors[0] /
+//    initial_scale * values[0] on every frame (a particle is always updated in the frame it spawns);
+//  * a handler for destroyed particles wants the previous frame's colours: such types keep everything.
+void stream_proofs(const fw_particle_settings &ps, uint32_t type, const fw_emission_settings *es, uint32_t n_emitters,
+                   uint32_t &variant, uint32_t &flags, DevParticleSettings &dev) {
     const bool collide = ps.collision.enabled != 0;
-    // deaths are a prefix of the Vec iff every particle has the same lifetime (ages are
-    // monotone in Vec order) and nothing else can kill a particle
-    const bool fifo = (ps.lifetime.min == ps.lifetime.max) && !(collide && ps.collision.destroy_on_collision) &&
-                      !ps.capture_destroyed;
-    if (fifo) return collide ? kFifoCollide : kFifo;
-    return collide ? kCompactCollide : kCompact;
+    const bool same_lifetime = ps.lifetime.min == ps.lifetime.max;
+    const bool fifo = same_lifetime && !(collide && ps.collision.destroy_on_collision) && !ps.capture_destroyed;
+    variant = (fifo ? 0u : (uint32_t)kVarCompact) | (collide ? (uint32_t)kVarCollide : 0u);
+    flags = 0;
+    if (ps.base_color.kind != FW_CURVE_CONSTANT) flags |= kStoreBase;
+    if (ps.emissive_color.kind != FW_CURVE_CONSTANT) flags |= kStoreEmi;
+    if (ps.scale_curve.kind != FW_CURVE_CONSTANT) flags |= kStoreScale;
+    if (!same_lifetime) flags |= kStoreLife;
+    dev.const_lifetime = 0.5f * (ps.lifetime.max - ps.lifetime.min) + ps.lifetime.min; // RandF32::generate with max == min
+    bool is_static = f32_bits(ps.angular_acceleration[0]) == 0u && f32_bits(ps.angular_acceleration[1]) == 0u &&
+                     f32_bits(ps.angular_acceleration[2]) == 0u && std::isfinite(ps.angular_drag);
+    bool have_rotation = false;
+    float rot[4] = {0.f, 0.f, 0.f, 1.f};
+    for (uint32_t i = 0; i < n_emitters && is_static; i++) {
+        if (es[i].particle_index != type) continue;
+        const fw_rand_vec3 &av = es[i].initial_angular_velocity;
+        is_static = av.magnitude.min == 0.0f && av.magnitude.max == 0.0f && std::isfinite(av.direction[0]) &&
+                    std::isfinite(av.direction[1]) && std::isfinite(av.direction[2]) && std::isfinite(av.spread);
+        float r1[4], r2[4];
+        qmul_identity(es[i].initial_rotation, r1);
+        qmul_identity(r1, r2);
+        for (int k = 0; k < 4; k++) is_static = is_static && std::isfinite(r1[k]) && f32_bits(r1[k]) == f32_bits(r2[k]);
+        if (have_rotation) {
+            for (int k = 0; k < 4; k++) is_static = is_static && f32_bits(r1[k]) == f32_bits(rot[k]);
+        } else {
+            memcpy(rot, r1, sizeof(rot));
+            have_rotation = true;
+        }
+    }
+    if (!have_rotation) is_static = false; // no emitter feeds the type: nothing to prove from
+    if (ps.capture_destroyed) {
+        is_static = false;
+        flags = kStoreAll;
+    }
+    memcpy(dev.const_rotation, rot, sizeof(rot));
+    if (!is_static) variant |= kVarRot;
+}
+// host-written rows (fw_write_particles) against the proofs: which flags / variant bits they break
+void check_rows_against_proofs(const Stream &st, const fw_particle_data *in, uint64_t n, uint32_t &variant, uint32_t &flags) {
+    variant = st.variant;
+    flags = st.flags;
+    const DevParticleSettings &dev = st.dev;
+    for (uint64_t i = 0; i < n; i++) {
+        const fw_particle_data &r = in[i];
+        if (!variant_rotates(variant)) {
+            bool ok = r.angular_velocity[0] == 0.0f && r.angular_velocity[1] == 0.0f && r.angular_velocity[2] == 0.0f;
+            for (int k = 0; k < 4; k++) ok = ok && f32_bits(r.rotation[k]) == f32_bits(dev.const_rotation[k]);
+            if (!ok) variant |= kVarRot;
+        }
+        if (!(flags & kStoreBase) && memcmp(r.base_color, &dev.base_color.colors[0], 16) != 0) flags |= kStoreBase;
+        if (!(flags & kStoreEmi) && memcmp(r.emissive_color, &dev.emissive_color.colors[0], 16) != 0) flags |= kStoreEmi;
+        if (!(flags & kStoreScale) && f32_bits(r.scale) != f32_bits(r.initial_scale * dev.scale_curve.values[0])) flags |= kStoreScale;
+        const bool same_life = f32_bits(r.lifetime) == f32_bits(dev.const_lifetime);
+        if (!(flags & kStoreLife) && !same_life) flags |= kStoreLife;
+        // FIFO: every lifetime is the type's constant and ages do not increase along the Vec
+        if (variant_is_fifo(variant) && (!same_life || (i != 0 && r.age > in[i - 1].age))) variant |= kVarCompact;
+    }
 }
 
 void fill_dev_settings(const fw_particle_settings &ps, DevParticleSettings &d) {
@@ -451,6 +541,7 @@ void fill_dev_settings(const fw_particle_settings &ps, DevParticleSettings &d) {
     d.collision = ps.collision;
     d.lifetime = ps.lifetime;
     d.initial_scale = ps.initial_scale;
+    d.const_rotation[3] = 1.0f; // (stream_proofs fills the constants)
 }
 
 int validate_curve(fw_context *ctx, uint32_t kind, uint32_t n, const float *times, const char *what) {
@@ -486,8 +577,11 @@ uint64_t estimate_capacity(const Spawner &sp, uint32_t type) {
 
 void free_stream(fw_context *ctx, Stream &st) {
     if (!st.block.base) return; // never got a slot / block (failed reset)
-    ctx->tiles_needed -= max_tiles_of(st.block.capacity);
-    ctx->variant_streams[st.variant]--;
+    if (st.accounted) {
+        ctx->tiles_needed -= max_tiles_of(st.block.capacity);
+        ctx->variant_streams[st.variant]--;
+        st.accounted = false;
+    }
     release_block(ctx, st.block);
     release_block(ctx, st.destroyed);
     StreamDesc zero{};
@@ -507,7 +601,7 @@ void free_spawner_resources(fw_context *ctx, Spawner &sp) {
 }
 
 int upload_desc(fw_context *ctx, const Stream &st) {
-    const StreamDesc d = block_desc(st.block, st.variant, st.destroyed.base ? &st.destroyed : nullptr);
+    const StreamDesc d = block_desc(st.block, st.variant, st.flags, st.destroyed.base ? &st.destroyed : nullptr);
     ctx->h_descs[st.slot] = d;
     CU(ctx, cudaMemcpyAsync(ctx->d_descs + st.slot, &d, sizeof(d), cudaMemcpyHostToDevice, ctx->stream));
     return FW_OK;
@@ -585,7 +679,7 @@ int grow_stream(fw_context *ctx, Stream &st, uint64_t need) {
     }
     // unwrap the ring into the start of the new block
     ctx->readback_is_current = false;
-    CU(ctx, launch_ring_copy(block_desc(st.block, st.variant), first, live, block_desc(nb, st.variant), ctx->stream));
+    CU(ctx, launch_ring_copy(block_desc(st.block, st.variant, st.flags), first, live, block_desc(nb, st.variant, st.flags), ctx->stream));
     StreamState ns = s;
     const StreamState inj = injected_state(st.variant, live, ncap);
     ns.head = inj.head;
@@ -728,7 +822,7 @@ uint32_t fw_abi_sizeof(const char *name) {
     if (!strcmp(name, #T)) return (uint32_t)sizeof(T);
     SZ(fw_rand_f32) SZ(fw_rand_vec3) SZ(fw_curve_f32) SZ(fw_gradient) SZ(fw_collision_settings)
     SZ(fw_particle_settings) SZ(fw_emission_settings) SZ(fw_spawner_frame_input) SZ(fw_particle_data)
-    SZ(fw_particle_instance) SZ(fw_collider) SZ(fw_config) SZ(fw_spawner_status) SZ(fw_frame_profile) SZ(fw_gather_handle)
+    SZ(fw_particle_instance) SZ(fw_collider) SZ(fw_config) SZ(fw_spawner_status) SZ(fw_frame_profile) SZ(fw_gather_handle) SZ(fw_stream_layout)
 #undef SZ
     return 0;
 }
@@ -932,10 +1026,12 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
             Stream &st = sp->streams[t];
             st.type = t;
             st.ps = ps[t];
-            st.variant = pick_variant(ps[t]);
+            fill_dev_settings(ps[t], st.dev);
+            stream_proofs(ps[t], t, es, n_emitters, st.variant, st.flags, st.dev);
             st.n_hi = 0;
             st.born_frame = ctx->frame_no + 1;
             st.injected = false;
+            st.accounted = false;
             st.n_lea = 0;
             for (uint32_t i = 0; i < n_emitters; i++)
                 if (es[i].mode == FW_MODE_NESTED && es[i].target_particle_type == t) st.n_lea++;
@@ -955,13 +1051,12 @@ int fw_spawner_reset(fw_context *ctx, uint32_t key, const fw_particle_settings *
                 ctx->free_slots.push_back(st.slot);
                 return rc;
             }
-            if (ps[t].capture_destroyed && (rc = alloc_block(ctx, st.block.capacity, st.n_lea, st.destroyed))) return rc;
             ctx->tiles_needed += max_tiles_of(st.block.capacity);
             ctx->variant_streams[st.variant]++;
+            st.accounted = true;
             ctx->slot_owner[st.slot] = &st;
-            DevParticleSettings ds;
-            fill_dev_settings(ps[t], ds);
-            CU(ctx, cudaMemcpyAsync(ctx->d_settings + st.slot, &ds, sizeof(ds), cudaMemcpyHostToDevice, ctx->stream));
+            if (ps[t].capture_destroyed && (rc = alloc_block(ctx, st.block.capacity, st.n_lea, st.destroyed))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->d_settings + st.slot, &st.dev, sizeof(st.dev), cudaMemcpyHostToDevice, ctx->stream));
             CU(ctx, cudaMemsetAsync(cur_states(ctx) + st.slot, 0, sizeof(StreamState), ctx->stream));
             if ((rc = upload_desc(ctx, st))) return rc;
         }
@@ -1278,6 +1373,9 @@ int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) 
 int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, uint32_t n_inputs) {
     ENTER(ctx);
     if (n_inputs && !inputs) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_frame: null inputs");
+    // dt is Res<Time>::delta_secs() (src/core.rs:413,594): a Duration as f32, finite and >= 0. The
+    // per-stream constants of static streams rely on that (fw_internal.h), so anything else is refused.
+    if (!std::isfinite(dt) || std::signbit(dt)) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_frame: dt = %g (must be finite and >= 0)", (double)dt);
     for (uint32_t k = 0; k < n_inputs; k++) {
         Spawner *sp = find(ctx, inputs[k].spawner_key);
         if (!sp) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_frame: unknown spawner %u", inputs[k].spawner_key);
@@ -1304,11 +1402,18 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     // are walked in order; its k-th Nested emitter closes phase k (see PhaseInfo).
     const uint32_t n_phases = ctx->n_phases;
     const uint32_t n_slots = ctx->n_slots;
-    std::vector<SpawnCmd> cmds[kMaxPhases];
-    std::vector<NestedCmd> nested[kMaxPhases];
-    std::vector<uint32_t> spawn_per_slot((size_t)n_phases * std::max(1u, n_slots), 0u); // [phase][slot]
+    // (scratch kept in the context: a steady-state frame allocates nothing)
+    std::vector<SpawnCmd> *cmds = ctx->fr_cmds;
+    std::vector<NestedCmd> *nested = ctx->fr_nested;
+    for (uint32_t p = 0; p < kMaxPhases; p++) {
+        cmds[p].clear();
+        nested[p].clear();
+    }
+    std::vector<uint32_t> &spawn_per_slot = ctx->fr_spawn_per_slot; // [phase][slot]
+    spawn_per_slot.assign((size_t)n_phases * std::max(1u, n_slots), 0u);
     uint64_t phase_total[kMaxPhases] = {0};
-    std::vector<SpawnerInput> sinputs;
+    std::vector<SpawnerInput> &sinputs = ctx->fr_inputs;
+    sinputs.clear();
     for (auto &spp : ctx->spawners) {
         Spawner &sp = *spp;
         if (!spawner_active(sp, true)) continue; // :378 (a nested emitter without parents emits nothing anyway)
@@ -1381,7 +1486,11 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     // charged an upper bound (parents x per-parent cap; the count kernel enforces the cap and
     // raises an error flag if the reference would have emitted more). Bounds first, the exact
     // device state only if a bound does not fit.
-    std::vector<uint64_t> add(std::max(1u, n_slots));
+    std::vector<uint64_t> &add = ctx->fr_add;
+    add.assign(std::max(1u, n_slots), 0);
+    // a parent's emission count covers the age it gained in the PREVIOUS frame's update
+    // (compute_emission_count runs before this frame's update, src/core.rs:490-500)
+    const float dt_bound = std::fmax(dt, ctx->prev_dt);
     auto plan_bounds = [&]() {
         std::fill(add.begin(), add.end(), 0);
         uint64_t scratch = 0;
@@ -1392,7 +1501,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
                 const fw_emission_settings &es = ctx->h_emitters[c.emitter_idx];
                 const float life_min = std::fmin(parent->ps.lifetime.min, parent->ps.lifetime.max);
                 const double span = std::fmax((double)es.offset_end - (double)es.offset_start, 1e-9);
-                double per = life_min > 0.f ? std::floor((double)es.count * ((double)dt / life_min) / span) * 2.0 + 4.0
+                double per = life_min > 0.f ? std::floor((double)es.count * ((double)dt_bound / life_min) / span) * 2.0 + 4.0
                                             : std::ceil((double)es.count) + 4.0;
                 if (parent->injected) per = std::fmax(per, std::ceil((double)es.count) + 4.0);
                 per = std::fmin(std::fmax(per, 1.0), 1048576.0);
@@ -1486,10 +1595,13 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     // the spawn kernel also gives its new particles their first update, so it needs no ordering
     // against the update kernel (which then only covers older particles) and runs on a forked
     // branch. Timed (profiling) frames stay sequential so that kernels are timed in isolation.
-    const bool step_in_spawn = derive && ctx->concurrent_spawn && !ctx->profiling &&
-                               ctx->variant_streams[kFifo] + ctx->variant_streams[kFifoCollide] > 0 &&
-                               ctx->variant_streams[kCompact] == 0 && ctx->variant_streams[kCompactCollide] == 0;
-    const int spawn_collides = ctx->variant_streams[kFifoCollide] > 0 ? (ctx->colliders_revolved ? 2 : 1) : 0;
+    uint32_t n_fifo = 0, n_compacting = 0, n_fifo_collide = 0;
+    for (uint32_t v = 0; v < kNumVariants; v++) {
+        (variant_is_fifo(v) ? n_fifo : n_compacting) += ctx->variant_streams[v];
+        if (variant_is_fifo(v) && variant_collides(v)) n_fifo_collide += ctx->variant_streams[v];
+    }
+    const bool step_in_spawn = derive && ctx->concurrent_spawn && !ctx->profiling && n_fifo > 0 && n_compacting == 0;
+    const int spawn_collides = n_fifo_collide > 0 ? (ctx->colliders_revolved ? 2 : 1) : 0;
     h->step_in_spawn = step_in_spawn ? 1u : 0u;
     if (derive) {
         uint32_t *hp = (uint32_t *)(fs.host + off_prefix);
@@ -1620,8 +1732,9 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
             launches++;
         }
         if (prof) CU(ctx, cudaEventRecord(fs.ev[2], ctx->stream));
-        if (ctx->variant_streams[kCompact]) { // death counts + per-stream prefixes for the compacting update (timed with it)
-            CU(ctx, launch_count_scan(t, f, kCompact, n_slots, ctx->stream));
+        for (uint32_t v : {(uint32_t)kCompact, (uint32_t)kCompact | (uint32_t)kVarRot}) {
+            if (!ctx->variant_streams[v]) continue; // death counts + per-stream prefixes for the compacting update (timed with it)
+            CU(ctx, launch_count_scan(t, f, v, n_slots, ctx->stream));
             launches += 2;
         }
         for (uint32_t v = 0; v < kNumVariants; v++) {
@@ -1693,6 +1806,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     ctx->snapshot_valid = false;
     ctx->readback_is_current = true;
     ctx->frame_no++;
+    ctx->prev_dt = dt;
     fs.in_flight = true;
     fs.frame = ctx->frame_no;
     fs.profiled = prof;
@@ -1786,6 +1900,28 @@ int fw_spawner_mark_finished_notified(fw_context *ctx, uint32_t key) {
     return FW_OK;
 }
 
+int fw_stream_layout_get(fw_context *ctx, uint32_t key, uint32_t type, fw_stream_layout *out) {
+    ENTER(ctx);
+    Spawner *sp = find(ctx, key);
+    if (!sp || type >= sp->streams.size() || !out) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_stream_layout_get: unknown spawner %u / type %u", key, type);
+    const Stream &st = sp->streams[type];
+    static_assert(FW_LAYOUT_COMPACTING == kVarCompact && FW_LAYOUT_COLLIDES == kVarCollide && FW_LAYOUT_ROTATES == kVarRot, "variant bits");
+    static_assert(FW_STORE_BASE_COLOR == kStoreBase && FW_STORE_EMISSIVE_COLOR == kStoreEmi && FW_STORE_SCALE == kStoreScale &&
+                      FW_STORE_LIFETIME == kStoreLife, "flag bits");
+    const bool rot = variant_rotates(st.variant), compact = !variant_is_fifo(st.variant), life = (st.flags & kStoreLife) != 0;
+    out->variant = st.variant;
+    out->flags = st.flags;
+    // position + age, velocity (+ angular_velocity.x | initial_scale): always; rotation 16, angular
+    // velocity y,z 8, (lifetime, initial_scale) 8 for a rotating stream; (lifetime, age) 8 when a static
+    // stream's lifetime varies
+    out->bytes_read = 32u + (rot ? 32u : (life ? 8u : 0u));
+    out->bytes_written = 32u + (rot ? 24u + (compact ? 8u : 0u) : (life ? 8u : 0u)) + ((st.flags & kStoreBase) ? 16u : 0u) +
+                         ((st.flags & kStoreEmi) ? 16u : 0u) + ((st.flags & kStoreScale) ? 4u : 0u) + (compact ? 4u * st.n_lea : 0u);
+    out->bytes_count_pass = (compact && !variant_collides(st.variant)) ? (rot ? 24u : (life ? 8u : 16u)) : 0u;
+    out->capacity = st.block.capacity;
+    return FW_OK;
+}
+
 int fw_read_particles(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_data *out, uint64_t cap, uint64_t *n) {
     ENTER(ctx);
     Spawner *sp = find(ctx, key);
@@ -1800,7 +1936,8 @@ int fw_read_particles(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_
     if (!live) return FW_OK;
     if ((rc = ensure_stage(ctx, (size_t)live * sizeof(fw_particle_data)))) return rc;
     // pbr is a copy of the type's setting (src/core.rs:462)
-    CU(ctx, launch_gather_particles((uint8_t *)st.block.base, st.block.capacity, first, live, st.ps.pbr, (fw_particle_data *)ctx->d_stage, ctx->stream));
+    CU(ctx, launch_gather_particles(block_desc(st.block, st.variant, st.flags), ctx->d_settings + st.slot, first, live, st.ps.pbr,
+                                    (fw_particle_data *)ctx->d_stage, ctx->stream));
     CU(ctx, cudaMemcpyAsync(out, ctx->d_stage, (size_t)live * sizeof(fw_particle_data), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, sync_all(ctx));
     return FW_OK;
@@ -1815,16 +1952,17 @@ int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_pa
     Stream &st = sp->streams[type];
     int rc = refresh_exact(ctx);
     if (rc) return rc;
-    // The FIFO variant relies on "deaths are a prefix of the Vec": every lifetime equals the
-    // type's constant lifetime and ages do not increase along the Vec. Host-written state that
-    // breaks this moves the stream to the compacting variant for good.
-    if (is_fifo(st.variant)) {
-        bool ok = true;
-        for (uint64_t i = 0; i < n && ok; i++)
-            ok = in[i].lifetime == st.ps.lifetime.min && (i == 0 || !(in[i].age > in[i - 1].age));
-        if (!ok) {
+    // What the stream does not keep per particle was proved at reset from its settings (stream_proofs);
+    // host-written rows that break a proof -- a lifetime other than the type's constant or ages that
+    // increase along the Vec (FIFO: deaths are a prefix), a rotation / angular velocity / colour / scale
+    // other than the constant -- turn that part of the state on for good.
+    {
+        uint32_t nv, nf;
+        check_rows_against_proofs(st, in, n, nv, nf);
+        if (nv != st.variant || nf != st.flags) {
             ctx->variant_streams[st.variant]--;
-            st.variant = st.variant == kFifoCollide ? kCompactCollide : kCompact;
+            st.variant = nv;
+            st.flags = nf;
             ctx->variant_streams[st.variant]++;
             topo_changed(ctx);
             if ((rc = upload_desc(ctx, st))) return rc;
@@ -1839,7 +1977,7 @@ int fw_write_particles(fw_context *ctx, uint32_t key, uint32_t type, const fw_pa
     if (n) {
         if ((rc = ensure_stage(ctx, (size_t)n * sizeof(fw_particle_data)))) return rc;
         CU(ctx, cudaMemcpyAsync(ctx->d_stage, in, (size_t)n * sizeof(fw_particle_data), cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, launch_scatter_particles(block_desc(st.block, st.variant), (uint32_t)n, (const fw_particle_data *)ctx->d_stage, ctx->stream));
+        CU(ctx, launch_scatter_particles(block_desc(st.block, st.variant, st.flags), (uint32_t)n, (const fw_particle_data *)ctx->d_stage, ctx->stream));
     }
     const StreamState ns = injected_state(st.variant, (uint32_t)n, st.block.capacity);
     CU(ctx, cudaMemcpyAsync(cur_states(ctx) + st.slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, ctx->stream));
@@ -1870,6 +2008,7 @@ int fw_read_instances(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_
     DeviceTables t{};
     t.descs = ctx->d_descs;
     t.states = cur_states(ctx);
+    t.settings = ctx->d_settings;
     CU(ctx, launch_pack_instances(t, st.slot, st.slot + 1, (float4 *)(ctx->d_stage + hdr), live, (unsigned long long *)ctx->d_stage, ctx->stream));
     CU(ctx, cudaMemcpyAsync(out, ctx->d_stage + hdr, (size_t)live * 64, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, sync_all(ctx));
@@ -1890,7 +2029,8 @@ int fw_read_destroyed(fw_context *ctx, uint32_t key, uint32_t type, fw_particle_
     if (dead > cap || (dead && !out)) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_read_destroyed: %u particles, room for %llu", dead, (unsigned long long)cap);
     if (!dead) return FW_OK;
     if ((rc = ensure_stage(ctx, (size_t)dead * sizeof(fw_particle_data)))) return rc;
-    CU(ctx, launch_gather_particles((uint8_t *)st.destroyed.base, st.destroyed.capacity, 0, dead, st.ps.pbr, (fw_particle_data *)ctx->d_stage, ctx->stream));
+    CU(ctx, launch_gather_particles(block_desc(st.destroyed, st.variant, st.flags), ctx->d_settings + st.slot, 0, dead, st.ps.pbr,
+                                    (fw_particle_data *)ctx->d_stage, ctx->stream));
     CU(ctx, cudaMemcpyAsync(out, ctx->d_stage, (size_t)dead * sizeof(fw_particle_data), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, sync_all(ctx));
     return FW_OK;
@@ -1934,6 +2074,7 @@ int fw_pack_instances_device(fw_context *ctx, void *device_dst, uint64_t cap_row
     DeviceTables t{};
     t.descs = ctx->d_descs;
     t.states = cur_states(ctx);
+    t.settings = ctx->d_settings;
     CU(ctx, launch_pack_instances(t, 0, ctx->n_slots, (float4 *)device_dst, cap_rows, ctx->d_pack, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->h_pack, ctx->d_pack, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, sync_all(ctx));
@@ -2062,6 +2203,7 @@ int fw_gather_instances(fw_context *ctx) {
     DeviceTables t{};
     t.descs = ctx->d_descs;
     t.states = cur_states(ctx);
+    t.settings = ctx->d_settings;
     PackDst dst{};
     dst.n = g.n_ranks;
     for (uint32_t r = 0; r < g.n_ranks; r++)

@@ -3,20 +3,32 @@
 //
 // Device data layout. One *stream* = one (spawner, particle type) vector
 // `data.particles[i]` (reference src/core.rs:274). A stream owns one device block of
-// `capacity` particle slots holding eight structure-of-arrays packs, laid out so that the
-// update kernel moves exactly the algorithmic bytes of the reference's per-particle step
-// (64 B read + 92 B written) with 16/8/4-byte fully coalesced accesses:
+// `capacity` particle slots holding eight structure-of-arrays packs. Which packs a frame touches
+// depends on what fw_spawner_reset could PROVE about the stream (StreamDesc::flags, the kVarRot bit
+// of its variant); a field that is provably the same for every particle of the stream, for ever, is
+// a per-stream constant in DevParticleSettings and is neither loaded nor stored:
 //
-//   pack  offset      type    contents                       update reads  update writes
-//   m0    0           float4  position.xyz, age                   16            16
-//   m1    16*cap      float4  rotation (x,y,z,w)                  16            16
-//   m2    32*cap      float4  velocity.xyz, angular_velocity.x    16            16
-//   m3    48*cap      float2  angular_velocity.y, .z               8             8
-//   k     56*cap      float2  lifetime, initial_scale              8             -  (constants)
-//   o0    64*cap      float4  base_color                           -            16
-//   o1    80*cap      float4  emissive_color                       -            16
-//   o2    96*cap      float   scale                                -             4
-//                                                         total   64            92   = 156 B
+//   pack  offset   type    contents                                       update reads  writes
+//   m0    0        float4  position.xyz, age                                   16         16
+//   m2    32*cap   float4  velocity.xyz, w                                     16         16
+//                          w = angular_velocity.x (rotating stream) | initial_scale (static one)
+//   m1    16*cap   float4  rotation (x,y,z,w)             rotating streams     16         16
+//   m3    48*cap   float2  angular_velocity.y, .z         rotating streams      8          8
+//   k     56*cap   float2  rotating: lifetime, initial_scale                    8          - (moved by compaction)
+//                          static + kStoreLife: lifetime, copy of age          (8)        (8)
+//   o0    64*cap   float4  base_color                     kStoreBase            -         16
+//   o1    80*cap   float4  emissive_color                 kStoreEmi             -         16
+//   o2    96*cap   float   scale                          kStoreScale           -          4
+//
+//   generic stream (everything varies)          64 B read + 92 B written = 156 B  
+//   examples/stress_test.rs (C2, C3; no angular motion, constant emissive / scale curve / lifetime):
+//                                               32 B read + 48 B written =  80 B
+//
+// "Static" = no angular motion can ever occur (every emitter of the type draws a zero angular
+// velocity, angular_acceleration is +0): rotation stays at the fixed point of
+// `from_scaled_axis(0) * initial_rotation`, angular velocity at +0 (src/core.rs:645-650 evaluated on
+// those inputs). Constant gradients / scale curve: src/core.rs:602-605,652-655 return the same value
+// every frame. Host-written state (fw_write_particles) that breaks a proof turns the flag on.
 //
 // (An earlier layout kept the 64-byte ParticleInstance row of reference src/render.rs:95-103
 // resident as AoS; ncu showed DRAM fetching the whole 64-byte row to read its 32-byte state
@@ -25,8 +37,9 @@
 //
 // Each stream is a ring: logical particle i (the reference's Vec index) lives in slot
 // (first + i) mod capacity, first = live_first(): head + dead for a FIFO ring, head + count for a
-// compacting ring (which writes its survivors behind the particles a frame reads). Order inside the ring == the reference's Vec order (survivors keep
-// their order, spawns are appended), so no per-particle serial is stored.
+// compacting ring (which writes its survivors behind the particles a frame reads). Order inside the
+// ring == the reference's Vec order (survivors keep their order, spawns are appended), so no
+// per-particle serial is stored.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -42,15 +55,31 @@ constexpr int kTile = FW_TILE; // particles per update tile == threads per CTA
 constexpr int kUpdateThreads = FW_TILE;
 constexpr uint32_t kBytesPerSlot = 100;
 
-// variants of the update kernel
+// variants of the update kernel = template instantiations, one launch and one tile table each.
+// bit 0: compacting (else FIFO: constant lifetime, no destroy-on-collision -- deaths are a prefix of
+//        the Vec; compacting = stable compaction out of place inside the ring, deaths precounted or,
+//        with collisions, found by decoupled look-back)
+// bit 1: sweeps its particles against the colliders
+// bit 2: rotating (rotation / angular velocity are per-particle state; else per-stream constants)
 enum Variant : uint32_t {
-    kFifo = 0,    // constant lifetime, no destroy-on-collision: deaths are a prefix of the Vec
-    kCompact = 1, // anything else: stable compaction, out of place inside the ring (precounted deaths;
-                  // with collisions: decoupled look-back)
+    kFifo = 0,
+    kCompact = 1,
     kFifoCollide = 2,
     kCompactCollide = 3,
-    kNumVariants = 4
+    kVarCompact = 1,
+    kVarCollide = 2,
+    kVarRot = 4,
+    kNumVariants = 8
 };
+__host__ __device__ inline bool variant_is_fifo(uint32_t v) { return (v & kVarCompact) == 0u; }
+__host__ __device__ inline bool variant_collides(uint32_t v) { return (v & kVarCollide) != 0u; }
+__host__ __device__ inline bool variant_rotates(uint32_t v) { return (v & kVarRot) != 0u; }
+// StreamDesc::flags: which derived / constant fields are per-particle state of this stream
+constexpr uint32_t kStoreBase = 1u;  // base_color varies (gradient not constant, or host-written)
+constexpr uint32_t kStoreEmi = 2u;   // emissive_color varies
+constexpr uint32_t kStoreScale = 4u; // scale != initial_scale * constant
+constexpr uint32_t kStoreLife = 8u;  // lifetime varies (static streams only; rotating ones always keep it in k)
+constexpr uint32_t kStoreAll = 15u;
 
 // device forms of fw_curve_f32 / fw_gradient with 16-byte aligned tables
 struct alignas(16) DevCurve {
@@ -78,7 +107,10 @@ struct alignas(16) DevParticleSettings {
     // spawn-only
     fw_rand_f32 lifetime;
     fw_rand_f32 initial_scale;
-    uint32_t pad[3];
+    // per-stream constants standing in for packs the stream does not keep (see the layout above)
+    float const_lifetime;    // lifetime.generate() when min == max
+    uint32_t pad[2];
+    float const_rotation[4]; // fixed point of from_scaled_axis(0) * initial_rotation
 };
 static_assert(sizeof(DevParticleSettings) % 16 == 0, "bulk copy needs a 16-byte multiple");
 
@@ -92,7 +124,7 @@ struct StreamDesc { // written by the host when a stream is created / grown / re
     uint32_t capacity;       // multiple of 256; 0 = slot unused
     uint32_t variant;
     uint32_t n_lea;          // last_emitted_age arrays (one per nested emitter targeting this type)
-    uint32_t pad;
+    uint32_t flags;          // kStore*
 };
 // ParticleData.last_emitted_age[i] of reference src/core.rs:320, kept only for the emitters that
 // read it (nested emitters whose target is this particle type): float[capacity] each, behind
@@ -235,9 +267,9 @@ struct PlanOut { // device, per frame; lives in front of the stream states of th
     uint32_t tile_base[kNumVariants]; // start of each variant inside the look-back array
     uint32_t error_flags;
     uint32_t total_update; // particles entering the update this frame
-    uint32_t pad[6];
+    uint32_t pad[14];
 };
-static_assert(sizeof(PlanOut) == 64, "state buffer layout: [PlanOut (64 B)][StreamState x slots]");
+static_assert(sizeof(PlanOut) == 128, "state buffer layout: [PlanOut (128 B)][StreamState x slots]");
 
 struct DeviceTables {
     const StreamDesc *descs;
@@ -311,7 +343,7 @@ cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uin
 // revolved: the collider set contains cylinders / cones (selects the kernel build that can test them)
 cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, int team_size, bool revolved,
                           cudaStream_t s);
-// compaction without collisions: per-tile death counts and their per-stream exclusive prefixes (before launch_update)
+// compaction without collisions (variants kCompact, kCompact | kVarRot): per-tile death counts and their per-stream exclusive prefixes (before launch_update)
 cudaError_t launch_count_scan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, uint32_t n_slots, cudaStream_t s);
 cudaError_t update_grid_size(int device, int *grids /*[kNumVariants]*/, int *team_size);
 // live ParticleInstance rows of the streams [slot_begin, slot_end) -> contiguous 64-byte rows
@@ -321,8 +353,9 @@ cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, ui
                                   uint64_t cap_rows, unsigned long long *n_rows_and_offsets, cudaStream_t s);
 cudaError_t launch_gather_signal(const GatherPeers &p, uint32_t which, unsigned long long epoch, const unsigned long long *rows_src,
                                  unsigned long long timeout_ns, cudaStream_t s);
-// one stream <-> fw_particle_data rows (host mirror / fw_write_particles)
-cudaError_t launch_gather_particles(uint8_t *base, uint32_t capacity, uint32_t first, uint32_t n, uint32_t pbr,
+// one stream <-> fw_particle_data rows (host mirror / fw_write_particles); d.base may be the stream's
+// destroyed block; ps = the stream's device settings (constants of the packs it does not keep)
+cudaError_t launch_gather_particles(const StreamDesc &d, const DevParticleSettings *ps, uint32_t first, uint32_t n, uint32_t pbr,
                                     fw_particle_data *dst, cudaStream_t s);
 cudaError_t launch_scatter_particles(const StreamDesc &d, uint32_t n, const fw_particle_data *src, cudaStream_t s);
 // include/fw_sincos.h evaluated on the device (parity hook)

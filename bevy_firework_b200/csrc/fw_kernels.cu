@@ -26,6 +26,11 @@
 // 0.320 ms, 5 CTAs/SM 0.261 ms, 6 CTAs/SM (40 regs, spills) 0.275 ms.
 #define FW_MINB 5
 #endif
+#ifndef FW_MINB_STATIC
+// static FIFO streams (32 B read + 48 B written per particle): half the bytes in flight per thread,
+// so more resident threads are asked for
+#define FW_MINB_STATIC 6
+#endif
 #ifndef FW_MINB_COMPACT
 #define FW_MINB_COMPACT 4 // 64 registers; C3r (precounted path): 4 CTAs/SM 0.412 ms, 5 (48 regs, spills) 0.421 ms, 6 0.468 ms
 #endif
@@ -64,7 +69,7 @@ __device__ __forceinline__ void st_pack(T *p, T v) {
 }
 
 __device__ __forceinline__ uint32_t wrap(uint32_t x, uint32_t cap) { return x >= cap ? x - cap : x; }
-__device__ __forceinline__ bool is_fifo(uint32_t variant) { return variant == kFifo || variant == kFifoCollide; }
+__device__ __forceinline__ bool is_fifo(uint32_t variant) { return variant_is_fifo(variant); }
 // A compacting ring compacts OUT OF PLACE inside its own ring: frame f reads [head, head + n) and
 // writes the survivors behind it, to [head + n, ...), so it may only ever be half full. After the
 // frame its live particles start at head + count (a FIFO ring's: at head + dead).
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(DeviceTables t, FrameDeviceI
             }
             if (threadIdx.x == 0) {
                 prefix[n_slots] = carry; // sentinel: total tiles of the variant
-                if ((v == kCompact || v == kCompactCollide) && base_total + carry > t.lookback_capacity)
+                if (!variant_is_fifo(v) && base_total + carry > t.lookback_capacity)
                     atomicOr(&t.plan->error_flags, kErrLookback);
             }
         }
@@ -200,24 +205,63 @@ __device__ __forceinline__ Derived derive_state(const StreamState &old, const St
 // One new particle: the shared body of reference src/core.rs:437-469 (Global: origin = the
 // spawner transform, inherited velocity = parent_velocity) and :506-544 (Nested: origin = the
 // parent particle). Draws 0..11 in the reference's draw order.
-struct ParticleRegs { // one particle in the pack layout
-    float4 m0, m1, m2;
-    float2 m3, k;
-    float4 o0, o1;
-    float o2;
+struct ParticleRegs { // one particle, every field of ParticleData (src/core.rs:305-321)
+    V3 pos, vel, av;
+    Q4 rot;
+    float age, lifetime, iscale, scale;
+    float4 c0, c1;
 };
+// ---- one particle <-> the packs its stream keeps (layout: fw_internal.h)
 __device__ __forceinline__ void store_particle(const StreamDesc &d, uint32_t slot, const ParticleRegs &p, bool init_lea) {
     const StreamArrays a = stream_arrays(d.base, d.capacity);
-    a.m0[slot] = p.m0;
-    a.m1[slot] = p.m1;
-    a.m2[slot] = p.m2;
-    a.m3[slot] = p.m3;
-    if (init_lea) a.k[slot] = p.k; // (also: constants are only written at spawn)
-    a.o0[slot] = p.o0;
-    a.o1[slot] = p.o1;
-    a.o2[slot] = p.o2;
+    const bool rot = variant_rotates(d.variant);
+    a.m0[slot] = make_float4(p.pos.x, p.pos.y, p.pos.z, p.age);
+    a.m2[slot] = make_float4(p.vel.x, p.vel.y, p.vel.z, rot ? p.av.x : p.iscale);
+    if (rot) {
+        a.m1[slot] = make_float4(p.rot.x, p.rot.y, p.rot.z, p.rot.w);
+        a.m3[slot] = make_float2(p.av.y, p.av.z);
+        a.k[slot] = make_float2(p.lifetime, p.iscale);
+    } else if (d.flags & kStoreLife) {
+        a.k[slot] = make_float2(p.lifetime, p.age);
+    }
+    if (d.flags & kStoreBase) a.o0[slot] = p.c0;
+    if (d.flags & kStoreEmi) a.o1[slot] = p.c1;
+    if (d.flags & kStoreScale) a.o2[slot] = p.scale;
     if (init_lea)
         for (uint32_t j = 0; j < d.n_lea; j++) lea_array(d.base, d.capacity, j)[slot] = kF32Min; // :467
+}
+__device__ __forceinline__ float load_lifetime(const StreamDesc &d, const StreamArrays &a, const DevParticleSettings &ps, uint32_t slot) {
+    return (variant_rotates(d.variant) || (d.flags & kStoreLife)) ? a.k[slot].x : ps.const_lifetime;
+}
+__device__ __forceinline__ Q4 load_rotation(const StreamDesc &d, const StreamArrays &a, const DevParticleSettings &ps, uint32_t slot) {
+    if (variant_rotates(d.variant)) {
+        const float4 r = a.m1[slot];
+        return Q4{r.x, r.y, r.z, r.w};
+    }
+    return Q4{ps.const_rotation[0], ps.const_rotation[1], ps.const_rotation[2], ps.const_rotation[3]};
+}
+__device__ __forceinline__ ParticleRegs load_particle(const StreamDesc &d, const DevParticleSettings &ps, uint32_t slot) {
+    const StreamArrays a = stream_arrays(d.base, d.capacity);
+    ParticleRegs p;
+    const float4 A = a.m0[slot], V = a.m2[slot];
+    p.pos = v3(A.x, A.y, A.z);
+    p.age = A.w;
+    p.vel = v3(V.x, V.y, V.z);
+    p.rot = load_rotation(d, a, ps, slot);
+    if (variant_rotates(d.variant)) {
+        const float2 W = a.m3[slot], K = a.k[slot];
+        p.av = v3(V.w, W.x, W.y);
+        p.lifetime = K.x;
+        p.iscale = K.y;
+    } else {
+        p.av = v3(0.0f, 0.0f, 0.0f);
+        p.iscale = V.w;
+        p.lifetime = (d.flags & kStoreLife) ? a.k[slot].x : ps.const_lifetime;
+    }
+    p.c0 = (d.flags & kStoreBase) ? a.o0[slot] : ps.base_color.colors[0];
+    p.c1 = (d.flags & kStoreEmi) ? a.o1[slot] : ps.emissive_color.colors[0];
+    p.scale = (d.flags & kStoreScale) ? a.o2[slot] : p.iscale * ps.scale_curve.values[0]; // :602-605 with a constant curve
+    return p;
 }
 __device__ __forceinline__ ParticleRegs make_particle(const DeviceTables &t, const fw_emission_settings &es, const DevParticleSettings &ps,
                                                       V3 origin_translation, Q4 origin_rotation,
@@ -276,14 +320,16 @@ __device__ __forceinline__ ParticleRegs make_particle(const DeviceTables &t, con
     const V3 av = rand_vec3(es.initial_angular_velocity, u_ang_angle, u_ang_radius, u_ang_mag);
 
     ParticleRegs p;
-    p.m0 = make_float4(position.x, position.y, position.z, 0.0f); // age = 0
-    p.m1 = make_float4(es.initial_rotation[0], es.initial_rotation[1], es.initial_rotation[2], es.initial_rotation[3]);
-    p.m2 = make_float4(velocity.x, velocity.y, velocity.z, av.x);
-    p.m3 = make_float2(av.y, av.z);
-    p.k = make_float2(lifetime, initial_scale);
-    p.o0 = sample_gradient(ps.base_color, 0.0f);     // :460
-    p.o1 = sample_gradient(ps.emissive_color, 0.0f); // :461
-    p.o2 = initial_scale;                            // scale = initial_scale (:457)
+    p.pos = position;
+    p.age = 0.0f;
+    p.rot = Q4{es.initial_rotation[0], es.initial_rotation[1], es.initial_rotation[2], es.initial_rotation[3]}; // :463
+    p.vel = velocity;
+    p.av = av;
+    p.lifetime = lifetime;
+    p.iscale = initial_scale;
+    p.c0 = sample_gradient(ps.base_color, 0.0f);     // :460
+    p.c1 = sample_gradient(ps.emissive_color, 0.0f); // :461
+    p.scale = initial_scale;                         // scale = initial_scale (:457)
     return p;
 }
 __device__ __forceinline__ void emit_particle(const DeviceTables &t, const fw_emission_settings &es, const DevParticleSettings &ps,
@@ -296,46 +342,43 @@ __device__ __forceinline__ void emit_particle(const DeviceTables &t, const fw_em
 
 // ------------------------------------------------------------------------------------------
 // One particle, one frame: reference src/core.rs:591-658 in the reference's order. Returns
-// whether the particle survives; the packs are updated in place, colours / scale are outputs.
+// whether the particle survives; p is updated in place (a particle that dies of age keeps its old
+// state but the bumped age, :594-598; one destroyed by a collision has position / velocity / scale
+// updated, :633-639).
 // COLLIDE (0 none, 1 cuboid / sphere colliders, 2 + cylinders / cones): warp-synchronous (every
 // lane of the warp must call; cand_queue = this thread's column of the CTA's candidate queue, see
-// cast_ray).
-template <int COLLIDE>
-__device__ __forceinline__ bool step_particle(const DeviceTables &t, const DevParticleSettings &ps, float dt, bool valid, float4 &M0,
-                                              float4 &M1, float4 &M2, float2 &M3, float2 K, float4 &c0, float4 &c1, float &scale,
-                                              float &age_out, bool &destroyed_by_collision, uint32_t *cand_queue = nullptr,
-                                              bool sweeps = true) {
-    const float lifetime = K.x, iscale = K.y;
-    const float age = M0.w + dt;              // :594
-    bool alive = valid && !(age >= lifetime); // :596-599
-    age_out = age;
+// cast_ray). ROT = false: the stream is static (fw_internal.h) -- rotation and angular velocity
+// are per-stream constants that :645-650 map to themselves, so they are not evaluated.
+template <int COLLIDE, bool ROT>
+__device__ __forceinline__ bool step_particle(const DeviceTables &t, const DevParticleSettings &ps, float dt, bool valid, ParticleRegs &p,
+                                              bool &destroyed_by_collision, uint32_t *cand_queue = nullptr, bool sweeps = true) {
+    const float age = p.age + dt;               // :594
+    bool alive = valid && !(age >= p.lifetime); // :596-599
+    p.age = age;
     destroyed_by_collision = false;
-    V3 pos = v3(M0.x, M0.y, M0.z), vel = v3(M2.x, M2.y, M2.z);
+    V3 pos = p.pos, vel = p.vel;
     bool should_destroy = false;
     if (COLLIDE) // :608-617, hoisted out of the branch so that the warp stays converged inside
         particle_collision<(COLLIDE == 2)>(t.colliders, t.broadphase, ps.collision, alive && sweeps, pos, vel, dt, cand_queue, should_destroy);
     if (alive) {
-        const float age_percent = age / lifetime;                   // :601
-        scale = iscale * sample_curve(ps.scale_curve, age_percent); // :602-605
-        if (!COLLIDE || !sweeps) pos = pos + vel * dt;              // :619-623
+        const float age_percent = age / p.lifetime;                     // :601
+        p.scale = p.iscale * sample_curve(ps.scale_curve, age_percent); // :602-605
+        if (!COLLIDE || !sweeps) pos = pos + vel * dt;                  // :619-623
+        p.pos = pos;                                                    // :633
         if (should_destroy) {
-            alive = false;                              // :636-639: position, velocity and scale
-            destroyed_by_collision = true;              // are already updated
-            M0 = make_float4(pos.x, pos.y, pos.z, age);
-            M2 = make_float4(vel.x, vel.y, vel.z, M2.w);
+            alive = false; // :636-639: position, velocity and scale are already updated
+            destroyed_by_collision = true;
+            p.vel = vel;
         } else {
             const V3 acc = v3(ps.acceleration[0], ps.acceleration[1], ps.acceleration[2]);
-            vel = vel + (acc - vel * ps.linear_drag) * dt; // :641-643
-            V3 av = v3(M2.w, M3.x, M3.y);
-            const Q4 rot = qmul(q_from_scaled_axis(av * dt), Q4{M1.x, M1.y, M1.z, M1.w}); // :645-647
-            const V3 aacc = v3(ps.angular_acceleration[0], ps.angular_acceleration[1], ps.angular_acceleration[2]);
-            av = av + (aacc - av * ps.angular_drag) * dt;         // :648-650
-            c0 = sample_gradient(ps.base_color, age_percent);     // :652-653
-            c1 = sample_gradient(ps.emissive_color, age_percent); // :654-655
-            M0 = make_float4(pos.x, pos.y, pos.z, age);
-            M1 = make_float4(rot.x, rot.y, rot.z, rot.w);
-            M2 = make_float4(vel.x, vel.y, vel.z, av.x);
-            M3 = make_float2(av.y, av.z);
+            p.vel = vel + (acc - vel * ps.linear_drag) * dt; // :641-643
+            if (ROT) {
+                p.rot = qmul(q_from_scaled_axis(p.av * dt), p.rot); // :645-647
+                const V3 aacc = v3(ps.angular_acceleration[0], ps.angular_acceleration[1], ps.angular_acceleration[2]);
+                p.av = p.av + (aacc - p.av * ps.angular_drag) * dt; // :648-650
+            }
+            p.c0 = sample_gradient(ps.base_color, age_percent);     // :652-653
+            p.c1 = sample_gradient(ps.emissive_color, age_percent); // :654-655
         }
     }
     return alive;
@@ -343,14 +386,14 @@ __device__ __forceinline__ bool step_particle(const DeviceTables &t, const DevPa
 // per-stream AABB of position -/+ scale (reference src/render.rs:681-692) for the spawn+step
 // kernel, where the lanes of a warp may belong to different streams: reduce over the lanes of
 // `group` (all of the same stream; every lane of the group must call)
-__device__ __forceinline__ void accumulate_aabb(StreamState *stp, uint32_t group, bool alive, const float4 &M0, float scale) {
+__device__ __forceinline__ void accumulate_aabb(StreamState *stp, uint32_t group, bool alive, V3 pos, float scale) {
     uint32_t mn[3], mx[3];
-    mn[0] = alive ? enc_f32(M0.x - scale) : 0xFFFFFFFFu;
-    mn[1] = alive ? enc_f32(M0.y - scale) : 0xFFFFFFFFu;
-    mn[2] = alive ? enc_f32(M0.z - scale) : 0xFFFFFFFFu;
-    mx[0] = alive ? enc_f32(M0.x + scale) : 0u;
-    mx[1] = alive ? enc_f32(M0.y + scale) : 0u;
-    mx[2] = alive ? enc_f32(M0.z + scale) : 0u;
+    mn[0] = alive ? enc_f32(pos.x - scale) : 0xFFFFFFFFu;
+    mn[1] = alive ? enc_f32(pos.y - scale) : 0xFFFFFFFFu;
+    mn[2] = alive ? enc_f32(pos.z - scale) : 0xFFFFFFFFu;
+    mx[0] = alive ? enc_f32(pos.x + scale) : 0u;
+    mx[1] = alive ? enc_f32(pos.y + scale) : 0u;
+    mx[2] = alive ? enc_f32(pos.z + scale) : 0u;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         mn[k] = __reduce_min_sync(group, mn[k]);
@@ -458,24 +501,23 @@ __global__ void __launch_bounds__(256, COLLIDE ? FW_MINB_COLLIDE : 5) spawn_kern
         if (!STEP) {
             if (have) store_particle(d, slot, p, true);
         } else {
-            // first update step of the new particle, then one store of the final state
-            float age;
+            // first update step of the new particle, then one store of the final state. (Static
+            // streams run the rotating body too: on their constants it is the identity, fw_internal.h.)
             bool by_collision;
             const DevParticleSettings &ps = t.settings[have ? stream : 0u];
             bool alive;
             if (COLLIDE) { // per lane: only the streams with collision settings sweep
-                const bool sweeps = have && d.variant == kFifoCollide;
-                alive = step_particle<COLLIDE>(t, ps, dt, have, p.m0, p.m1, p.m2, p.m3, p.k, p.o0, p.o1, p.o2, age, by_collision,
-                                               cq.q + threadIdx.x, sweeps);
+                const bool sweeps = have && variant_collides(d.variant);
+                alive = step_particle<COLLIDE, true>(t, ps, dt, have, p, by_collision, cq.q + threadIdx.x, sweeps);
             } else {
-                alive = step_particle<0>(t, ps, dt, have, p.m0, p.m1, p.m2, p.m3, p.k, p.o0, p.o1, p.o2, age, by_collision);
+                alive = step_particle<0, true>(t, ps, dt, have, p, by_collision);
             }
             if (alive) store_particle(d, slot, p, true);
             // AABB and death count per stream: lanes of a warp may belong to different streams
             const uint32_t group = __match_any_sync(0xffffffffu, stream);
             if (stream != 0xFFFFFFFFu) {
                 StreamState *stp = &t.states[stream];
-                accumulate_aabb(stp, group, alive, p.m0, p.o2);
+                accumulate_aabb(stp, group, alive, p.pos, p.scale);
                 const uint32_t dead_mask = __ballot_sync(group, have && !alive) & group;
                 if (dead_mask && (group & ((1u << lane_id()) - 1u)) == 0u) atomicAdd(&stp->dead, __popc(dead_mask));
             }
@@ -501,12 +543,13 @@ __global__ void __launch_bounds__(256) nested_count_kernel(DeviceTables t, Frame
     const StreamDesc d = t.descs[cmd.parent_stream];
     const StreamState st = t.states[cmd.parent_stream];
     const StreamArrays a = stream_arrays(d.base, d.capacity);
+    const DevParticleSettings &pps = t.settings[cmd.parent_stream];
     float *lea = lea_array(d.base, d.capacity, cmd.lea_index);
     uint32_t *counts = t.nested_scratch + cmd.scratch_off;
     const float start = es.offset_start, end = es.offset_end, per_cycle = es.count;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < st.count; j += gridDim.x * blockDim.x) {
         const uint32_t slot = wrap(st.head + j, d.capacity);
-        const float age = a.m0[slot].w, lifetime = a.k[slot].x, last = lea[slot];
+        const float age = a.m0[slot].w, lifetime = load_lifetime(d, a, pps, slot), last = lea[slot];
         const float percent_passed = age / lifetime;
         const float last_emission_percent = last / lifetime;
         const float lo = fmaxf(last_emission_percent, start);
@@ -584,9 +627,10 @@ __global__ void __launch_bounds__(256) nested_spawn_kernel(DeviceTables t, Frame
             if (offsets[mid] <= g) lo = mid; else hi = mid;
         }
         const uint32_t pslot = wrap(pst.head + lo, pd.capacity);
-        const float4 p0 = pa.m0[pslot], p1 = pa.m1[pslot], p2 = pa.m2[pslot];
+        const float4 p0 = pa.m0[pslot], p2 = pa.m2[pslot];
         emit_particle(t, t.emitters[cmd.emitter_idx], t.settings[cmd.child_stream], cd,
-                      wrap(cst.head + out.spawn_base + g, cd.capacity), v3(p0.x, p0.y, p0.z), Q4{p1.x, p1.y, p1.z, p1.w},
+                      wrap(cst.head + out.spawn_base + g, cd.capacity), v3(p0.x, p0.y, p0.z),
+                      load_rotation(pd, pa, t.settings[cmd.parent_stream], pslot),
                       v3(p2.x, p2.y, p2.z), in.modifier_scale, in.modifier_speed, cmd.spawner_key, cmd.emitter_local,
                       out.serial_base + g);
     }
@@ -719,6 +763,10 @@ __global__ void __launch_bounds__(256) count_kernel(DeviceTables t, FrameDeviceI
         const StreamDesc d = t.descs[e.stream];
         const StreamArrays a = stream_arrays(d.base, d.capacity);
         const uint32_t shift = e.head & 31u, tile_first = e.tile * kTile;
+        // where (age, lifetime) live: rotating stream m0.w / k.x; static stream k = (lifetime, age)
+        // -- 8 instead of 24 bytes per particle -- or, with a constant lifetime, m0.w alone
+        const bool rot = variant_rotates(d.variant), klife = (d.flags & kStoreLife) != 0u;
+        const float const_life = t.settings[e.stream].const_lifetime;
         uint32_t dead = 0;
         unsigned long long before_warp = 0; // dead particles of the tile in front of warp j, 8 bits each (j = 1..7)
         static_assert(kTile == 256, "the per-warp death counts of a tile are packed as 7 x 8 bits");
@@ -730,7 +778,14 @@ __global__ void __launch_bounds__(256) count_kernel(DeviceTables t, FrameDeviceI
             bool dies = false;
             if (valid) {
                 const uint32_t slot = wrap(e.head + i, d.capacity);
-                dies = a.m0[slot].w + dt >= a.k[slot].x;
+                if (rot) {
+                    dies = a.m0[slot].w + dt >= a.k[slot].x;
+                } else if (klife) {
+                    const float2 K = a.k[slot];
+                    dies = K.y + dt >= K.x;
+                } else {
+                    dies = a.m0[slot].w + dt >= const_life;
+                }
             }
             dead += __popc(__ballot_sync(0xffffffffu, dies));
         }
@@ -782,8 +837,9 @@ struct alignas(16) UpdateSmem {
 // look-back of the compact variants: a tile only ever waits on lower-numbered tiles, and every
 // CTA of the grid is resident). Thread 0 looks up the next tile's stream and prefetches its
 // settings block with a bulk async copy while the CTA works on the current tile.
-template <bool COMPACT, int COLLIDE>
-__global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (COMPACT ? FW_MINB_COMPACT : FW_MINB))
+// ROT: the streams of this launch keep rotation / angular velocity per particle (fw_internal.h).
+template <bool COMPACT, int COLLIDE, bool ROT>
+__global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (COMPACT ? FW_MINB_COMPACT : (ROT ? FW_MINB : FW_MINB_STATIC)))
     update_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant, uint32_t team_size) {
     __shared__ UpdateSmem sm;
     __shared__ CandQueue<(COLLIDE != 0)> cq;
@@ -872,15 +928,21 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
             pre_excl = (uint32_t)t.lookback[tile_base + tile] + (warp ? (uint32_t)(in_tile >> (8u * (warp - 1u))) & 255u : 0u);
         }
 
-        // ---- loads: 64 B per particle, five independent coalesced requests per thread
+        // ---- loads: 64 B per particle of a rotating stream (five independent coalesced requests
+        // per thread), 32 B of a static one (+ 8 B when its lifetime varies)
         float4 M0 = make_float4(0.f, 0.f, 0.f, 0.f), M1 = M0, M2 = M0;
         float2 M3 = make_float2(0.f, 0.f), K = make_float2(1.f, 0.f);
+        const uint32_t flags = d.flags;
         if (valid) {
             M0 = ld_pack(a.m0 + slot);
-            M1 = ld_pack(a.m1 + slot);
             M2 = ld_pack(a.m2 + slot);
-            M3 = ld_pack(a.m3 + slot);
-            K = ld_pack(a.k + slot);
+            if (ROT) {
+                M1 = ld_pack(a.m1 + slot);
+                M3 = ld_pack(a.m3 + slot);
+                K = ld_pack(a.k + slot);
+            } else if (flags & kStoreLife) {
+                K = ld_pack(a.k + slot);
+            }
         }
         // next tile: stream lookup + settings prefetch into the other buffer (every thread left
         // that buffer at the __syncthreads closing the previous iteration). ~2.5k cycles of
@@ -900,21 +962,34 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         const DevParticleSettings &ps = sm.settings[buf];
 
         // ---- reference src/core.rs:591-658
-        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-        float scale = 0.f, age;
+        ParticleRegs p;
+        p.pos = v3(M0.x, M0.y, M0.z);
+        p.age = M0.w;
+        p.vel = v3(M2.x, M2.y, M2.z);
+        if (ROT) {
+            p.rot = Q4{M1.x, M1.y, M1.z, M1.w};
+            p.av = v3(M2.w, M3.x, M3.y);
+            p.lifetime = K.x;
+            p.iscale = K.y;
+        } else {
+            p.rot = Q4{0.f, 0.f, 0.f, 1.f}; // (not used: per-stream constants)
+            p.av = v3(0.f, 0.f, 0.f);
+            p.iscale = M2.w;
+            p.lifetime = (flags & kStoreLife) ? K.x : ps.const_lifetime;
+        }
+        p.c0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        p.c1 = p.c0;
+        p.scale = 0.f;
         bool destroyed_by_collision;
-        bool alive = step_particle<COLLIDE>(t, ps, dt, valid, M0, M1, M2, M3, K, c0, c1, scale, age, destroyed_by_collision,
-                                            COLLIDE ? cq.q + tid : nullptr);
+        bool alive = step_particle<COLLIDE, ROT>(t, ps, dt, valid, p, destroyed_by_collision, COLLIDE ? cq.q + tid : nullptr);
         // destroyed-particle stream (:588,597,637): the record the handler receives keeps the old
-        // colours (and the old scale unless a collision destroyed it)
+        // colours (and the old scale unless a collision destroyed it). Capturing streams keep every
+        // pack (fw_api.cu: stream_proofs).
         const bool capture = COMPACT && d.destroyed_base != nullptr && valid && !alive;
         if (capture) {
-            c0 = a.o0[slot];
-            c1 = a.o1[slot];
-            if (!destroyed_by_collision) {
-                scale = a.o2[slot];
-                M0.w = age; // age is bumped before the lifetime test (:594-598)
-            }
+            p.c0 = a.o0[slot];
+            p.c1 = a.o1[slot];
+            if (!destroyed_by_collision) p.scale = a.o2[slot];
         }
         FW_DBG(0)
         const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
@@ -995,36 +1070,33 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
                                                   : excl + ((i - first_logical) - (before + __popc(alive_mask & lanes_lt)));
             dslot = wrap(dst_base + (i - dead_before), d.capacity);
             if (capture) { // destroyed particles, in Vec order, into the side block
-                const uint32_t di = dead_before;
-                const StreamArrays b = stream_arrays(d.destroyed_base, d.capacity);
-                b.m0[di] = M0;
-                b.m1[di] = M1;
-                b.m2[di] = M2;
-                b.m3[di] = M3;
-                b.k[di] = K;
-                b.o0[di] = c0;
-                b.o1[di] = c1;
-                b.o2[di] = scale;
+                StreamDesc dd = d;
+                dd.base = d.destroyed_base;
+                dd.n_lea = 0u;
+                store_particle(dd, dead_before, p, false);
             }
         } else {
             const uint32_t n_dead_w = __popc(valid_mask & ~alive_mask);
             if (lane == 0 && n_dead_w) atomicAdd(&stp->dead, n_dead_w);
         }
 
-        // ---- stores: 92 B per survivor (more when a compacting stream moves its constants)
+        // ---- stores: 92 B per survivor of a rotating stream, 28 B + the colours / scale that vary
+        // of a static one (more when a compacting stream moves its constants)
         if (alive) {
-            st_pack(a.m0 + dslot, M0);
-            st_pack(a.m1 + dslot, M1);
-            st_pack(a.m2 + dslot, M2);
-            st_pack(a.m3 + dslot, M3);
-            if (COMPACT) {
-                st_pack(a.k + dslot, K);
-                // last_emitted_age moves with the particle (out of place: the source is still intact)
-                for (uint32_t j = 0; j < d.n_lea; j++) lea_array(d.base, d.capacity, j)[dslot] = lea_array(d.base, d.capacity, j)[slot];
+            st_pack(a.m0 + dslot, make_float4(p.pos.x, p.pos.y, p.pos.z, p.age));
+            st_pack(a.m2 + dslot, make_float4(p.vel.x, p.vel.y, p.vel.z, ROT ? p.av.x : p.iscale));
+            if (ROT) {
+                st_pack(a.m1 + dslot, make_float4(p.rot.x, p.rot.y, p.rot.z, p.rot.w));
+                st_pack(a.m3 + dslot, make_float2(p.av.y, p.av.z));
+                if (COMPACT) st_pack(a.k + dslot, K);
+            } else if (flags & kStoreLife) {
+                st_pack(a.k + dslot, make_float2(p.lifetime, p.age)); // (lifetime, copy of age): what count_kernel reads
             }
-            st_pack(a.o0 + dslot, c0);
-            st_pack(a.o1 + dslot, c1);
-            st_pack(a.o2 + dslot, scale);
+            if (COMPACT) // last_emitted_age moves with the particle (out of place: the source is still intact)
+                for (uint32_t j = 0; j < d.n_lea; j++) lea_array(d.base, d.capacity, j)[dslot] = lea_array(d.base, d.capacity, j)[slot];
+            if (flags & kStoreBase) st_pack(a.o0 + dslot, p.c0);
+            if (flags & kStoreEmi) st_pack(a.o1 + dslot, p.c1);
+            if (flags & kStoreScale) st_pack(a.o2 + dslot, p.scale);
         }
 
         // ---- per-stream AABB of position -/+ scale (reference src/render.rs:681-692), after the
@@ -1033,12 +1105,12 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
         // profiles/r1_tuning.md)
         {
             uint32_t mn[3], mx[3];
-            mn[0] = alive ? enc_f32(M0.x - scale) : 0xFFFFFFFFu;
-            mn[1] = alive ? enc_f32(M0.y - scale) : 0xFFFFFFFFu;
-            mn[2] = alive ? enc_f32(M0.z - scale) : 0xFFFFFFFFu;
-            mx[0] = alive ? enc_f32(M0.x + scale) : 0u;
-            mx[1] = alive ? enc_f32(M0.y + scale) : 0u;
-            mx[2] = alive ? enc_f32(M0.z + scale) : 0u;
+            mn[0] = alive ? enc_f32(p.pos.x - p.scale) : 0xFFFFFFFFu;
+            mn[1] = alive ? enc_f32(p.pos.y - p.scale) : 0xFFFFFFFFu;
+            mn[2] = alive ? enc_f32(p.pos.z - p.scale) : 0xFFFFFFFFu;
+            mx[0] = alive ? enc_f32(p.pos.x + p.scale) : 0u;
+            mx[1] = alive ? enc_f32(p.pos.y + p.scale) : 0u;
+            mx[2] = alive ? enc_f32(p.pos.z + p.scale) : 0u;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
@@ -1089,21 +1161,25 @@ __global__ void __launch_bounds__(256) pack_copy_kernel(DeviceTables t, uint32_t
     const uint32_t first = live_first(d, st);
     const unsigned long long off = offsets[1 + blockIdx.y];
     const StreamArrays a = stream_arrays(d.base, d.capacity);
-    // one 16-byte chunk of a row per thread: fully coalesced 64-byte row writes
+    const DevParticleSettings &ps = t.settings[s];
+    const bool rot = variant_rotates(d.variant);
+    // one 16-byte chunk of a row per thread: fully coalesced 64-byte row writes; what the stream
+    // does not keep per particle comes from its constants (fw_internal.h)
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < (uint64_t)live * 4u; q += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t r = (uint32_t)(q >> 2), c = (uint32_t)(q & 3u);
         if (off + r >= cap_rows) return;
         const uint32_t slot = wrap(first + r, d.capacity);
         float4 v;
-        if (c == 0u) {
+        if (c == 0u) { // position.xyz, scale
             v = a.m0[slot];
-            v.w = a.o2[slot]; // position.xyz, scale
+            if (d.flags & kStoreScale) v.w = a.o2[slot];
+            else v.w = (rot ? a.k[slot].y : a.m2[slot].w) * ps.scale_curve.values[0];
         } else if (c == 1u) {
-            v = a.m1[slot];
+            v = rot ? a.m1[slot] : make_float4(ps.const_rotation[0], ps.const_rotation[1], ps.const_rotation[2], ps.const_rotation[3]);
         } else if (c == 2u) {
-            v = a.o0[slot];
+            v = (d.flags & kStoreBase) ? a.o0[slot] : ps.base_color.colors[0];
         } else {
-            v = a.o1[slot];
+            v = (d.flags & kStoreEmi) ? a.o1[slot] : ps.emissive_color.colors[0];
         }
         for (uint32_t k = 0; k < dst.n; k++) dst.rows[k][(off + r) * 4u + c] = v;
     }
@@ -1153,42 +1229,41 @@ __global__ void __launch_bounds__(32) gather_signal_kernel(GatherPeers p, uint32
 }
 
 // ParticleData rows of one block (host mirror, destroyed stream, tests)
-__global__ void __launch_bounds__(256) gather_particles_kernel(uint8_t *base, uint32_t capacity, uint32_t first, uint32_t n,
+__global__ void __launch_bounds__(256) gather_particles_kernel(StreamDesc d, const DevParticleSettings *psp, uint32_t first, uint32_t n,
                                                                uint32_t pbr, fw_particle_data *dst) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const StreamArrays a = stream_arrays(base, capacity);
-    const uint32_t slot = wrap(first + i, capacity);
-    const float4 m0 = a.m0[slot], m1 = a.m1[slot], m2 = a.m2[slot], o0 = a.o0[slot], o1 = a.o1[slot];
-    const float2 m3 = a.m3[slot], k = a.k[slot];
+    const ParticleRegs r = load_particle(d, *psp, wrap(first + i, d.capacity));
     fw_particle_data p;
-    p.position[0] = m0.x; p.position[1] = m0.y; p.position[2] = m0.z;
-    p.velocity[0] = m2.x; p.velocity[1] = m2.y; p.velocity[2] = m2.z;
-    p.rotation[0] = m1.x; p.rotation[1] = m1.y; p.rotation[2] = m1.z; p.rotation[3] = m1.w;
-    p.angular_velocity[0] = m2.w; p.angular_velocity[1] = m3.x; p.angular_velocity[2] = m3.y;
-    p.initial_scale = k.y;
-    p.scale = a.o2[slot];
-    p.age = m0.w;
-    p.lifetime = k.x;
-    p.base_color[0] = o0.x; p.base_color[1] = o0.y; p.base_color[2] = o0.z; p.base_color[3] = o0.w;
-    p.emissive_color[0] = o1.x; p.emissive_color[1] = o1.y; p.emissive_color[2] = o1.z; p.emissive_color[3] = o1.w;
+    p.position[0] = r.pos.x; p.position[1] = r.pos.y; p.position[2] = r.pos.z;
+    p.velocity[0] = r.vel.x; p.velocity[1] = r.vel.y; p.velocity[2] = r.vel.z;
+    p.rotation[0] = r.rot.x; p.rotation[1] = r.rot.y; p.rotation[2] = r.rot.z; p.rotation[3] = r.rot.w;
+    p.angular_velocity[0] = r.av.x; p.angular_velocity[1] = r.av.y; p.angular_velocity[2] = r.av.z;
+    p.initial_scale = r.iscale;
+    p.scale = r.scale;
+    p.age = r.age;
+    p.lifetime = r.lifetime;
+    p.base_color[0] = r.c0.x; p.base_color[1] = r.c0.y; p.base_color[2] = r.c0.z; p.base_color[3] = r.c0.w;
+    p.emissive_color[0] = r.c1.x; p.emissive_color[1] = r.c1.y; p.emissive_color[2] = r.c1.z; p.emissive_color[3] = r.c1.w;
     p.pbr = pbr;
     dst[i] = p;
 }
 __global__ void __launch_bounds__(256) scatter_particles_kernel(StreamDesc d, uint32_t n, const fw_particle_data *src) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const StreamArrays a = stream_arrays(d.base, d.capacity);
-    const fw_particle_data p = src[i];
-    a.m0[i] = make_float4(p.position[0], p.position[1], p.position[2], p.age);
-    a.m1[i] = make_float4(p.rotation[0], p.rotation[1], p.rotation[2], p.rotation[3]);
-    a.m2[i] = make_float4(p.velocity[0], p.velocity[1], p.velocity[2], p.angular_velocity[0]);
-    a.m3[i] = make_float2(p.angular_velocity[1], p.angular_velocity[2]);
-    a.k[i] = make_float2(p.lifetime, p.initial_scale);
-    a.o0[i] = make_float4(p.base_color[0], p.base_color[1], p.base_color[2], p.base_color[3]);
-    a.o1[i] = make_float4(p.emissive_color[0], p.emissive_color[1], p.emissive_color[2], p.emissive_color[3]);
-    a.o2[i] = p.scale;
-    for (uint32_t j = 0; j < d.n_lea; j++) lea_array(d.base, d.capacity, j)[i] = kF32Min;
+    const fw_particle_data s = src[i];
+    ParticleRegs p;
+    p.pos = v3(s.position[0], s.position[1], s.position[2]);
+    p.vel = v3(s.velocity[0], s.velocity[1], s.velocity[2]);
+    p.rot = Q4{s.rotation[0], s.rotation[1], s.rotation[2], s.rotation[3]};
+    p.av = v3(s.angular_velocity[0], s.angular_velocity[1], s.angular_velocity[2]);
+    p.age = s.age;
+    p.lifetime = s.lifetime;
+    p.iscale = s.initial_scale;
+    p.scale = s.scale;
+    p.c0 = make_float4(s.base_color[0], s.base_color[1], s.base_color[2], s.base_color[3]);
+    p.c1 = make_float4(s.emissive_color[0], s.emissive_color[1], s.emissive_color[2], s.emissive_color[3]);
+    store_particle(d, i, p, true); // (what the stream does not keep was checked against its constants by the host)
 }
 __global__ void __launch_bounds__(256) sincos_kernel(const float *x, uint64_t n, float *s, float *c) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
@@ -1235,21 +1310,24 @@ cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uin
     nested_spawn_kernel<<<dim3(gx, n_cmds), 256, 0, s>>>(t, f, phase);
     return cudaGetLastError();
 }
+template <bool COMPACT, bool ROT>
+static void launch_update_t(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, uint32_t ts, int collide,
+                            cudaStream_t s) {
+    if (collide == 2) update_kernel<COMPACT, 2, ROT><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
+    else if (collide == 1) update_kernel<COMPACT, 1, ROT><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
+    else update_kernel<COMPACT, 0, ROT><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
+}
 cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, int team_size, bool revolved,
                           cudaStream_t s) {
+    if (variant >= kNumVariants) return cudaErrorInvalidValue;
     const uint32_t ts = (uint32_t)team_size;
-    switch (variant) {
-    case kFifo: update_kernel<false, 0><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
-    case kCompact: update_kernel<true, 0><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts); break;
-    case kFifoCollide:
-        if (revolved) update_kernel<false, 2><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
-        else update_kernel<false, 1><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
-        break;
-    case kCompactCollide:
-        if (revolved) update_kernel<true, 2><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
-        else update_kernel<true, 1><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
-        break;
-    default: return cudaErrorInvalidValue;
+    const int collide = variant_collides(variant) ? (revolved ? 2 : 1) : 0;
+    if (variant_rotates(variant)) {
+        if (variant_is_fifo(variant)) launch_update_t<false, true>(t, f, variant, grid, ts, collide, s);
+        else launch_update_t<true, true>(t, f, variant, grid, ts, collide, s);
+    } else {
+        if (variant_is_fifo(variant)) launch_update_t<false, false>(t, f, variant, grid, ts, collide, s);
+        else launch_update_t<true, false>(t, f, variant, grid, ts, collide, s);
     }
     return cudaGetLastError();
 }
@@ -1262,15 +1340,20 @@ cudaError_t update_grid_size(int device, int *grids, int *team_size) {
     int sms = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
-    int occ[kNumVariants] = {0, 0, 0, 0};
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kFifo], update_kernel<false, 0>, kUpdateThreads, 0);
+    int occ[kNumVariants] = {0};
+    // (collision variants: the build with the cylinder / cone tests is the larger one)
+#define FW_OCC(v, K) \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], K, kUpdateThreads, 0); \
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kCompact], update_kernel<true, 0>, kUpdateThreads, 0);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kFifoCollide], update_kernel<false, 2>, kUpdateThreads, 0);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[kCompactCollide], update_kernel<true, 2>, kUpdateThreads, 0);
-    if (e != cudaSuccess) return e;
+    FW_OCC(kFifo, (update_kernel<false, 0, false>))
+    FW_OCC(kCompact, (update_kernel<true, 0, false>))
+    FW_OCC(kFifoCollide, (update_kernel<false, 2, false>))
+    FW_OCC(kCompactCollide, (update_kernel<true, 2, false>))
+    FW_OCC(kFifo | kVarRot, (update_kernel<false, 0, true>))
+    FW_OCC(kCompact | kVarRot, (update_kernel<true, 0, true>))
+    FW_OCC(kFifoCollide | kVarRot, (update_kernel<false, 2, true>))
+    FW_OCC(kCompactCollide | kVarRot, (update_kernel<true, 2, true>))
+#undef FW_OCC
     // persistent grids: every CTA must be resident (the look-back of the compact variants
     // spins on lower-numbered tiles)
     for (int v = 0; v < (int)kNumVariants; v++) grids[v] = sms * (occ[v] > 0 ? occ[v] : 1);
@@ -1301,10 +1384,10 @@ cudaError_t launch_gather_signal(const GatherPeers &p, uint32_t which, unsigned 
     gather_signal_kernel<<<1, 32, 0, s>>>(p, which, epoch, rows_src, timeout_ns);
     return cudaGetLastError();
 }
-cudaError_t launch_gather_particles(uint8_t *base, uint32_t capacity, uint32_t first, uint32_t n, uint32_t pbr,
+cudaError_t launch_gather_particles(const StreamDesc &d, const DevParticleSettings *ps, uint32_t first, uint32_t n, uint32_t pbr,
                                     fw_particle_data *dst, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    gather_particles_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(base, capacity, first, n, pbr, dst);
+    gather_particles_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(d, ps, first, n, pbr, dst);
     return cudaGetLastError();
 }
 cudaError_t launch_scatter_particles(const StreamDesc &d, uint32_t n, const fw_particle_data *src, cudaStream_t s) {

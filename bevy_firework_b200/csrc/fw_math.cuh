@@ -241,7 +241,15 @@ __device__ __forceinline__ bool ray_cuboid_local(V3 he, V3 o, V3 d, float max_to
     }
     if (tmin <= max_toi) {
         float nx = 0.0f, ny = 0.0f, nz = 0.0f;
-        if (!near_diag && near_side != 0) {
+        if (near_diag) {
+            // the ray enters through an edge or a corner (two slabs at the same parameter): parry's
+            // clip_aabb_line reports -dir.normalize() (a zero normal here would turn the bounce of
+            // src/core.rs:778-784 into NaNs)
+            const V3 nd = normalize(d);
+            nx = -nd.x;
+            ny = -nd.y;
+            nz = -nd.z;
+        } else if (near_side != 0) {
             float sgn = near_side < 0 ? 1.0f : -1.0f;
             int ax = (near_side < 0 ? -near_side : near_side) - 1;
             if (ax == 0) nx = sgn;

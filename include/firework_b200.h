@@ -244,6 +244,29 @@ typedef struct fw_frame_profile {
     uint64_t d2h_bytes; /* per-frame state readback copied device -> host */
 } fw_frame_profile;
 
+/* What the library keeps per particle for one stream (spawner, particle type). Fields that
+ * fw_spawner_reset can prove constant over the stream's whole life from its settings -- no angular
+ * motion (rotation, angular_velocity), a constant colour gradient or scale curve, one lifetime -- are
+ * per-stream constants and cost no memory traffic; fw_read_* return them like any other field, and
+ * fw_write_particles rows that contradict a proof make the field per-particle state again.
+ * bytes_* = the algorithmic bytes one update moves per particle of this stream (SURVEY section 8d
+ * restated per stream: 64 + 92 for a stream where nothing is provable). */
+#define FW_LAYOUT_COMPACTING 1u /* variant bits */
+#define FW_LAYOUT_COLLIDES 2u
+#define FW_LAYOUT_ROTATES 4u
+#define FW_STORE_BASE_COLOR 1u /* flags bits */
+#define FW_STORE_EMISSIVE_COLOR 2u
+#define FW_STORE_SCALE 4u
+#define FW_STORE_LIFETIME 8u
+typedef struct fw_stream_layout {
+    uint32_t variant;
+    uint32_t flags;
+    uint32_t bytes_read;
+    uint32_t bytes_written;
+    uint32_t bytes_count_pass; /* compacting streams without collisions: read by the death-counting pass */
+    uint32_t capacity;         /* slots of the stream's ring */
+} fw_stream_layout;
+
 const char *fw_last_global_error(void);
 const char *fw_last_error(const fw_context *ctx);
 uint32_t fw_abi_version(void);
@@ -290,7 +313,8 @@ int fw_spawner_remove(fw_context *ctx, uint32_t spawner_key);
 int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n);
 
 /* one tick of (spawn_particles ; update_particles) over every spawner of the context.
- * Asynchronous on the context's stream. */
+ * Asynchronous on the context's stream. dt = Res<Time>::delta_secs() (src/core.rs:413,594): finite
+ * and >= 0, anything else is FW_ERR_INVALID_ARGUMENT. */
 int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, uint32_t n_inputs);
 
 /* wait for all queued frames */
@@ -305,6 +329,8 @@ int fw_counts_all(fw_context *ctx, uint32_t *out_keys, uint32_t *out_types, uint
 int fw_spawner_status_get(fw_context *ctx, uint32_t spawner_key, fw_spawner_status *out);
 /* data.finished_notified = true (src/core.rs:685), after the shim triggered the event */
 int fw_spawner_mark_finished_notified(fw_context *ctx, uint32_t spawner_key);
+
+int fw_stream_layout_get(fw_context *ctx, uint32_t spawner_key, uint32_t type, fw_stream_layout *out);
 
 /* host mirror of data.particles[type] in the reference's Vec order (synchronises) */
 int fw_read_particles(fw_context *ctx, uint32_t spawner_key, uint32_t type,

@@ -354,7 +354,10 @@ static int ray_cuboid_local(v3 he, v3 o, v3 d, float max_toi, float *toi, v3 *no
     }
     if (tmin <= max_toi) {
         float nn[3] = {0.0f, 0.0f, 0.0f};
-        if (!near_diag && near_side != 0) {
+        if (near_diag) { /* edge / corner hit: parry's clip_aabb_line returns -dir.normalize() */
+            v3 nd = v3_normalize(d);
+            nn[0] = -nd.x; nn[1] = -nd.y; nn[2] = -nd.z;
+        } else if (near_side != 0) {
             if (near_side < 0) nn[-near_side - 1] = 1.0f; else nn[near_side - 1] = -1.0f;
         }
         *toi = tmin;

@@ -298,3 +298,20 @@ def test_culled_ray_cast_equals_brute_force(oracle):
     assert hits > 500
     inf = float("inf")
     assert oracle.cast_ray(arr, (0, 5, 0), (0, -1, 0), inf) == oracle.cast_ray(arr, (0, 5, 0), (0, -1, 0), inf, culled=True)
+
+
+def test_cuboid_edge_hit_normal(oracle):
+    """a ray that enters a cuboid exactly through an edge (two slabs at the same parameter): parry's
+    clip_aabb_line reports -dir.normalize(); a zero normal would turn the bounce of
+    src/core.rs:778-784 into NaNs"""
+    from bevy_firework_b200.workloads import cuboid
+
+    cube = cuboid((1.0, 1.0, 1.0), (0.0, 0.0, 0.0))
+    d = np.array([1.0, 1.0, 0.0], dtype=np.float32) / np.sqrt(np.float32(2.0))
+    hit = oracle.cast_ray([cube], (-1.5, -1.5, 0.0), tuple(d), 10.0)
+    assert hit is not None and hit[0] == pytest.approx(math.sqrt(2.0), rel=1e-6)
+    assert np.allclose(hit[1], -d, atol=1e-7)
+    cs = _abi.fw_collision_settings(1, 0.5, 0.1, 0, 0xFFFFFFFF)
+    pos, vel, destroyed = oracle.particle_collision([cube], cs, (-0.55, -0.55, 0.0), (6.0, 6.0, 0.0), 1.0 / 60.0)
+    assert np.isfinite(pos).all() and np.isfinite(vel).all() and not destroyed
+    assert vel[0] < 0 and vel[1] < 0  # bounced straight back along the diagonal
