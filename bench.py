@@ -58,6 +58,19 @@ def make_workload(name: str, rank: int):
         return ("C3r = C3 with lifetime U[0.5, 1.5] s: deaths anywhere in the Vec, in-place stable compaction "
                 "(~10 M live particles per GPU)",
                 [(base + i, sp, p, ident) for i, p in enumerate(pos)], None, 96, None)
+    if name == "c3g":
+        # C3's scene with NOTHING provable: angular velocity, emissive gradient, scale curve -> every
+        # ParticleData field is per-particle state, the 156 B/particle layout of SURVEY section 8d
+        from bevy_firework_b200 import FireworkCurve, FireworkGradient, LinearRgba, RandF32, RandVec3
+
+        sp = W.stress_spawner(rate=19531.0)
+        sp.particle_settings[0].scale_curve = FireworkCurve.even_samples([1.0, 0.5])
+        sp.particle_settings[0].emissive_color = FireworkGradient.even_samples([LinearRgba(1.0, 0.5, 0.1, 1.0), LinearRgba(0.0, 0.0, 0.0, 0.0)])
+        sp.emission_settings[0].initial_angular_velocity = RandVec3(RandF32(1.0, 4.0), (0.0, 1.0, 0.0), 0.5)
+        pos = W.grid_positions(512)
+        return ("C3g = C3 with angular velocity, an emissive gradient and a scale curve: every ParticleData field varies "
+                "(generic 156 B/particle layout, ~10 M live particles per GPU)",
+                [(base + i, sp, p, ident) for i, p in enumerate(pos)], None, 64, None)
     if name == "c2":
         sp = W.stress_spawner(rate=15625.0)
         pos = W.grid_positions(64)
@@ -250,13 +263,14 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c3r", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c3g", "c3r", "c4", "c5"])
     ap.add_argument("--cpu-steps", type=int, default=8, help="timed frames of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=120.0,
                     help="--impl reference: bound of the whole CPU run in seconds (the sample shrinks for large --steps)")
     ap.add_argument("--no-extract", action="store_true", help="skip the e2e_extract leg (full instance-row extract, D2H)")
     ap.add_argument("--blocks", type=int, default=10, help="timed blocks of --steps frames each; value = the median block")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the render-extract gather leg")
     ap.add_argument("--single-scaling", action="store_true", help="N > 1: do not also measure the other scaling mode")
     ap.add_argument("--no-graphs", action="store_true", help="launch kernel by kernel instead of replaying frame graphs")
     ap.add_argument("--no-concurrent-spawn", action="store_true", help="run the spawn kernel before the update kernel")
@@ -455,6 +469,44 @@ def main():
     live_all, launches_all = reduce_sum([live, main_t["launches"]])
     clocks_now = sampler.stop()
 
+    # ---- N > 1: the one exchange of the path, the render extract -- every GPU's ParticleInstance rows
+    # on every GPU (reference consumer src/render.rs:439-461). fw_gather_instances (pack kernel storing
+    # into every rank's buffer over NVLink) against pack + NCCL all-gather; rows compared for equality.
+    gather = None
+    if world > 1 and not args.no_gather:
+        from bevy_firework_b200.distributed import PeerGather, all_gather_instances
+
+        rows_nccl, counts = all_gather_instances(eng)
+        pg = PeerGather(eng, cap_rows_per_rank=max(counts) + 4096)
+        pg.issue()
+        rows_peer, pcounts = pg.result()
+        same = bool(pcounts == counts and rows_peer.shape == rows_nccl.shape and torch.equal(rows_peer, rows_nccl))
+        del rows_peer
+        reps = 5
+        barrier(eng)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            pg.issue()
+            eng.gather_result(world)  # waits for this rank's landed flags
+        ms_peer = (time.perf_counter() - t0) / reps * 1e3
+        barrier(eng)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r_, c_ = all_gather_instances(eng)
+            torch.cuda.synchronize()
+        ms_nccl = (time.perf_counter() - t0) / reps * 1e3
+        del r_, rows_nccl
+        ms_peer_all, ms_nccl_all = reduce_max([ms_peer, ms_nccl])
+        same_all = min(gather_ranks(same))
+        recv = (sum(counts) - min(counts)) * 64  # bytes the busiest link receives
+        gather = {"rows_total": int(sum(counts)), "peer_store_ms": ms_peer_all, "nccl_ms": ms_nccl_all,
+                  "received_gbs_per_gpu": recv / (ms_peer_all * 1e-3) / 1e9, "peer_copy_peak_gbs": 770.0,
+                  "frac_of_peer_copy_peak": recv / (ms_peer_all * 1e-3) / 1e9 / 770.0,
+                  "rows_equal_to_nccl_path": bool(same_all), "reps": reps,
+                  "what": "fw_gather_instances + fw_gather_result (pack kernel with peer stores, device-side flags) vs "
+                          "fw_pack_instances_device + NCCL all_gather; wall clock incl. the host sync, max over ranks"}
+        pg.close()
+
     # ---- weak scaling beside the strong headline (N > 1), same run
     other = None
     if world > 1 and not args.single_scaling:
@@ -514,6 +566,8 @@ def main():
             line["e2e_extract"] = extract
         if other:
             line[other["scaling"]] = other
+        if gather:
+            line["render_extract_gather"] = gather
         if world > 1:
             line["reference_arm_note"] = "the --impl reference arm times ONE CPU workload on rank 0 whatever N is"
         if world == 1 and not args.no_cpu_baseline:

@@ -7,8 +7,10 @@ from __future__ import annotations
 
 import ctypes as C
 
-FW_ABI_VERSION = 1
+FW_ABI_VERSION = 2
 FW_MAX_KNOTS = 16
+FW_MAX_EXCLUDED = 8
+FW_NO_KEY = 0xFFFFFFFF
 
 # enum fw_status
 FW_OK = 0
@@ -56,7 +58,8 @@ class fw_gradient(C.Structure):
 
 class fw_collision_settings(C.Structure):
     _fields_ = [("enabled", u32), ("restitution", f32), ("friction", f32),
-                ("destroy_on_collision", u32), ("filter_mask", u32)]
+                ("destroy_on_collision", u32), ("filter_mask", u32),
+                ("n_excluded", u32), ("excluded_keys", u32 * FW_MAX_EXCLUDED)]
 
 
 class fw_particle_settings(C.Structure):
@@ -133,7 +136,7 @@ class fw_particle_instance(C.Structure):
 
 
 class fw_collider(C.Structure):
-    _fields_ = [("kind", u32), ("layers", u32), ("half_extents", f32 * 3),
+    _fields_ = [("kind", u32), ("layers", u32), ("key", u32), ("half_extents", f32 * 3),
                 ("translation", f32 * 3), ("rotation", f32 * 4)]
 
 
@@ -195,6 +198,7 @@ EXPORTS = {
     "fw_last_error": (C.c_char_p, [_ctx]),
     "fw_abi_version": (u32, []),
     "fw_abi_sizeof": (u32, [C.c_char_p]),
+    "fw_abi_offsetof": (u32, [C.c_char_p, C.c_char_p]),
     "fw_host_emission_count": (C.c_int, [f32, f32, f32, f32, f32, f32, P(u64), P(f32)]),
     "fw_host_build_broadphase": (C.c_int, [P(fw_collider), u32, C.c_void_p, u64, P(u64)]),
     "fw_device_sincos": (C.c_int, [_ctx, C.c_void_p, u64, C.c_void_p, C.c_void_p]),
@@ -228,6 +232,10 @@ EXPORTS = {
     "fw_profile_sum": (C.c_int, [_ctx, P(fw_frame_profile), P(u32)]),
     "fw_profile_reset": (C.c_int, [_ctx]),
     "fw_extract_instances": (C.c_int, [_ctx, C.c_void_p, u64, P(u64)]),
+    "fw_extract_begin": (C.c_int, [_ctx, P(u32), u32, C.c_void_p, u64]),
+    "fw_extract_wait": (C.c_int, [_ctx, P(u64), P(u64), u32, P(u32)]),
+    "fw_export_instances_fd": (C.c_int, [_ctx, P(i32), P(u64), P(u64)]),
+    "fw_import_instances_fd": (C.c_int, [i32, i32, u64, u64, C.c_void_p]),
     "fw_event_record": (C.c_int, [_ctx, u32]),
     "fw_event_elapsed_ms": (C.c_int, [_ctx, u32, u32, P(f32)]),
     "fw_stream_handle": (C.c_void_p, [_ctx]),

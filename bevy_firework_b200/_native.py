@@ -214,6 +214,27 @@ class Engine:
         self._check(self._L.fw_extract_instances(self._ctx, host_ptr, cap_rows, C.byref(n)))
         return int(n.value)
 
+    def extract_begin(self, host_ptr: int, cap_rows: int, spawner_keys=None):
+        """asynchronous render extract (rows of the listed spawners, or of all) into pinned host memory"""
+        if spawner_keys is None:
+            self._check(self._L.fw_extract_begin(self._ctx, None, 0, host_ptr, cap_rows))
+        else:
+            arr = (C.c_uint32 * max(len(spawner_keys), 1))(*spawner_keys)
+            self._check(self._L.fw_extract_begin(self._ctx, arr, len(spawner_keys), host_ptr, cap_rows))
+
+    def extract_wait(self, cap_streams: int = 0):
+        """-> (rows landed, first row of every listed stream)"""
+        n, ns = C.c_uint64(), C.c_uint32()
+        firsts = (C.c_uint64 * max(cap_streams, 1))()
+        self._check(self._L.fw_extract_wait(self._ctx, C.byref(n), firsts, cap_streams, C.byref(ns)))
+        return int(n.value), [int(firsts[k]) for k in range(min(cap_streams, ns.value))]
+
+    def export_instances_fd(self):
+        """-> (fd, bytes, rows): the packed rows as a POSIX file descriptor of a CUDA VMM allocation"""
+        fd, nbytes, rows = C.c_int32(-1), C.c_uint64(), C.c_uint64()
+        self._check(self._L.fw_export_instances_fd(self._ctx, C.byref(fd), C.byref(nbytes), C.byref(rows)))
+        return int(fd.value), int(nbytes.value), int(rows.value)
+
     # -- multi-GPU render extract over peer memory (fw_gather_*)
     def gather_create(self, n_ranks: int, my_rank: int, cap_rows_per_rank: int) -> bytes:
         """allocate this rank's gather buffer; returns its handle as bytes (send it to the peers)"""

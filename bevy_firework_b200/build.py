@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libfirework_b200.so")
 SOURCES = ["fw_kernels.cu", "fw_api.cu"]
-HEADERS = ["fw_internal.h", "fw_math.cuh", os.path.join("..", "..", "include", "firework_b200.h"),
+HEADERS = ["fw_internal.h", "fw_math.cuh", "fw_abi_offsets.inc", os.path.join("..", "..", "include", "firework_b200.h"),
            os.path.join("..", "..", "include", "fw_sincos.h")]
 
 NVCC_FLAGS = [

@@ -137,6 +137,8 @@ class ParticleCollisionSettings:
     friction: float
     destroy_on_collision: bool = False
     filter: int = 0xFFFFFFFF
+    # SpatialQueryFilter::excluded_entities: keys of colliders (fw_collider.key) the sweep does not see
+    excluded: Sequence[int] = ()
 
 
 @dataclass
@@ -190,6 +192,11 @@ class ParticleSettings:
             pod.collision.friction = float(cs.friction)
             pod.collision.destroy_on_collision = 1 if cs.destroy_on_collision else 0
             pod.collision.filter_mask = int(cs.filter) & 0xFFFFFFFF
+            if len(cs.excluded) > _abi.FW_MAX_EXCLUDED:
+                raise ValueError(f"at most {_abi.FW_MAX_EXCLUDED} excluded colliders per SpatialQueryFilter")
+            pod.collision.n_excluded = len(cs.excluded)
+            for k, key in enumerate(cs.excluded):
+                pod.collision.excluded_keys[k] = int(key) & 0xFFFFFFFF
         pod.capture_destroyed = 1 if self.event_handlers.particles_destroyed is not None else 0
         pod.capacity_hint = int(self.capacity_hint)
         return pod

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstddef>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -159,6 +160,25 @@ struct fw_context {
     unsigned long long *h_pack = nullptr; // pinned
     float4 *d_extract = nullptr;          // staging of fw_extract_instances
     uint64_t extract_cap = 0;
+    // fw_extract_begin / fw_extract_wait: two staging slots alternate; the D2H copies run on xt_stream
+    struct ExtractSlot {
+        float4 *d_rows = nullptr;
+        uint64_t cap_rows = 0;
+        unsigned long long *d_offsets = nullptr, *h_offsets = nullptr; // [0] = n rows, [1 + k] = first row of listed stream k
+        uint32_t offsets_cap = 0;
+        std::vector<uint32_t> slots; // stream slots packed, in order
+        uint32_t *d_slots = nullptr;
+        void *host_dst = nullptr;
+        uint64_t host_cap_rows = 0;
+        cudaEvent_t packed = nullptr, landed = nullptr;
+        bool pending = false;
+    } xt[2];
+    cudaStream_t xt_stream = nullptr;
+    uint64_t xt_issued = 0, xt_waited = 0;
+    // fw_export_instances_fd: a VMM allocation exported as a POSIX file descriptor
+    unsigned long long vmm_handle = 0;
+    unsigned long long vmm_ptr = 0;
+    size_t vmm_bytes = 0;
     // multi-GPU render extract over peer memory (fw_gather_*)
     uint8_t *d_gather = nullptr; // this rank's gather buffer: [GatherHeader | n_ranks regions]
     GatherPeers gather{};        // base[r] = rank r's buffer as mapped here (base[my_rank] = d_gather)
@@ -818,13 +838,24 @@ uint32_t fw_abi_version(void) { return FW_ABI_VERSION; }
 
 uint32_t fw_abi_sizeof(const char *name) {
     if (!name) return 0;
-#define SZ(T) \
+#define FW_S(T) \
     if (!strcmp(name, #T)) return (uint32_t)sizeof(T);
-    SZ(fw_rand_f32) SZ(fw_rand_vec3) SZ(fw_curve_f32) SZ(fw_gradient) SZ(fw_collision_settings)
-    SZ(fw_particle_settings) SZ(fw_emission_settings) SZ(fw_spawner_frame_input) SZ(fw_particle_data)
-    SZ(fw_particle_instance) SZ(fw_collider) SZ(fw_config) SZ(fw_spawner_status) SZ(fw_frame_profile) SZ(fw_gather_handle) SZ(fw_stream_layout)
-#undef SZ
+#define FW_F(T, f)
+#include "fw_abi_offsets.inc"
+#undef FW_S
+#undef FW_F
     return 0;
+}
+
+uint32_t fw_abi_offsetof(const char *struct_name, const char *field_name) {
+    if (!struct_name || !field_name) return 0xFFFFFFFFu;
+#define FW_S(T)
+#define FW_F(T, f) \
+    if (!strcmp(struct_name, #T) && !strcmp(field_name, #f)) return (uint32_t)offsetof(T, f);
+#include "fw_abi_offsets.inc"
+#undef FW_S
+#undef FW_F
+    return 0xFFFFFFFFu;
 }
 
 int fw_create(const fw_config *cfg, fw_context **out_ctx) {
@@ -882,6 +913,9 @@ int fw_create(const fw_config *cfg, fw_context **out_ctx) {
 }
 
 static void gather_release(fw_context *ctx);
+namespace {
+void vmm_release(fw_context *ctx);
+}
 int fw_destroy(fw_context *ctx) {
     if (!ctx) return FW_OK;
     cudaSetDevice(ctx->device);
@@ -924,6 +958,17 @@ int fw_destroy(fw_context *ctx) {
     cudaFree(ctx->d_lookback);
     cudaFree(ctx->d_pack);
     cudaFree(ctx->d_extract);
+    if (ctx->xt_stream) cudaStreamSynchronize(ctx->xt_stream);
+    for (auto &x : ctx->xt) {
+        if (x.d_rows) cudaFree(x.d_rows);
+        if (x.d_offsets) cudaFree(x.d_offsets);
+        if (x.d_slots) cudaFree(x.d_slots);
+        if (x.h_offsets) cudaFreeHost(x.h_offsets);
+        if (x.packed) cudaEventDestroy(x.packed);
+        if (x.landed) cudaEventDestroy(x.landed);
+    }
+    if (ctx->xt_stream) cudaStreamDestroy(ctx->xt_stream);
+    vmm_release(ctx);
     for (auto &ev : ctx->user_events)
         if (ev) cudaEventDestroy(ev);
     if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
@@ -2106,6 +2151,229 @@ int fw_extract_instances(fw_context *ctx, void *host_dst, uint64_t cap_rows, uin
         CU(ctx, sync_all(ctx));
     }
     return FW_OK;
+}
+
+// ---- render hand-off that does not stall the simulation (reference consumer src/render.rs:439-461,
+// upload :568-584): pack on the context's stream, copy on a stream of its own
+int fw_extract_begin(fw_context *ctx, const uint32_t *spawner_keys, uint32_t n_keys, void *host_dst, uint64_t cap_rows) {
+    ENTER(ctx);
+    if ((!host_dst && cap_rows) || (n_keys && !spawner_keys)) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_extract_begin: null argument");
+    if (ctx->xt_issued - ctx->xt_waited >= 2) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_extract_begin: two extracts are outstanding, call fw_extract_wait first");
+    fw_context::ExtractSlot &x = ctx->xt[ctx->xt_issued & 1u];
+    if (!ctx->xt_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->xt_stream, cudaStreamNonBlocking));
+    if (!x.packed) {
+        CU(ctx, cudaEventCreateWithFlags(&x.packed, cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&x.landed, cudaEventDisableTiming));
+    }
+    // which streams: every stream of the listed spawners (all spawners when no list), creation order
+    x.slots.clear();
+    uint64_t bound = 0; // host-side upper bound of the rows, no sync needed
+    auto take = [&](Spawner &sp) {
+        for (Stream &st : sp.streams) {
+            x.slots.push_back(st.slot);
+            bound += std::min<uint64_t>(st.n_hi, st.block.capacity);
+        }
+    };
+    if (spawner_keys) {
+        for (uint32_t k = 0; k < n_keys; k++) {
+            Spawner *sp = find(ctx, spawner_keys[k]);
+            if (!sp) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_extract_begin: unknown spawner %u", spawner_keys[k]);
+            take(*sp);
+        }
+    } else {
+        for (auto &sp : ctx->spawners) take(*sp);
+    }
+    if (bound > cap_rows) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_extract_begin: up to %llu rows, room for %llu", (unsigned long long)bound, (unsigned long long)cap_rows);
+    if (bound > x.cap_rows) {
+        CU(ctx, sync_all(ctx));
+        CU(ctx, cudaStreamSynchronize(ctx->xt_stream));
+        if (x.d_rows) CU(ctx, cudaFree(x.d_rows));
+        x.d_rows = nullptr;
+        x.cap_rows = bound + bound / 8 + 1024;
+        CU(ctx, cudaMalloc((void **)&x.d_rows, x.cap_rows * 64));
+    }
+    if (x.slots.size() + 2 > x.offsets_cap) {
+        CU(ctx, sync_all(ctx));
+        CU(ctx, cudaStreamSynchronize(ctx->xt_stream));
+        if (x.d_offsets) CU(ctx, cudaFree(x.d_offsets));
+        if (x.h_offsets) CU(ctx, cudaFreeHost(x.h_offsets));
+        x.d_offsets = nullptr;
+        x.h_offsets = nullptr;
+        if (x.d_slots) CU(ctx, cudaFree(x.d_slots));
+        x.d_slots = nullptr;
+        x.offsets_cap = (uint32_t)std::max<size_t>(1024, (x.slots.size() + 2) * 2);
+        CU(ctx, cudaMalloc((void **)&x.d_offsets, sizeof(unsigned long long) * x.offsets_cap));
+        CU(ctx, cudaMalloc((void **)&x.d_slots, sizeof(uint32_t) * x.offsets_cap));
+        CU(ctx, cudaMallocHost((void **)&x.h_offsets, sizeof(unsigned long long) * x.offsets_cap));
+    }
+    if (!x.slots.empty()) CU(ctx, cudaMemcpyAsync(x.d_slots, x.slots.data(), sizeof(uint32_t) * x.slots.size(), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        DeviceTables t{};
+        t.descs = ctx->d_descs;
+        t.states = cur_states(ctx);
+        t.settings = ctx->d_settings;
+        CU(ctx, launch_pack_listed(t, x.d_slots, (uint32_t)x.slots.size(), x.d_rows, x.cap_rows, x.d_offsets, ctx->stream));
+    }
+    CU(ctx, cudaEventRecord(x.packed, ctx->stream));
+    // the copies: the row count is only known on the device, so the offsets come first and the rows
+    // are copied up to the host-side bound (rows past the real count are never read by the caller)
+    CU(ctx, cudaStreamWaitEvent(ctx->xt_stream, x.packed, 0));
+    CU(ctx, cudaMemcpyAsync(x.h_offsets, x.d_offsets, sizeof(unsigned long long) * (x.slots.size() + 1), cudaMemcpyDeviceToHost, ctx->xt_stream));
+    if (bound) CU(ctx, cudaMemcpyAsync(host_dst, x.d_rows, bound * 64, cudaMemcpyDeviceToHost, ctx->xt_stream));
+    CU(ctx, cudaEventRecord(x.landed, ctx->xt_stream));
+    // (this slot is packed again two extracts later; by then fw_extract_wait has waited for `landed`)
+    x.host_dst = host_dst;
+    x.host_cap_rows = cap_rows;
+    x.pending = true;
+    ctx->xt_issued++;
+    return FW_OK;
+}
+
+int fw_extract_wait(fw_context *ctx, uint64_t *n_rows, uint64_t *stream_first_rows, uint32_t cap_streams, uint32_t *n_streams) {
+    ENTER(ctx);
+    if (ctx->xt_issued == ctx->xt_waited) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_extract_wait: no extract is outstanding");
+    fw_context::ExtractSlot &x = ctx->xt[ctx->xt_waited & 1u];
+    CU(ctx, cudaEventSynchronize(x.landed));
+    x.pending = false;
+    ctx->xt_waited++;
+    if (n_rows) *n_rows = x.h_offsets[0];
+    if (n_streams) *n_streams = (uint32_t)x.slots.size();
+    if (stream_first_rows)
+        for (uint32_t k = 0; k < cap_streams && k < x.slots.size(); k++) stream_first_rows[k] = x.h_offsets[1 + k];
+    if (x.h_offsets[0] > x.host_cap_rows) return fail(ctx, FW_ERR_BUFFER_TOO_SMALL, "fw_extract_wait: %llu rows, room for %llu", x.h_offsets[0], (unsigned long long)x.host_cap_rows);
+    return FW_OK;
+}
+
+// ---- zero-copy hand-off: the packed rows in a VMM allocation exported as a POSIX file descriptor.
+// The driver entry points are fetched at run time (cudaGetDriverEntryPoint): the library does not link
+// libcuda, so it still loads on a machine without a driver (the `-m "not gpu"` tests).
+namespace {
+struct VmmApi {
+    // (signatures of cuda.h, spelled with plain types)
+    int (*cuMemGetAllocationGranularity)(size_t *, const void *prop, int option) = nullptr;
+    int (*cuMemCreate)(unsigned long long *handle, size_t size, const void *prop, unsigned long long flags) = nullptr;
+    int (*cuMemAddressReserve)(unsigned long long *ptr, size_t size, size_t alignment, unsigned long long addr, unsigned long long flags) = nullptr;
+    int (*cuMemMap)(unsigned long long ptr, size_t size, size_t offset, unsigned long long handle, unsigned long long flags) = nullptr;
+    int (*cuMemSetAccess)(unsigned long long ptr, size_t size, const void *desc, size_t count) = nullptr;
+    int (*cuMemExportToShareableHandle)(void *shareable, unsigned long long handle, int type, unsigned long long flags) = nullptr;
+    int (*cuMemImportFromShareableHandle)(unsigned long long *handle, void *os_handle, int type) = nullptr;
+    int (*cuMemUnmap)(unsigned long long ptr, size_t size) = nullptr;
+    int (*cuMemRelease)(unsigned long long handle) = nullptr;
+    int (*cuMemAddressFree)(unsigned long long ptr, size_t size) = nullptr;
+    bool ok = false;
+};
+// CUmemAllocationProp / CUmemAccessDesc of cuda.h (CUDA 12): restated so that cuda.h is not needed
+struct VmmLocation { int type; int id; };                       // CU_MEM_LOCATION_TYPE_DEVICE = 1
+struct VmmAllocFlags { unsigned char compressionType, gpuDirectRDMACapable; unsigned short usage; unsigned char reserved[4]; };
+struct VmmProp { int type; int requestedHandleTypes; VmmLocation location; void *win32HandleMetaData; VmmAllocFlags allocFlags; }; // type: PINNED = 1; handle type POSIX_FD = 1
+struct VmmAccessDesc { VmmLocation location; int flags; };      // CU_MEM_ACCESS_FLAGS_PROT_READWRITE = 3
+const VmmApi &vmm_api() {
+    static VmmApi api = [] {
+        VmmApi a;
+        auto get = [](const char *name, void **fn) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+        };
+        a.ok = get("cuMemGetAllocationGranularity", (void **)&a.cuMemGetAllocationGranularity) && get("cuMemCreate", (void **)&a.cuMemCreate) &&
+               get("cuMemAddressReserve", (void **)&a.cuMemAddressReserve) && get("cuMemMap", (void **)&a.cuMemMap) &&
+               get("cuMemSetAccess", (void **)&a.cuMemSetAccess) && get("cuMemExportToShareableHandle", (void **)&a.cuMemExportToShareableHandle) &&
+               get("cuMemImportFromShareableHandle", (void **)&a.cuMemImportFromShareableHandle) && get("cuMemUnmap", (void **)&a.cuMemUnmap) &&
+               get("cuMemRelease", (void **)&a.cuMemRelease) && get("cuMemAddressFree", (void **)&a.cuMemAddressFree);
+        (void)cudaGetLastError();
+        return a;
+    }();
+    return api;
+}
+VmmProp vmm_prop(int device) {
+    VmmProp p;
+    memset(&p, 0, sizeof(p));
+    p.type = 1;                 // CU_MEM_ALLOCATION_TYPE_PINNED
+    p.requestedHandleTypes = 1; // CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+    p.location.type = 1;        // CU_MEM_LOCATION_TYPE_DEVICE
+    p.location.id = device;
+    return p;
+}
+void vmm_release(fw_context *ctx) {
+    const VmmApi &a = vmm_api();
+    if (ctx->vmm_ptr && a.ok) {
+        a.cuMemUnmap(ctx->vmm_ptr, ctx->vmm_bytes);
+        a.cuMemAddressFree(ctx->vmm_ptr, ctx->vmm_bytes);
+        a.cuMemRelease(ctx->vmm_handle);
+    }
+    ctx->vmm_ptr = 0;
+    ctx->vmm_handle = 0;
+    ctx->vmm_bytes = 0;
+}
+} // namespace
+
+int fw_export_instances_fd(fw_context *ctx, int32_t *fd, uint64_t *bytes, uint64_t *n_rows) {
+    ENTER(ctx);
+    if (!fd) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_export_instances_fd: null");
+    const VmmApi &a = vmm_api();
+    if (!a.ok) return fail(ctx, FW_ERR_UNSUPPORTED, "fw_export_instances_fd: the driver does not expose the virtual-memory API");
+    int rc = refresh_exact(ctx);
+    if (rc) return rc;
+    uint64_t rows = 0;
+    for (auto &sp : ctx->spawners)
+        for (Stream &st : sp->streams) rows += st.n_hi;
+    const VmmProp prop = vmm_prop(ctx->device);
+    size_t gran = 0;
+    if (a.cuMemGetAllocationGranularity(&gran, &prop, 0 /* MINIMUM */) != 0 || gran == 0) return fail(ctx, FW_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+    const size_t need = ((std::max<uint64_t>(rows, 1) * 64 + gran - 1) / gran) * gran;
+    CU(ctx, sync_all(ctx));
+    vmm_release(ctx);
+    if (a.cuMemCreate(&ctx->vmm_handle, need, &prop, 0) != 0) return fail(ctx, FW_ERR_OUT_OF_MEMORY, "cuMemCreate(%zu bytes, POSIX fd handle) failed", need);
+    if (a.cuMemAddressReserve(&ctx->vmm_ptr, need, 0, 0, 0) != 0) {
+        a.cuMemRelease(ctx->vmm_handle);
+        ctx->vmm_handle = 0;
+        ctx->vmm_ptr = 0;
+        return fail(ctx, FW_ERR_CUDA, "cuMemAddressReserve failed");
+    }
+    ctx->vmm_bytes = need;
+    VmmAccessDesc acc;
+    acc.location = prop.location;
+    acc.flags = 3;
+    if (a.cuMemMap(ctx->vmm_ptr, need, 0, ctx->vmm_handle, 0) != 0 || a.cuMemSetAccess(ctx->vmm_ptr, need, &acc, 1) != 0) {
+        vmm_release(ctx);
+        return fail(ctx, FW_ERR_CUDA, "cuMemMap / cuMemSetAccess failed");
+    }
+    uint64_t n = 0;
+    rc = fw_pack_instances_device(ctx, (void *)(uintptr_t)ctx->vmm_ptr, need / 64, &n);
+    if (rc) return rc;
+    int os_fd = -1;
+    if (a.cuMemExportToShareableHandle(&os_fd, ctx->vmm_handle, 1, 0) != 0 || os_fd < 0) return fail(ctx, FW_ERR_CUDA, "cuMemExportToShareableHandle failed");
+    *fd = os_fd;
+    if (bytes) *bytes = need;
+    if (n_rows) *n_rows = n;
+    return FW_OK;
+}
+
+int fw_import_instances_fd(int32_t device, int32_t fd, uint64_t bytes, uint64_t n_rows, void *host_dst) {
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, FW_ERR_NO_DEVICE, "fw_import_instances_fd: cudaSetDevice(%d) failed", device);
+    cudaFree(nullptr); // make sure the primary context exists
+    const VmmApi &a = vmm_api();
+    if (!a.ok) return fail(nullptr, FW_ERR_UNSUPPORTED, "fw_import_instances_fd: the driver does not expose the virtual-memory API");
+    if (n_rows * 64 > bytes || (n_rows && !host_dst)) return fail(nullptr, FW_ERR_INVALID_ARGUMENT, "fw_import_instances_fd: %llu rows do not fit %llu bytes", (unsigned long long)n_rows, (unsigned long long)bytes);
+    unsigned long long handle = 0, ptr = 0;
+    if (a.cuMemImportFromShareableHandle(&handle, (void *)(uintptr_t)fd, 1) != 0) return fail(nullptr, FW_ERR_CUDA, "cuMemImportFromShareableHandle failed");
+    int rc = FW_OK;
+    if (a.cuMemAddressReserve(&ptr, bytes, 0, 0, 0) != 0) {
+        a.cuMemRelease(handle);
+        return fail(nullptr, FW_ERR_CUDA, "cuMemAddressReserve failed");
+    }
+    VmmAccessDesc acc;
+    acc.location.type = 1;
+    acc.location.id = device;
+    acc.flags = 3;
+    if (a.cuMemMap(ptr, bytes, 0, handle, 0) != 0 || a.cuMemSetAccess(ptr, bytes, &acc, 1) != 0) {
+        rc = fail(nullptr, FW_ERR_CUDA, "cuMemMap / cuMemSetAccess of the imported allocation failed");
+    } else if (n_rows && cudaMemcpy(host_dst, (void *)(uintptr_t)ptr, n_rows * 64, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        rc = fail(nullptr, FW_ERR_CUDA, "copy from the imported allocation failed");
+    }
+    a.cuMemUnmap(ptr, bytes);
+    a.cuMemAddressFree(ptr, bytes);
+    a.cuMemRelease(handle);
+    return rc;
 }
 
 // ---- multi-GPU render extract over NVLink peer memory (reference consumer

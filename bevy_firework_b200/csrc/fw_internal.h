@@ -103,13 +103,13 @@ struct alignas(16) DevParticleSettings {
     float linear_drag;
     float angular_acceleration[3];
     float angular_drag;
-    fw_collision_settings collision; // 20 B
+    fw_collision_settings collision; // 56 B
     // spawn-only
     fw_rand_f32 lifetime;
     fw_rand_f32 initial_scale;
     // per-stream constants standing in for packs the stream does not keep (see the layout above)
     float const_lifetime;    // lifetime.generate() when min == max
-    uint32_t pad[2];
+    uint32_t pad[1];
     float const_rotation[4]; // fixed point of from_scaled_axis(0) * initial_rotation
 };
 static_assert(sizeof(DevParticleSettings) % 16 == 0, "bulk copy needs a 16-byte multiple");
@@ -351,6 +351,9 @@ cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, ui
                                   uint64_t cap_rows, unsigned long long *n_rows_and_offsets, cudaStream_t s);
 cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, const PackDst &dst,
                                   uint64_t cap_rows, unsigned long long *n_rows_and_offsets, cudaStream_t s);
+// the same for the streams d_slot_list[0 .. n) (device array): render extract of a subset of the spawners
+cudaError_t launch_pack_listed(const DeviceTables &t, const uint32_t *d_slot_list, uint32_t n, float4 *dst, uint64_t cap_rows,
+                               unsigned long long *n_rows_and_offsets, cudaStream_t s);
 cudaError_t launch_gather_signal(const GatherPeers &p, uint32_t which, unsigned long long epoch, const unsigned long long *rows_src,
                                  unsigned long long timeout_ns, cudaStream_t s);
 // one stream <-> fw_particle_data rows (host mirror / fw_write_particles); d.base may be the stream's

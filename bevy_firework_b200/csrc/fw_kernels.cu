@@ -16,6 +16,7 @@
 // Built with -fmad=false (see fw_math.cuh).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "fw_math.cuh"
 
@@ -29,8 +30,9 @@
 #ifndef FW_MINB_STATIC
 // static FIFO streams (32 B read + 48 B written per particle): half the bytes in flight per thread,
 // so more resident threads are asked for
-#define FW_MINB_STATIC 6
+#define FW_MINB_STATIC 5
 #endif
+
 #ifndef FW_MINB_COMPACT
 #define FW_MINB_COMPACT 4 // 64 registers; C3r (precounted path): 4 CTAs/SM 0.412 ms, 5 (48 regs, spills) 0.421 ms, 6 0.468 ms
 #endif
@@ -651,6 +653,16 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
         : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef FW_PREFETCH
+#define FW_PREFETCH 0 // static update: 0 none (measured best), 1 prefetch.global.L1, 2 prefetch.global.L2
+#endif
+__device__ __forceinline__ void prefetch_pack(const void *p) {
+#if FW_PREFETCH == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -693,6 +705,23 @@ __device__ __forceinline__ TileRef find_tile(const uint32_t *__restrict__ prefix
     }
     return TileRef{lo, tile - prefix[lo], 0u, 0u};
 }
+// find_tile by a whole warp: 32-ary search, one round of loads per factor 32 of the table (the
+// binary search above is ~9 dependent loads for 512 streams: microseconds on the critical path of a
+// CTA that starts a new stream segment). Every lane of the warp must call; all return the result.
+__device__ __forceinline__ TileRef find_tile_warp(const uint32_t *__restrict__ prefix, uint32_t n_slots, uint32_t tile) {
+    const uint32_t lane = lane_id();
+    uint32_t lo = 0, n = n_slots; // answer in [lo, lo + n): the last s with prefix[s] <= tile
+    while (n > 1u) {
+        const uint32_t step = (n + 31u) / 32u;
+        const uint32_t s = lo + lane * step;
+        const bool le = lane * step < n && prefix[s] <= tile;
+        const uint32_t m = __ballot_sync(0xffffffffu, le); // lanes 0..k (prefix is non-decreasing)
+        const uint32_t k = m ? 31u - (uint32_t)__clz((int)m) : 0u;
+        lo += k * step;
+        n = min(step, n - k * step);
+    }
+    return TileRef{lo, tile - prefix[lo], 0u, 0u};
+}
 // the stream, ring head and particle count behind update tile `tile` (no side effects)
 __device__ __forceinline__ TileRef resolve_tile(const DeviceTables &t, const FrameDeviceInputs &f, const uint32_t *prefix,
                                                 uint32_t n_slots, uint32_t tile, bool derive) {
@@ -711,9 +740,12 @@ __device__ __forceinline__ TileRef resolve_tile(const DeviceTables &t, const Fra
 }
 // thread 0 of a CTA: everything the CTA needs to know about an upcoming tile. On the derive
 // path the first tile of a stream also publishes the stream's state for this frame.
+__device__ __forceinline__ TileRef prepare_found_tile(const DeviceTables &t, const FrameDeviceInputs &f, TileRef r, bool derive);
 __device__ __forceinline__ TileRef prepare_tile(const DeviceTables &t, const FrameDeviceInputs &f, const uint32_t *prefix,
                                                 uint32_t n_slots, uint32_t tile, bool derive) {
-    TileRef r = find_tile(prefix, n_slots, tile);
+    return prepare_found_tile(t, f, find_tile(prefix, n_slots, tile), derive);
+}
+__device__ __forceinline__ TileRef prepare_found_tile(const DeviceTables &t, const FrameDeviceInputs &f, TileRef r, bool derive) {
     StreamState *stp = &t.states[r.stream];
     if (derive) {
         const StreamState old = t.states_prev[r.stream];
@@ -1135,13 +1167,225 @@ __global__ void __launch_bounds__(kUpdateThreads, COLLIDE ? FW_MINB_COLLIDE : (C
 }
 
 // ------------------------------------------------------------------------------------------
+// The fused per-frame update of STATIC streams without a collision sweep (FIFO rings and compaction
+// with precounted deaths) -- C1..C4 of BASELINE.json. A static stream moves 32 B in and 48 B out per
+// particle instead of 64 + 92, so what bounds the tile-scheduled update_kernel above (0.94 of the HBM
+// peak on a rotating stream) is no longer memory: ncu on C3 showed 335 warp instructions per 32
+// particles and the issue slots 62 % busy (profiles/r2/c_c3_static_tile_schedule_ncu.txt). Same
+// per-particle arithmetic (src/core.rs:591-658 in the reference's order), another schedule:
+//   * a CTA takes GROUPS of consecutive tiles, so consecutive tiles belong to the same stream: the
+//     stream lookup, the ring geometry and all addressing are done once per stream segment, not
+//     once per tile;
+//   * there is no CTA-wide barrier and no shared memory at all: the 8 warps of a CTA free-run, each
+//     looks its segment up itself and reads the per-stream settings through the read-only path;
+//   * the per-stream AABB (src/render.rs:681-692) and the FIFO death count are accumulated in
+//     registers over the whole segment and reduced (REDUX + atomics) once at its end;
+//   * outputs the stream does not keep (constant gradients) are not evaluated; the knot interval of
+//     the colour gradient is carried from tile to tile (ages along a ring change slowly) and only
+//     re-searched when it no longer brackets the particle's age.
+// FireworkGradient::sample_clamped as sample_gradient (fw_math.cuh), with the uneven core's knot
+// search started from the interval the previous call found (same result: the first knot that is
+// not < t is unique)
+__device__ __forceinline__ float4 sample_gradient_hint(const DevGradient &g, float t, uint32_t &hint) {
+    const float4 *colors = g.colors;
+    if (g.kind == FW_CURVE_CONSTANT) return colors[0];
+    t = clamp01(t);
+    Interp it;
+    if (g.kind == FW_CURVE_EVEN) {
+        it = even_interp(g.n, t);
+    } else {
+        const uint32_t n = g.n;
+        uint32_t idx = hint;
+        const bool ok = (idx == 0u || g.times[idx - 1u] < t) && (idx >= n || !(g.times[idx] < t));
+        if (!ok) {
+            idx = 0;
+            while (idx < n && g.times[idx] < t) idx++;
+        }
+        hint = idx;
+        it = Interp{0u, 0u, 0.0f, false};
+        if (idx < n && g.times[idx] == t) {
+            it.lo = idx;
+        } else if (idx == 0u) {
+        } else if (idx >= n) {
+            it.lo = n - 1u;
+        } else {
+            const float t_lower = g.times[idx - 1u], t_upper = g.times[idx];
+            it.lo = idx - 1u;
+            it.hi = idx;
+            it.s = (t - t_lower) / (t_upper - t_lower);
+            it.between = true;
+        }
+    }
+    const float4 a = colors[it.lo];
+    if (!it.between) return a;
+    const float4 b = colors[it.hi];
+    const float nf = 1.0f - it.s;
+    return make_float4(a.x * nf + b.x * it.s, a.y * nf + b.y * it.s, a.z * nf + b.z * it.s, a.w * nf + b.w * it.s);
+}
+template <bool COMPACT>
+__global__ void __launch_bounds__(kUpdateThreads, COMPACT ? FW_MINB_COMPACT : FW_MINB_STATIC)
+    update_static_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t variant, uint32_t group_tiles) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const bool derive = f.header->derive != 0u;
+    const uint32_t all_tiles = derive ? f.header->host_n_tiles[variant] : t.plan->n_tiles[variant];
+    const uint32_t n_slots = f.header->n_slots;
+    const uint32_t *prefix = derive ? f.host_tile_prefix + (size_t)variant * (n_slots + 1u)
+                                    : t.tile_prefix + (size_t)variant * (t.slots_cap + 1u);
+    // Tile order: groups of G consecutive tiles are dealt round robin to the CTAs, so that at any time
+    // the grid sweeps one moving window of the particle arrays while a warp still stays inside one
+    // stream for a whole group (never fewer groups than CTAs: a small scene spreads over the grid).
+    // There is NO CTA-wide barrier and no shared memory: every warp looks its group's stream up itself
+    // (32-ary search, two rounds of loads for 512 streams) and reads the per-stream settings through
+    // the read-only path -- warp-uniform loads that hit in L1 after the first tile.
+    const uint32_t share = max(1u, (all_tiles + gridDim.x - 1u) / gridDim.x);
+    const uint32_t G = group_tiles ? min(group_tiles, share) : share;
+    const uint32_t tile_base = derive ? f.header->host_tile_base[variant] : t.plan->tile_base[variant];
+    const float dt = f.header->dt;
+    const float kInf = __int_as_float(0x7f800000);
+    for (uint64_t g0 = (uint64_t)blockIdx.x * G; g0 < all_tiles; g0 += (uint64_t)gridDim.x * G) {
+        uint32_t tile = (uint32_t)g0;
+        const uint32_t tile_end = (uint32_t)min((uint64_t)all_tiles, g0 + G);
+        while (tile < tile_end) {
+            // ---- a segment: the tiles [tile, seg_end) of one stream
+            TileRef e = find_tile_warp(prefix, n_slots, tile);
+            if (warp == 0u && lane == 0u) {
+                e = prepare_found_tile(t, f, e, derive); // (publishes the stream's state with its tile 0)
+            } else if (derive) {
+                const Derived dv = derive_state(t.states_prev[e.stream], t.descs[e.stream], f.spawn_per_slot[e.stream]);
+                e.head = dv.head;
+                e.n_update = f.header->step_in_spawn ? dv.c0 : dv.n_update; // (see resolve_tile)
+            }
+            if (!derive) { // the plan kernel wrote this frame's state already
+                e.head = t.states[e.stream].head;
+                e.n_update = t.states[e.stream].count;
+            }
+            e.head = __shfl_sync(0xffffffffu, e.head, 0);
+            e.n_update = __shfl_sync(0xffffffffu, e.n_update, 0);
+            const uint32_t seg_end = min(tile_end, prefix[e.stream + 1u]);
+            const StreamDesc d = t.descs[e.stream];
+            StreamState *stp = &t.states[e.stream];
+            // pack addresses from ONE base pointer: pack p of slot s sits at base + cap16 * (16-byte units of
+            // the pack's offset) + s * element size (fw_internal.h) -- eight hoisted 64-bit pointers would
+            // not fit the register budget of 5 CTAs per SM
+            uint8_t *const base = d.base;
+            const size_t cap16 = (size_t)d.capacity * 16u;
+            const DevParticleSettings &ps = t.settings[e.stream];
+            const uint32_t head = e.head, n_update = e.n_update, flags = d.flags, cap = d.capacity;
+            // FIFO rings: tiles are aligned to the ring's physical slots, not to the logical index --
+            // the head moves by an arbitrary count every frame, and a warp whose 32 slots start at a
+            // multiple of 32 touches 4 full 128-byte lines per float4 pack instead of straddling 5
+            // (the first `shift` lanes of a stream's tile 0 idle). q = offset from the aligned head:
+            // a particle's logical index is q - shift, it exists iff shift <= q < q_end.
+            const uint32_t shift = head & 31u, head_aligned = head - shift, q_end = n_update + shift;
+            // compacting rings: the survivors go OUT OF PLACE, behind the particles this frame reads
+            // (usable_capacity keeps the ring half empty); the death counts in front of every tile /
+            // warp were taken by count_kernel / scan_kernel
+            const uint32_t dst_base = wrap(head + n_update, cap);
+            const bool klife = (flags & kStoreLife) != 0u;
+
+            float mn0 = kInf, mn1 = kInf, mn2 = kInf, mx0 = -kInf, mx1 = -kInf, mx2 = -kInf; // AABB of this thread's survivors
+            uint32_t n_alive = 0, n_dead = 0, hint = 0;
+            uint32_t q = e.tile * (uint32_t)kTile + tid;
+            for (; tile < seg_end; tile++, q += (uint32_t)kTile) {
+                if (q - tid >= q_end) { // tiles past the stream's real count (the host's tile table holds upper bounds)
+                    tile = seg_end;
+                    break;
+                }
+                const bool valid = q >= shift && q < q_end;
+                uint32_t slot = head_aligned + q;
+                if (slot >= cap) slot -= cap;
+                // ---- loads: 32 B per particle (+ 8 B when the lifetime varies)
+                float4 A = make_float4(0.f, 0.f, 0.f, 0.f), V = A;
+                float2 K = make_float2(1.f, 0.f);
+                uint8_t *const row = base + (size_t)slot * 16u; // m0[slot]
+                if (valid) {
+                    A = ld_pack((const float4 *)row);
+                    V = ld_pack((const float4 *)(row + 2u * cap16));
+                    if (klife) K = ld_pack((const float2 *)(base + 3u * cap16 + cap16 / 2u) + slot);
+                }
+                unsigned long long pre_tile = 0, pre_warps = 0;
+                if (COMPACT) {
+                    pre_tile = t.lookback[tile_base + tile];
+                    pre_warps = t.lookback[t.lookback_capacity + tile_base + tile];
+                }
+                // ---- reference src/core.rs:591-658 for a static stream (rotation and angular velocity
+                // are per-stream constants that :645-650 map to themselves)
+                const float lifetime = klife ? K.x : ps.const_lifetime, iscale = V.w;
+                const float age = A.w + dt;                      // :594
+                const bool alive = valid && !(age >= lifetime);  // :596-599
+                uint32_t dslot = slot;
+                if (COMPACT) {
+                    const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
+                    const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
+                    const uint32_t excl = (uint32_t)pre_tile + (warp ? (uint32_t)(pre_warps >> (8u * (warp - 1u))) & 255u : 0u);
+                    const uint32_t dead_before = excl + __popc(valid_mask & ~alive_mask & ((1u << lane) - 1u));
+                    dslot = wrap(dst_base + ((q - shift) - dead_before), cap);
+                } else {
+                    n_dead += (valid && !alive) ? 1u : 0u;
+                }
+                if (alive) {
+                    const float age_percent = age / lifetime;                                // :601
+                    const float scale = iscale * sample_curve(ps.scale_curve, age_percent);  // :602-605
+                    const V3 vel = v3(V.x, V.y, V.z);
+                    const V3 pos = v3(A.x, A.y, A.z) + vel * dt;                             // :619-623
+                    const V3 acc = v3(ps.acceleration[0], ps.acceleration[1], ps.acceleration[2]);
+                    const V3 nvel = vel + (acc - vel * ps.linear_drag) * dt;                 // :641-643
+                    // ---- stores: 28 B + the colours / scale that vary (+ 8 B when the lifetime does)
+                    uint8_t *const drow = COMPACT ? base + (size_t)dslot * 16u : row;
+                    st_pack((float4 *)drow, make_float4(pos.x, pos.y, pos.z, age));
+                    st_pack((float4 *)(drow + 2u * cap16), make_float4(nvel.x, nvel.y, nvel.z, iscale));
+                    if (klife) st_pack((float2 *)(base + 3u * cap16 + cap16 / 2u) + dslot, make_float2(lifetime, age)); // (lifetime, copy of age): what count_kernel reads
+                    if (COMPACT) // last_emitted_age moves with the particle (out of place: the source is still intact)
+                        for (uint32_t j = 0; j < d.n_lea; j++) lea_array(d.base, cap, j)[dslot] = lea_array(d.base, cap, j)[slot];
+                    if (flags & kStoreBase) st_pack((float4 *)(drow + 4u * cap16), sample_gradient_hint(ps.base_color, age_percent, hint)); // :652-653
+                    if (flags & kStoreEmi) st_pack((float4 *)(drow + 5u * cap16), sample_gradient(ps.emissive_color, age_percent));         // :654-655
+                    if (flags & kStoreScale) st_pack((float *)(base + 6u * cap16) + dslot, scale);
+                    // AABB of position -/+ scale (reference src/render.rs:681-692; fminf / fmaxf like it)
+                    mn0 = fminf(mn0, pos.x - scale);
+                    mn1 = fminf(mn1, pos.y - scale);
+                    mn2 = fminf(mn2, pos.z - scale);
+                    mx0 = fmaxf(mx0, pos.x + scale);
+                    mx1 = fmaxf(mx1, pos.y + scale);
+                    mx2 = fmaxf(mx2, pos.z + scale);
+                    n_alive++;
+                }
+            }
+            // ---- end of the segment: one reduction per warp
+            const uint32_t warp_alive = __reduce_add_sync(0xffffffffu, n_alive);
+            if (!COMPACT) {
+                const uint32_t warp_dead = __reduce_add_sync(0xffffffffu, n_dead);
+                if (lane == 0 && warp_dead) atomicAdd(&stp->dead, warp_dead);
+            }
+            if (warp_alive) {
+                uint32_t lo[3], hi[3];
+                lo[0] = __reduce_min_sync(0xffffffffu, enc_f32(mn0));
+                lo[1] = __reduce_min_sync(0xffffffffu, enc_f32(mn1));
+                lo[2] = __reduce_min_sync(0xffffffffu, enc_f32(mn2));
+                hi[0] = __reduce_max_sync(0xffffffffu, enc_f32(mx0));
+                hi[1] = __reduce_max_sync(0xffffffffu, enc_f32(mx1));
+                hi[2] = __reduce_max_sync(0xffffffffu, enc_f32(mx2));
+                if (lane < 3u) { // zero = empty, so the minimum is kept as the max of the inverted encoding
+                    const uint32_t lo_inv = ~(lane == 0 ? lo[0] : (lane == 1 ? lo[1] : lo[2]));
+                    const uint32_t h = lane == 0 ? hi[0] : (lane == 1 ? hi[1] : hi[2]);
+                    if (lo_inv > stp->aabb_min_inv[lane]) atomicMax(&stp->aabb_min_inv[lane], lo_inv);
+                    if (h > stp->aabb_max[lane]) atomicMax(&stp->aabb_max[lane], h);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // pack: live ParticleInstance rows of the streams [slot_begin, slot_end), creation order, Vec
 // order inside a stream. out[0] = total rows, out[1 + k] = first row of stream slot_begin + k.
-__global__ void pack_prefix_kernel(DeviceTables t, uint32_t slot_begin, uint32_t slot_end, unsigned long long *out) {
+// slot_list != nullptr: the streams slot_list[slot_begin .. slot_end) instead of the slots themselves
+// (render extract of a subset of the spawners)
+__global__ void pack_prefix_kernel(DeviceTables t, const uint32_t *slot_list, uint32_t slot_begin, uint32_t slot_end, unsigned long long *out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long acc = 0;
-        for (uint32_t s = slot_begin; s < slot_end; s++) {
-            out[1 + (s - slot_begin)] = acc;
+        for (uint32_t k = slot_begin; k < slot_end; k++) {
+            const uint32_t s = slot_list ? slot_list[k] : k;
+            out[1 + (k - slot_begin)] = acc;
             if (t.descs[s].capacity) acc += t.states[s].count - t.states[s].dead;
         }
         out[0] = acc;
@@ -1150,10 +1394,10 @@ __global__ void pack_prefix_kernel(DeviceTables t, uint32_t slot_begin, uint32_t
 // PackDst: where the rows go -- one caller buffer, or (multi-GPU render extract) this rank's
 // region of the gather buffer of EVERY rank: peer buffers are mapped over NVLink, so the all-gather
 // is just these stores (one HBM read, n_dst coalesced 16-byte writes per chunk).
-__global__ void __launch_bounds__(256) pack_copy_kernel(DeviceTables t, uint32_t slot_begin, uint32_t slot_end,
+__global__ void __launch_bounds__(256) pack_copy_kernel(DeviceTables t, const uint32_t *slot_list, uint32_t slot_begin, uint32_t slot_end,
                                                         const unsigned long long *offsets, PackDst dst, uint64_t cap_rows) {
-    const uint32_t s = slot_begin + blockIdx.y;
-    if (s >= slot_end) return;
+    if (slot_begin + blockIdx.y >= slot_end) return;
+    const uint32_t s = slot_list ? slot_list[slot_begin + blockIdx.y] : slot_begin + blockIdx.y;
     const StreamDesc d = t.descs[s];
     if (d.capacity == 0u) return;
     const StreamState st = t.states[s];
@@ -1310,12 +1554,25 @@ cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uin
     nested_spawn_kernel<<<dim3(gx, n_cmds), 256, 0, s>>>(t, f, phase);
     return cudaGetLastError();
 }
+#ifndef FW_GROUP_TILES
+#define FW_GROUP_TILES 8
+#endif
+// tiles per group of the static update (see update_static_kernel); FW_GROUP_TILES in the environment
+// overrides the built-in value (tuning runs)
+static uint32_t group_tiles_setting() {
+    static const uint32_t v = [] {
+        const char *e = getenv("FW_GROUP_TILES");
+        return e ? (uint32_t)strtoul(e, nullptr, 10) : (uint32_t)FW_GROUP_TILES;
+    }();
+    return v;
+}
 template <bool COMPACT, bool ROT>
 static void launch_update_t(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, uint32_t ts, int collide,
                             cudaStream_t s) {
     if (collide == 2) update_kernel<COMPACT, 2, ROT><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
     else if (collide == 1) update_kernel<COMPACT, 1, ROT><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
-    else update_kernel<COMPACT, 0, ROT><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
+    else if constexpr (ROT) update_kernel<COMPACT, 0, true><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, ts);
+    else update_static_kernel<COMPACT><<<grid, kUpdateThreads, 0, s>>>(t, f, variant, group_tiles_setting()); // static, no sweep: C1..C4
 }
 cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, int grid, int team_size, bool revolved,
                           cudaStream_t s) {
@@ -1345,8 +1602,8 @@ cudaError_t update_grid_size(int device, int *grids, int *team_size) {
 #define FW_OCC(v, K) \
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[v], K, kUpdateThreads, 0); \
     if (e != cudaSuccess) return e;
-    FW_OCC(kFifo, (update_kernel<false, 0, false>))
-    FW_OCC(kCompact, (update_kernel<true, 0, false>))
+    FW_OCC(kFifo, (update_static_kernel<false>))
+    FW_OCC(kCompact, (update_static_kernel<true>))
     FW_OCC(kFifoCollide, (update_kernel<false, 2, false>))
     FW_OCC(kCompactCollide, (update_kernel<true, 2, false>))
     FW_OCC(kFifo | kVarRot, (update_kernel<false, 0, true>))
@@ -1360,17 +1617,28 @@ cudaError_t update_grid_size(int device, int *grids, int *team_size) {
     *team_size = sms; // one CTA slot of every SM (see update_kernel)
     return cudaSuccess;
 }
-cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, const PackDst &dst,
-                                  uint64_t cap_rows, unsigned long long *out, cudaStream_t s) {
-    pack_prefix_kernel<<<1, 32, 0, s>>>(t, slot_begin, slot_end, out);
+static cudaError_t launch_pack_any(const DeviceTables &t, const uint32_t *slot_list, uint32_t slot_begin, uint32_t slot_end, const PackDst &dst,
+                                   uint64_t cap_rows, unsigned long long *out, cudaStream_t s) {
+    pack_prefix_kernel<<<1, 32, 0, s>>>(t, slot_list, slot_begin, slot_end, out);
     if (slot_end > slot_begin) {
         const uint32_t n = slot_end - slot_begin;
         for (uint32_t y0 = 0; y0 < n; y0 += 32768u) { // gridDim.y limit is 65535
             dim3 grid(n == 1 ? 1184 : 16, std::min(32768u, n - y0));
-            pack_copy_kernel<<<grid, 256, 0, s>>>(t, slot_begin + y0, slot_end, out + y0, dst, cap_rows);
+            pack_copy_kernel<<<grid, 256, 0, s>>>(t, slot_list, slot_begin + y0, slot_end, out + y0, dst, cap_rows);
         }
     }
     return cudaGetLastError();
+}
+cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, const PackDst &dst,
+                                  uint64_t cap_rows, unsigned long long *out, cudaStream_t s) {
+    return launch_pack_any(t, nullptr, slot_begin, slot_end, dst, cap_rows, out, s);
+}
+cudaError_t launch_pack_listed(const DeviceTables &t, const uint32_t *d_slot_list, uint32_t n, float4 *dst, uint64_t cap_rows,
+                               unsigned long long *out, cudaStream_t s) {
+    PackDst d{};
+    d.rows[0] = dst;
+    d.n = 1;
+    return launch_pack_any(t, d_slot_list, 0, n, d, cap_rows, out, s);
 }
 cudaError_t launch_pack_instances(const DeviceTables &t, uint32_t slot_begin, uint32_t slot_end, float4 *dst,
                                   uint64_t cap_rows, unsigned long long *out, cudaStream_t s) {

@@ -379,8 +379,9 @@ constexpr uint32_t kCandQueue = 4;
 __device__ __forceinline__ float grid_coord(float x, float lo, float inv_cell) { return floorf((x - lo) * inv_cell); }
 template <bool REVOLVED>
 __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ colliders, const uint8_t *__restrict__ bp,
-                                         uint32_t filter_mask, bool act, V3 o, V3 d, float max_distance, uint32_t *queue,
+                                         const fw_collision_settings &cs, bool act, V3 o, V3 d, float max_distance, uint32_t *queue,
                                          float &distance, V3 &normal) {
+    const uint32_t filter_mask = cs.filter_mask;
     if (bp == nullptr) { // no collider set was ever uploaded
         distance = 0.0f;
         normal = v3(0.0f, 0.0f, 0.0f);
@@ -492,6 +493,8 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
                 else if (REVOLVED && c.kind == FW_COLLIDER_CYLINDER) hit = ray_frustum_local(c.half_extents[0], c.half_extents[0], c.half_extents[1], ol, dl, max_distance, toi, nl);
                 else if (REVOLVED && c.kind == FW_COLLIDER_CONE) hit = ray_frustum_local(c.half_extents[0], 0.0f, c.half_extents[1], ol, dl, max_distance, toi, nl);
                 else hit = ray_cuboid_local(v3(c.half_extents[0], c.half_extents[1], c.half_extents[2]), ol, dl, max_distance, toi, nl);
+                // SpatialQueryFilter::excluded_entities (src/core.rs:247,764): a listed collider is not seen
+                for (uint32_t x = 0; x < cs.n_excluded; x++) hit = hit && cs.excluded_keys[x] != c.key;
                 if (hit && (!found || toi < best || (toi == best && cand < best_i))) {
                     found = true;
                     best = toi;
@@ -522,7 +525,7 @@ __device__ __forceinline__ void particle_collision(const fw_collider *__restrict
         V3 dir = (isfinite(len) && len > 0.0f) ? vel / len : v3(0.0f, 1.0f, 0.0f);
         float distance;
         V3 hit_normal;
-        const bool hit = cast_ray<REVOLVED>(colliders, broadphase, cs.filter_mask, go, pos, dir, length(vel) * delta, queue, distance, hit_normal);
+        const bool hit = cast_ray<REVOLVED>(colliders, broadphase, cs, go, pos, dir, length(vel) * delta, queue, distance, hit_normal);
         if (go) {
             if (hit) {
                 if (distance == 0.0f) {

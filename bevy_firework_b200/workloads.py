@@ -140,21 +140,23 @@ def quat_mul(a, b):
             aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz)
 
 
-def cuboid(size, translation, rotation=(0.0, 0.0, 0.0, 1.0), layers: int = 1) -> _abi.fw_collider:
+def cuboid(size, translation, rotation=(0.0, 0.0, 0.0, 1.0), layers: int = 1, key: int = _abi.FW_NO_KEY) -> _abi.fw_collider:
     """``Collider::cuboid(x, y, z)`` takes full extents (examples/stress_test_collision.rs:88)."""
     c = _abi.fw_collider()
     c.kind = _abi.FW_COLLIDER_CUBOID
     c.layers = layers
+    c.key = key
     c.half_extents[:] = [0.5 * float(s) for s in size]
     c.translation[:] = [float(t) for t in translation]
     c.rotation[:] = [float(r) for r in rotation]
     return c
 
 
-def sphere(radius, translation, layers: int = 1) -> _abi.fw_collider:
+def sphere(radius, translation, layers: int = 1, key: int = _abi.FW_NO_KEY) -> _abi.fw_collider:
     c = _abi.fw_collider()
     c.kind = _abi.FW_COLLIDER_SPHERE
     c.layers = layers
+    c.key = key
     c.half_extents[:] = [float(radius), 0.0, 0.0]
     c.translation[:] = [float(t) for t in translation]
     c.rotation[:] = [0.0, 0.0, 0.0, 1.0]
@@ -165,6 +167,7 @@ def _revolved(kind, radius, height, translation, rotation, layers) -> _abi.fw_co
     c = _abi.fw_collider()
     c.kind = kind
     c.layers = layers
+    c.key = _abi.FW_NO_KEY
     c.half_extents[:] = [float(radius), 0.5 * float(height), 0.0]
     c.translation[:] = [float(t) for t in translation]
     c.rotation[:] = [float(r) for r in rotation]

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 1u
+#define FW_ABI_VERSION 2u
 
 /* Maximum number of knots in one curve / gradient (the reference accepts any number of
  * samples, src/curve.rs:40-75; every shipped example uses <= 5). */
@@ -87,13 +87,18 @@ typedef struct fw_gradient {
     float colors[FW_MAX_KNOTS][4]; /* LinearRgba r,g,b,a */
 } fw_gradient;
 
-/* ---- ParticleCollisionSettings (src/core.rs:240-248); filter = layer mask test */
+/* ---- ParticleCollisionSettings (src/core.rs:240-248). `filter` is avian's SpatialQueryFilter
+ * (:247, passed to cast_ray at :764): a layer mask and a set of excluded entities. */
+#define FW_MAX_EXCLUDED 8u
+#define FW_NO_KEY 0xFFFFFFFFu
 typedef struct fw_collision_settings {
     uint32_t enabled; /* Option::is_some() */
     float restitution;
     float friction;
     uint32_t destroy_on_collision;
-    uint32_t filter_mask; /* collider is seen when (collider.layers & filter_mask) != 0 */
+    uint32_t filter_mask; /* SpatialQueryFilter::mask: a collider is seen when (collider.layers & filter_mask) != 0 */
+    uint32_t n_excluded;  /* SpatialQueryFilter::excluded_entities: colliders whose key is listed are skipped */
+    uint32_t excluded_keys[FW_MAX_EXCLUDED];
 } fw_collision_settings;
 
 /* ---- ParticleSettings (src/core.rs:99-142), simulation-relevant fields only.
@@ -202,6 +207,8 @@ enum fw_collider_kind {
 typedef struct fw_collider {
     uint32_t kind;
     uint32_t layers;       /* membership bits tested against fw_collision_settings.filter_mask */
+    uint32_t key;          /* the collider's entity (any caller-chosen id, FW_NO_KEY = none): matched against
+                              fw_collision_settings.excluded_keys */
     float half_extents[3]; /* see fw_collider_kind */
     float translation[3];
     float rotation[4]; /* Quat x,y,z,w */
@@ -273,6 +280,9 @@ uint32_t fw_abi_version(void);
 /* sizeof() of a POD struct of this header by name ("fw_particle_settings", ...); 0 if unknown.
  * Lets a binding verify its layout against the compiled library. */
 uint32_t fw_abi_sizeof(const char *struct_name);
+/* offsetof(struct, field) by name, 0xFFFFFFFF if unknown: a binding in another language checks its
+ * field order against the compiled library (rust/firework_b200_sys.rs, tests/test_abi.py) */
+uint32_t fw_abi_offsetof(const char *struct_name, const char *field_name);
 
 /* ---- host-side logic of the path, callable without a device (pinned by the `-m "not gpu"` tests) */
 /* compute_emission_count (src/core.rs:553-575) exactly as fw_frame evaluates it on the host:
@@ -402,6 +412,30 @@ int fw_profile_reset(fw_context *ctx);
  * fw_pack_instances_device) copied into ONE caller-owned HOST buffer (pinned memory makes it a
  * single DMA). Synchronises. */
 int fw_extract_instances(fw_context *ctx, void *host_dst, uint64_t cap_rows, uint64_t *n_rows);
+
+/* ---- render hand-off that does not stall the simulation (reference consumer: extract_firework_components,
+ * src/render.rs:439-461, and the per-frame vertex-buffer upload, :568-584).
+ * fw_extract_begin: pack the live ParticleInstance rows of the listed spawners (spawner_keys = NULL: of
+ * every spawner; a renderer passes the spawners whose AABB -- fw_read_aabb -- survived its frustum
+ * culling, src/render.rs:677-703) and start copying them into the caller's HOST buffer (pinned memory
+ * makes it one DMA) on a stream of its own: the call returns at once, later fw_frame calls run while
+ * the copy is in flight (two staging buffers alternate, so one extract may be outstanding while the
+ * next one is packed). fw_extract_wait: wait for the oldest outstanding extract; *n_rows rows have
+ * landed, stream_first_rows[k] = first row of the k-th listed stream (creation order, Vec order
+ * inside a stream; cap_streams entries are written at most, *n_streams = how many there are). */
+int fw_extract_begin(fw_context *ctx, const uint32_t *spawner_keys, uint32_t n_keys, void *host_dst, uint64_t cap_rows);
+int fw_extract_wait(fw_context *ctx, uint64_t *n_rows, uint64_t *stream_first_rows, uint32_t cap_streams,
+                    uint32_t *n_streams);
+/* zero-copy hand-off to another API or process: pack the live rows of every stream into a device
+ * allocation made with the CUDA virtual-memory API and export it as a POSIX file descriptor
+ * (cuMemExportToShareableHandle) -- what VK_KHR_external_memory_fd / a wgpu external-memory import
+ * takes. *bytes = size of the allocation, *n_rows = rows packed (64 bytes each, same order as
+ * fw_pack_instances_device). The descriptor is the caller's to close; the allocation lives until the
+ * next fw_export_instances_fd or fw_destroy. Synchronises. */
+int fw_export_instances_fd(fw_context *ctx, int32_t *fd, uint64_t *bytes, uint64_t *n_rows);
+/* the importing side of the above for a consumer without its own CUDA code (and for the tests): map
+ * the descriptor on `device`, copy n_rows rows to host_dst, unmap. No context needed. */
+int fw_import_instances_fd(int32_t device, int32_t fd, uint64_t bytes, uint64_t n_rows, void *host_dst);
 
 /* CUDA-event stopwatch on the context's stream: record marker `slot` (0..15) now; elapsed
  * milliseconds between two recorded markers (synchronises on the later one). */

@@ -473,9 +473,10 @@ static void collider_cull_box(const fw_collider *c, float box[6]) {
         if (!isfinite(box[a]) || !isfinite(box[3 + a])) { box[a] = -FLT_MAX; box[3 + a] = FLT_MAX; }
     }
 }
-static int cast_ray_impl(const fw_collider *c, uint32_t n, const float *boxes, uint32_t filter_mask, const float origin[3],
+static int cast_ray_impl(const fw_collider *c, uint32_t n, const float *boxes, const fw_collision_settings *filter, const float origin[3],
                          const float dir[3], float max_distance, float *distance, float normal[3],
                          uint32_t *index) {
+    const uint32_t filter_mask = filter->filter_mask; /* SpatialQueryFilter::mask */
     int found = 0;
     float best = 0.0f;
     v3 best_n = v3_make(0.0f, 0.0f, 0.0f);
@@ -491,6 +492,11 @@ static int cast_ray_impl(const fw_collider *c, uint32_t n, const float *boxes, u
     }
     for (uint32_t i = 0; i < n; i++) {
         if ((c[i].layers & filter_mask) == 0u) continue;
+        { /* SpatialQueryFilter::excluded_entities (ref src/core.rs:247,764) */
+            int excluded = 0;
+            for (uint32_t x = 0; x < filter->n_excluded && x < FW_MAX_EXCLUDED; x++) excluded |= filter->excluded_keys[x] == c[i].key;
+            if (excluded) continue;
+        }
         if (cull) {
             const float *b = boxes + 6 * (size_t)i;
             if (shi[0] < b[0] || slo[0] > b[3] || shi[1] < b[1] || slo[1] > b[4] || shi[2] < b[2] || slo[2] > b[5]) continue;
@@ -528,14 +534,20 @@ static int cast_ray_impl(const fw_collider *c, uint32_t n, const float *boxes, u
 int fwo_cast_ray(const fw_collider *c, uint32_t n, uint32_t filter_mask, const float origin[3],
                  const float dir[3], float max_distance, float *distance, float normal[3],
                  uint32_t *index) {
-    return cast_ray_impl(c, n, NULL, filter_mask, origin, dir, max_distance, distance, normal, index);
+    fw_collision_settings f;
+    memset(&f, 0, sizeof(f));
+    f.filter_mask = filter_mask;
+    return cast_ray_impl(c, n, NULL, &f, origin, dir, max_distance, distance, normal, index);
 }
 int fwo_cast_ray_culled(const fw_collider *c, uint32_t n, uint32_t filter_mask, const float origin[3],
                         const float dir[3], float max_distance, float *distance, float normal[3],
                         uint32_t *index) {
     float *boxes = (float *)malloc(sizeof(float) * 6 * (n ? n : 1));
     for (uint32_t i = 0; i < n; i++) collider_cull_box(&c[i], boxes + 6 * (size_t)i);
-    const int r = cast_ray_impl(c, n, boxes, filter_mask, origin, dir, max_distance, distance, normal, index);
+    fw_collision_settings f;
+    memset(&f, 0, sizeof(f));
+    f.filter_mask = filter_mask;
+    const int r = cast_ray_impl(c, n, boxes, &f, origin, dir, max_distance, distance, normal, index);
     free(boxes);
     return r;
 }
@@ -555,7 +567,7 @@ static void particle_collision_impl(const fw_collider *colliders, uint32_t n_col
         float len = v3_length(vel);
         v3 dir = (isfinite(len) && len > 0.0f) ? v3_div(vel, len) : v3_make(0.0f, 1.0f, 0.0f);
         float o[3] = {pos.x, pos.y, pos.z}, d[3] = {dir.x, dir.y, dir.z}, nrm[3], distance;
-        if (cast_ray_impl(colliders, n_colliders, boxes, cs->filter_mask, o, d, v3_length(vel) * delta,
+        if (cast_ray_impl(colliders, n_colliders, boxes, cs, o, d, v3_length(vel) * delta,
                           &distance, nrm, NULL)) {
             v3 hit_normal = v3_make(nrm[0], nrm[1], nrm[2]);
             if (distance == 0.0f) {

@@ -1,9 +1,11 @@
 //! firework_b200_sys — raw FFI declarations of `include/firework_b200.h`.
 //!
 //! UNCOMPILED SOURCE: there is no Rust toolchain in the build image. The
-//! `#[repr(C)]` layouts below restate the C header field by field; `tests/test_abi.py` checks the
-//! C side (`fw_abi_sizeof`), and `shim.rs::check_layouts()` asserts the same sizes from Rust at
-//! plugin start-up, so a drift fails loudly instead of corrupting memory.
+//! `#[repr(C)]` layouts below restate the C header field by field. `tests/test_abi.py` parses THIS
+//! file and the header mechanically -- every export (name, arity, argument types), every struct (field
+//! names, order, types -> offsets by the C layout rules) -- and compares both with each other and with
+//! the compiled library (`fw_abi_sizeof`, `fw_abi_offsetof`); `shim.rs::check_layouts()` asserts the
+//! same from Rust at plugin start-up, so a drift fails loudly instead of corrupting memory.
 //!
 //! Link with `cargo:rustc-link-lib=dylib=firework_b200` (build.rs) and ship
 //! `libfirework_b200.so` beside the executable.
@@ -11,10 +13,31 @@
 
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const FW_ABI_VERSION: u32 = 1;
+pub const FW_ABI_VERSION: u32 = 2;
 pub const FW_MAX_KNOTS: usize = 16;
+pub const FW_MAX_EXCLUDED: usize = 8;
+pub const FW_NO_KEY: u32 = 0xFFFF_FFFF;
+pub const FW_FLAG_PROFILE: u32 = 1;
+pub const FW_FLAG_NO_GRAPHS: u32 = 2;
+pub const FW_FLAG_NO_CONCURRENT_SPAWN: u32 = 4;
+pub const FW_LAYOUT_COMPACTING: u32 = 1;
+pub const FW_LAYOUT_COLLIDES: u32 = 2;
+pub const FW_LAYOUT_ROTATES: u32 = 4;
+pub const FW_STORE_BASE_COLOR: u32 = 1;
+pub const FW_STORE_EMISSIVE_COLOR: u32 = 2;
+pub const FW_STORE_SCALE: u32 = 4;
+pub const FW_STORE_LIFETIME: u32 = 8;
+pub const FW_GATHER_MAX_RANKS: usize = 16;
 
 pub const FW_OK: c_int = 0;
+pub const FW_ERR_INVALID_ARGUMENT: c_int = 1;
+pub const FW_ERR_NO_DEVICE: c_int = 2;
+pub const FW_ERR_CUDA: c_int = 3;
+pub const FW_ERR_OUT_OF_MEMORY: c_int = 4;
+pub const FW_ERR_UNKNOWN_SPAWNER: c_int = 5;
+pub const FW_ERR_BUFFER_TOO_SMALL: c_int = 6;
+pub const FW_ERR_UNSUPPORTED: c_int = 7;
+pub const FW_ERR_INTERNAL: c_int = 8;
 
 pub const FW_CURVE_CONSTANT: u32 = 0;
 pub const FW_CURVE_EVEN: u32 = 1;
@@ -73,6 +96,8 @@ pub struct fw_collision_settings {
     pub friction: f32,
     pub destroy_on_collision: u32,
     pub filter_mask: u32,
+    pub n_excluded: u32,
+    pub excluded_keys: [u32; FW_MAX_EXCLUDED],
 }
 
 #[repr(C)]
@@ -160,6 +185,7 @@ pub struct fw_particle_instance {
 pub struct fw_collider {
     pub kind: u32,
     pub layers: u32,
+    pub key: u32,
     pub half_extents: [f32; 3],
     pub translation: [f32; 3],
     pub rotation: [f32; 4],
@@ -183,6 +209,33 @@ pub struct fw_spawner_status {
     pub finished: u32,
     pub finished_notified: u32,
     pub live_particles: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct fw_frame_profile {
+    pub plan_ms: f32,
+    pub spawn_ms: f32,
+    pub update_ms: f32,
+    pub total_ms: f32,
+    pub kernel_launches: u32,
+    pub timed_frames: u32,
+    pub particles_updated: u64,
+    pub particles_spawned: u64,
+    pub h2d_bytes: u64,
+    pub d2h_bytes: u64,
+}
+
+/// what the library keeps per particle for one stream (`fw_stream_layout_get`)
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct fw_stream_layout {
+    pub variant: u32,
+    pub flags: u32,
+    pub bytes_read: u32,
+    pub bytes_written: u32,
+    pub bytes_count_pass: u32,
+    pub capacity: u32,
 }
 
 #[repr(C)]
@@ -211,10 +264,12 @@ extern "C" {
     pub fn fw_last_error(ctx: *const fw_context) -> *const c_char;
     pub fn fw_abi_version() -> u32;
     pub fn fw_abi_sizeof(struct_name: *const c_char) -> u32;
+    pub fn fw_abi_offsetof(struct_name: *const c_char, field_name: *const c_char) -> u32;
     // host-side logic, callable without a device
     pub fn fw_host_emission_count(time_passed_in_cycle: f32, last_emission: f32, cycle_duration: f32, offset_start: f32,
         offset_end: f32, particles_per_cycle: f32, times: *mut u64, next_last_emission: *mut f32) -> c_int;
     pub fn fw_host_build_broadphase(colliders: *const fw_collider, n: u32, out: *mut c_void, cap_bytes: u64, n_bytes: *mut u64) -> c_int;
+    pub fn fw_device_sincos(ctx: *mut fw_context, x: *const f32, n: u64, sin_out: *mut f32, cos_out: *mut f32) -> c_int;
     pub fn fw_create(cfg: *const fw_config, out_ctx: *mut *mut fw_context) -> c_int;
     pub fn fw_destroy(ctx: *mut fw_context) -> c_int;
     pub fn fw_spawner_reset(
@@ -231,8 +286,10 @@ extern "C" {
     pub fn fw_frame(ctx: *mut fw_context, dt: f32, inputs: *const fw_spawner_frame_input, n_inputs: u32) -> c_int;
     pub fn fw_sync(ctx: *mut fw_context) -> c_int;
     pub fn fw_counts(ctx: *mut fw_context, spawner_key: u32, out_counts: *mut u32, n_types: u32) -> c_int;
+    pub fn fw_counts_all(ctx: *mut fw_context, out_keys: *mut u32, out_types: *mut u32, out_counts: *mut u32, cap: u32, n_streams: *mut u32) -> c_int;
     pub fn fw_spawner_status_get(ctx: *mut fw_context, spawner_key: u32, out: *mut fw_spawner_status) -> c_int;
     pub fn fw_spawner_mark_finished_notified(ctx: *mut fw_context, spawner_key: u32) -> c_int;
+    pub fn fw_stream_layout_get(ctx: *mut fw_context, spawner_key: u32, ty: u32, out: *mut fw_stream_layout) -> c_int;
     pub fn fw_read_particles(ctx: *mut fw_context, spawner_key: u32, ty: u32, out: *mut fw_particle_data, cap: u64, n: *mut u64) -> c_int;
     pub fn fw_write_particles(ctx: *mut fw_context, spawner_key: u32, ty: u32, rows: *const fw_particle_data, n: u64) -> c_int;
     pub fn fw_read_instances(ctx: *mut fw_context, spawner_key: u32, ty: u32, out: *mut fw_particle_instance, cap: u64, n: *mut u64) -> c_int;
@@ -247,4 +304,17 @@ extern "C" {
     pub fn fw_gather_instances(ctx: *mut fw_context) -> c_int;
     pub fn fw_gather_result(ctx: *mut fw_context, device_rows: *mut *mut c_void, rows_per_rank: *mut u64, n_ranks: u32, region_stride_rows: *mut u64) -> c_int;
     pub fn fw_gather_destroy(ctx: *mut fw_context) -> c_int;
+    // render hand-off without a host round trip / without blocking the simulation
+    pub fn fw_extract_begin(ctx: *mut fw_context, spawner_keys: *const u32, n_keys: u32, host_dst: *mut c_void, cap_rows: u64) -> c_int;
+    pub fn fw_extract_wait(ctx: *mut fw_context, n_rows: *mut u64, stream_first_rows: *mut u64, cap_streams: u32, n_streams: *mut u32) -> c_int;
+    pub fn fw_export_instances_fd(ctx: *mut fw_context, fd: *mut i32, bytes: *mut u64, n_rows: *mut u64) -> c_int;
+    pub fn fw_import_instances_fd(device: i32, fd: i32, bytes: u64, n_rows: u64, host_dst: *mut c_void) -> c_int;
+    // frame accounting and timing
+    pub fn fw_set_profiling(ctx: *mut fw_context, on: u32) -> c_int;
+    pub fn fw_profile_last(ctx: *mut fw_context, out: *mut fw_frame_profile) -> c_int;
+    pub fn fw_profile_sum(ctx: *mut fw_context, out: *mut fw_frame_profile, n_frames: *mut u32) -> c_int;
+    pub fn fw_profile_reset(ctx: *mut fw_context) -> c_int;
+    pub fn fw_event_record(ctx: *mut fw_context, slot: u32) -> c_int;
+    pub fn fw_event_elapsed_ms(ctx: *mut fw_context, slot_begin: u32, slot_end: u32, out_ms: *mut f32) -> c_int;
+    pub fn fw_stream_handle(ctx: *mut fw_context) -> *mut c_void;
 }

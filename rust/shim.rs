@@ -98,6 +98,11 @@ fn check_layouts() -> Result<(), String> {
             }
         }};
     }
+    chk!(fw_rand_f32);
+    chk!(fw_rand_vec3);
+    chk!(fw_curve_f32);
+    chk!(fw_gradient);
+    chk!(fw_collision_settings);
     chk!(fw_particle_settings);
     chk!(fw_emission_settings);
     chk!(fw_spawner_frame_input);
@@ -105,6 +110,30 @@ fn check_layouts() -> Result<(), String> {
     chk!(fw_particle_instance);
     chk!(fw_collider);
     chk!(fw_config);
+    chk!(fw_spawner_status);
+    chk!(fw_frame_profile);
+    chk!(fw_stream_layout);
+    chk!(fw_gather_handle);
+    // field offsets of the structs whose fields are not all the same size (std::mem::offset_of!)
+    macro_rules! off {
+        ($t:ty, $f:ident) => {{
+            let (sn, fnm) = (CString::new(stringify!($t)).unwrap(), CString::new(stringify!($f)).unwrap());
+            let c = unsafe { fw_abi_offsetof(sn.as_ptr(), fnm.as_ptr()) } as usize;
+            if c != std::mem::offset_of!($t, $f) {
+                return Err(format!("layout drift: {}.{} at {} in C, {} in Rust", stringify!($t), stringify!($f), c, std::mem::offset_of!($t, $f)));
+            }
+        }};
+    }
+    off!(fw_emission_settings, one_shot_count);
+    off!(fw_emission_settings, initial_angular_velocity);
+    off!(fw_particle_settings, collision);
+    off!(fw_particle_settings, capacity_hint);
+    off!(fw_config, seed);
+    off!(fw_config, external_stream);
+    off!(fw_spawner_status, live_particles);
+    off!(fw_frame_profile, particles_updated);
+    off!(fw_collider, half_extents);
+    off!(fw_gather_handle, address);
     Ok(())
 }
 
@@ -181,6 +210,19 @@ fn particle_settings(s: &ParticleSettings) -> fw_particle_settings {
             friction: c.friction,
             destroy_on_collision: c.destroy_on_collision as u32,
             filter_mask: c.filter.mask.0, // LayerMask bits of the SpatialQueryFilter
+            // SpatialQueryFilter::excluded_entities (src/core.rs:247,764): the colliders carry their
+            // entity key (gpu_sync_colliders), the sweep skips the listed ones
+            n_excluded: c.filter.excluded_entities.len().min(FW_MAX_EXCLUDED) as u32,
+            excluded_keys: {
+                let mut k = [FW_NO_KEY; FW_MAX_EXCLUDED];
+                if c.filter.excluded_entities.len() > FW_MAX_EXCLUDED {
+                    bevy::log::warn_once!("firework_b200: more than {} excluded entities in a SpatialQueryFilter, the rest is ignored", FW_MAX_EXCLUDED);
+                }
+                for (slot, e) in k.iter_mut().zip(c.filter.excluded_entities.iter()) {
+                    *slot = key(*e);
+                }
+                k
+            },
         }),
         #[cfg(not(feature = "physics_avian"))]
         collision: fw_collision_settings::default(),
@@ -257,7 +299,9 @@ pub fn gpu_frame(
     gpu: ResMut<GpuParticles>,
     mut q: Query<(Entity, &Transform, &GlobalTransform, &ParticleSpawner, &mut ParticleSpawnerData, Option<&EffectModifier>)>,
     time: Res<Time>,
+    mut commands: Commands,
     mut inputs: Local<Vec<fw_spawner_frame_input>>,
+    mut destroyed: Local<Vec<fw_particle_data>>,
 ) {
     inputs.clear();
     for (entity, transform, global_transform, settings, mut data, modifier) in &mut q {
@@ -277,16 +321,39 @@ pub fn gpu_frame(
         });
     }
     let rc = unsafe { fw_frame(gpu.ctx, time.delta_secs(), inputs.as_ptr(), inputs.len() as u32) };
-    gpu.check(rc, "fw_frame");
+    if !gpu.check(rc, "fw_frame") {
+        return;
+    }
+    // particles_destroyed handlers (src/core.rs:660-667): the reference runs the handler system with
+    // the Vec of particles the update just destroyed. Types with a handler were reset with
+    // capture_destroyed = 1, so the library kept those rows (age already bumped, old colours).
+    for (entity, _, _, settings, _, _) in &q {
+        for (ty, ps) in settings.particle_settings.iter().enumerate() {
+            let Some(handler) = ps.event_handlers.particles_destroyed else { continue };
+            let mut n: u64 = 0;
+            // first call sizes the buffer (FW_ERR_BUFFER_TOO_SMALL still reports the count)
+            unsafe { fw_read_destroyed(gpu.ctx, key(entity), ty as u32, std::ptr::null_mut(), 0, &mut n) };
+            if n == 0 {
+                continue;
+            }
+            destroyed.clear();
+            destroyed.resize(n as usize, unsafe { std::mem::zeroed() });
+            let rc = unsafe { fw_read_destroyed(gpu.ctx, key(entity), ty as u32, destroyed.as_mut_ptr(), n, &mut n) };
+            if gpu.check(rc, "fw_read_destroyed") {
+                let rows: Vec<ParticleData> = destroyed[..n as usize].iter().map(particle_from_pod).collect();
+                commands.run_system_with(handler, rows); // :665
+            }
+        }
+    }
 }
 
 /// replaces `notify_finished_particle_spawners` (src/core.rs:674-688)
 pub fn gpu_notify_finished(gpu: ResMut<GpuParticles>, mut commands: Commands, q: Query<(Entity, &ParticleSpawner), With<ParticleSpawnerData>>) {
-    for (entity, settings) in &q {
-        // only spawners whose every emitter is one-shot / on-demand can ever finish
-        if !settings.emission_settings.iter().all(|e| !matches!(e.emission_pacing, EmissionPacing::CountOverDuration { .. })) {
-            continue;
-        }
+    for (entity, _settings) in &q {
+        // the reference's condition is only `all empty && !active()` (:679-682) -- a spawner that starts
+        // disabled, or a OneShot burst with a Nested trail, finishes too -- so every spawner is asked;
+        // fw_spawner_status_get is served from the frame's own state readback (one event wait per
+        // frame, no copy per spawner)
         let mut st = fw_spawner_status::default();
         if gpu.check(unsafe { fw_spawner_status_get(gpu.ctx, key(entity), &mut st) }, "fw_spawner_status_get") && st.finished != 0 {
             commands.trigger(ParticleSpawnerFinished { entity });
@@ -309,12 +376,12 @@ pub fn gpu_forget_removed(gpu: ResMut<GpuParticles>, mut removed: RemovedCompone
 #[cfg(feature = "physics_avian")]
 pub fn gpu_sync_colliders(
     gpu: ResMut<GpuParticles>,
-    q: Query<(&Collider, &GlobalTransform, Option<&CollisionLayers>)>,
+    q: Query<(Entity, &Collider, &GlobalTransform, Option<&CollisionLayers>)>,
     mut scratch: Local<Vec<fw_collider>>,
 ) {
     use avian3d::parry::shape::TypedShape;
     scratch.clear();
-    for (collider, transform, layers) in &q {
+    for (entity, collider, transform, layers) in &q {
         let t = transform.compute_transform();
         let (kind, half_extents) = match collider.shape_scaled().as_typed_shape() {
             TypedShape::Cuboid(c) => (FW_COLLIDER_CUBOID, [c.half_extents.x, c.half_extents.y, c.half_extents.z]),
@@ -329,6 +396,7 @@ pub fn gpu_sync_colliders(
         scratch.push(fw_collider {
             kind,
             layers: layers.map(|l| l.memberships.0).unwrap_or(1),
+            key: key(entity),
             half_extents,
             translation: t.translation.to_array(),
             rotation: t.rotation.to_array(),
