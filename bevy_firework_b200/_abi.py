@@ -210,6 +210,7 @@ EXPORTS = {
     "fw_set_colliders": (C.c_int, [_ctx, P(fw_collider), u32]),
     "fw_frame": (C.c_int, [_ctx, f32, P(fw_spawner_frame_input), u32]),
     "fw_sync": (C.c_int, [_ctx]),
+    "fw_poll_device_errors": (C.c_int, [_ctx, P(u32)]),
     "fw_counts": (C.c_int, [_ctx, u32, P(u32), u32]),
     "fw_counts_all": (C.c_int, [_ctx, P(u32), P(u32), P(u32), u32, P(u32)]),
     "fw_spawner_status_get": (C.c_int, [_ctx, u32, P(fw_spawner_status)]),

@@ -137,6 +137,12 @@ class Engine:
     def sync(self):
         self._check(self._L.fw_sync(self._ctx))
 
+    def poll_device_errors(self) -> int:
+        """FW_DEVICE_* bits raised by frames that have completed (never waits)"""
+        f = C.c_uint32()
+        self._check(self._L.fw_poll_device_errors(self._ctx, C.byref(f)))
+        return int(f.value)
+
     def counts(self, key, n_types=None) -> List[int]:
         n_types = self._n_types[key] if n_types is None else n_types
         out = (C.c_uint32 * max(n_types, 1))()

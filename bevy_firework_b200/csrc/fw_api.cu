@@ -665,6 +665,10 @@ void poll_readbacks(fw_context *ctx) {
         if (!fs.in_flight) continue;
         if (cudaEventQuery(fs.done) == cudaSuccess) {
             fs.in_flight = false;
+            if (fs.plan_host) { // what the device flagged in that frame (reported by fw_sync / fw_poll_device_errors)
+                ctx->device_error_flags |= fs.plan_host->error_flags;
+                fs.plan_host->error_flags = 0;
+            }
             if (fs.frame >= newest) { newest = fs.frame; best = &fs; }
         } else {
             (void)cudaGetLastError();
@@ -1876,6 +1880,14 @@ int fw_sync(fw_context *ctx) {
         ctx->device_error_flags = 0;
         return fail(ctx, FW_ERR_INTERNAL, "device reported error flags 0x%x (1 = a ring overflowed and spawns were dropped, 2 = look-back table too small, 4 = a nested emitter exceeded its planned per-parent bound)", fl);
     }
+    return FW_OK;
+}
+
+int fw_poll_device_errors(fw_context *ctx, uint32_t *flags) {
+    ENTER(ctx);
+    poll_readbacks(ctx); // (never waits)
+    if (flags) *flags = ctx->device_error_flags;
+    ctx->device_error_flags = 0;
     return FW_OK;
 }
 

@@ -784,46 +784,68 @@ __global__ void __launch_bounds__(256) count_kernel(DeviceTables t, FrameDeviceI
     const uint32_t *prefix = derive ? f.host_tile_prefix + (size_t)variant * (n_slots + 1u)
                                     : t.tile_prefix + (size_t)variant * (t.slots_cap + 1u);
     const float dt = f.header->dt;
-    const uint32_t lane = lane_id(), warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
-        TileRef e{};
-        if (lane == 0) e = resolve_tile(t, f, prefix, n_slots, tile, derive);
-        e.stream = __shfl_sync(0xffffffffu, e.stream, 0);
-        e.tile = __shfl_sync(0xffffffffu, e.tile, 0);
-        e.head = __shfl_sync(0xffffffffu, e.head, 0);
-        e.n_update = __shfl_sync(0xffffffffu, e.n_update, 0);
+    // every warp owns a contiguous share of the tiles: consecutive tiles belong to the same stream, so
+    // the stream lookup (32-ary search by the whole warp) and its ring geometry are resolved once per
+    // segment, and what is left per tile is eight independent loads, eight ballots and two stores
+    const uint32_t lane = lane_id(), warps = (gridDim.x * blockDim.x) >> 5, w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t per_warp = (n_tiles + warps - 1u) / warps;
+    uint32_t tile = w * per_warp;
+    const uint32_t tile_end = min(n_tiles, tile + per_warp);
+    static_assert(kTile == 256, "the per-warp death counts of a tile are packed as 7 x 8 bits");
+    while (tile < tile_end) {
+        TileRef e = find_tile_warp(prefix, n_slots, tile);
         const StreamDesc d = t.descs[e.stream];
+        if (derive) {
+            const Derived dv = derive_state(t.states_prev[e.stream], d, f.spawn_per_slot[e.stream]);
+            e.head = dv.head;
+            e.n_update = f.header->step_in_spawn ? dv.c0 : dv.n_update; // (see resolve_tile)
+        } else {
+            e.head = t.states[e.stream].head;
+            e.n_update = t.states[e.stream].count;
+        }
+        const uint32_t seg_end = min(tile_end, prefix[e.stream + 1u]);
         const StreamArrays a = stream_arrays(d.base, d.capacity);
-        const uint32_t shift = e.head & 31u, tile_first = e.tile * kTile;
+        const uint32_t shift = e.head & 31u;
         // where (age, lifetime) live: rotating stream m0.w / k.x; static stream k = (lifetime, age)
         // -- 8 instead of 24 bytes per particle -- or, with a constant lifetime, m0.w alone
         const bool rot = variant_rotates(d.variant), klife = (d.flags & kStoreLife) != 0u;
         const float const_life = t.settings[e.stream].const_lifetime;
-        uint32_t dead = 0;
-        unsigned long long before_warp = 0; // dead particles of the tile in front of warp j, 8 bits each (j = 1..7)
-        static_assert(kTile == 256, "the per-warp death counts of a tile are packed as 7 x 8 bits");
+        for (uint32_t tis = e.tile; tile < seg_end; tile++, tis++) {
+            const uint32_t tile_first = tis * kTile;
+            // all eight rows of the tile are loaded before the first ballot: eight requests in flight per lane
+            float age[kTile / 32], life[kTile / 32];
 #pragma unroll
-        for (uint32_t j = 0; j < (uint32_t)kTile / 32u; j++) {
-            if (j) before_warp |= (unsigned long long)dead << (8u * (j - 1u));
-            const uint32_t p = tile_first + j * 32u + lane, i = p - shift;
-            const bool valid = p >= shift && i < e.n_update;
-            bool dies = false;
-            if (valid) {
-                const uint32_t slot = wrap(e.head + i, d.capacity);
-                if (rot) {
-                    dies = a.m0[slot].w + dt >= a.k[slot].x;
-                } else if (klife) {
-                    const float2 K = a.k[slot];
-                    dies = K.y + dt >= K.x;
-                } else {
-                    dies = a.m0[slot].w + dt >= const_life;
+            for (uint32_t j = 0; j < (uint32_t)kTile / 32u; j++) {
+                const uint32_t p = tile_first + j * 32u + lane, i = p - shift;
+                const bool valid = p >= shift && i < e.n_update;
+                age[j] = 0.0f;
+                life[j] = __int_as_float(0x7f800000); // +inf: never dies
+                if (valid) {
+                    const uint32_t slot = wrap(e.head + i, d.capacity);
+                    if (rot) {
+                        age[j] = a.m0[slot].w;
+                        life[j] = a.k[slot].x;
+                    } else if (klife) {
+                        const float2 K = a.k[slot];
+                        age[j] = K.y;
+                        life[j] = K.x;
+                    } else {
+                        age[j] = a.m0[slot].w;
+                        life[j] = const_life;
+                    }
                 }
             }
-            dead += __popc(__ballot_sync(0xffffffffu, dies));
-        }
-        if (lane == 0) {
-            t.lookback[tile_base + tile] = dead;
-            t.lookback[t.lookback_capacity + tile_base + tile] = before_warp;
+            uint32_t dead = 0;
+            unsigned long long before_warp = 0; // dead particles of the tile in front of warp j, 8 bits each (j = 1..7)
+#pragma unroll
+            for (uint32_t j = 0; j < (uint32_t)kTile / 32u; j++) {
+                if (j) before_warp |= (unsigned long long)dead << (8u * (j - 1u));
+                dead += __popc(__ballot_sync(0xffffffffu, age[j] + dt >= life[j])); // src/core.rs:594-599
+            }
+            if (lane == 0) {
+                t.lookback[tile_base + tile] = dead;
+                t.lookback[t.lookback_capacity + tile_base + tile] = before_warp;
+            }
         }
     }
 }
@@ -1555,7 +1577,11 @@ cudaError_t launch_nested(const DeviceTables &t, const FrameDeviceInputs &f, uin
     return cudaGetLastError();
 }
 #ifndef FW_GROUP_TILES
-#define FW_GROUP_TILES 8
+// 0 = one contiguous share of the tiles per CTA. Measured on C3 (10 M particles, 80 B each, update kernel
+// alone): contiguous 0.145 ms; groups of 32 / 16 / 8 / 4 / 2 tiles dealt round robin 0.157 / 0.159 / 0.161 /
+// 0.163 / 0.186 ms, odd group sizes (3 .. 27) the same -- the moving window buys nothing, the per-group
+// lookups cost (profiles/r2/tuning.md)
+#define FW_GROUP_TILES 0
 #endif
 // tiles per group of the static update (see update_static_kernel); FW_GROUP_TILES in the environment
 // overrides the built-in value (tuning runs)
@@ -1589,7 +1615,7 @@ cudaError_t launch_update(const DeviceTables &t, const FrameDeviceInputs &f, uin
     return cudaGetLastError();
 }
 cudaError_t launch_count_scan(const DeviceTables &t, const FrameDeviceInputs &f, uint32_t variant, uint32_t n_slots, cudaStream_t s) {
-    count_kernel<<<148 * 8, 256, 0, s>>>(t, f, variant); // one warp per tile, grid-stride: 64 warps per SM
+    count_kernel<<<148 * 6, 256, 0, s>>>(t, f, variant); // one resident wave (38 registers: 6 CTAs per SM); a contiguous share of the tiles per warp
     scan_kernel<<<std::max(1u, std::min(148u * 8u, (n_slots + 7u) / 8u)), 256, 0, s>>>(t, f, variant); // one warp per stream
     return cudaGetLastError();
 }

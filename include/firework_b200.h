@@ -327,8 +327,15 @@ int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n);
  * and >= 0, anything else is FW_ERR_INVALID_ARGUMENT. */
 int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, uint32_t n_inputs);
 
-/* wait for all queued frames */
+/* wait for all queued frames; reports (once) what the device flagged since the last report */
 int fw_sync(fw_context *ctx);
+/* the same report without waiting: *flags = FW_DEVICE_* bits raised by frames that have already
+ * completed (and not yet reported); returns FW_OK. A shim calls it once per tick after fw_frame, so a
+ * dropped spawn is logged within a few frames instead of at the next synchronisation. */
+#define FW_DEVICE_RING_OVERFLOW 1u   /* a ring was full: spawns were dropped (the host grows rings before that can happen) */
+#define FW_DEVICE_LOOKBACK_SMALL 2u  /* look-back table too small */
+#define FW_DEVICE_NESTED_CAP 4u      /* a parent wanted to emit more children than the planned per-parent bound */
+int fw_poll_device_errors(fw_context *ctx, uint32_t *flags);
 
 /* data.particles[i].len() for every particle type of a spawner (synchronises) */
 int fw_counts(fw_context *ctx, uint32_t spawner_key, uint32_t *out_counts, uint32_t n_types);

@@ -28,6 +28,9 @@ pub const FW_STORE_EMISSIVE_COLOR: u32 = 2;
 pub const FW_STORE_SCALE: u32 = 4;
 pub const FW_STORE_LIFETIME: u32 = 8;
 pub const FW_GATHER_MAX_RANKS: usize = 16;
+pub const FW_DEVICE_RING_OVERFLOW: u32 = 1;
+pub const FW_DEVICE_LOOKBACK_SMALL: u32 = 2;
+pub const FW_DEVICE_NESTED_CAP: u32 = 4;
 
 pub const FW_OK: c_int = 0;
 pub const FW_ERR_INVALID_ARGUMENT: c_int = 1;
@@ -285,6 +288,7 @@ extern "C" {
     pub fn fw_set_colliders(ctx: *mut fw_context, colliders: *const fw_collider, n: u32) -> c_int;
     pub fn fw_frame(ctx: *mut fw_context, dt: f32, inputs: *const fw_spawner_frame_input, n_inputs: u32) -> c_int;
     pub fn fw_sync(ctx: *mut fw_context) -> c_int;
+    pub fn fw_poll_device_errors(ctx: *mut fw_context, flags: *mut u32) -> c_int;
     pub fn fw_counts(ctx: *mut fw_context, spawner_key: u32, out_counts: *mut u32, n_types: u32) -> c_int;
     pub fn fw_counts_all(ctx: *mut fw_context, out_keys: *mut u32, out_types: *mut u32, out_counts: *mut u32, cap: u32, n_streams: *mut u32) -> c_int;
     pub fn fw_spawner_status_get(ctx: *mut fw_context, spawner_key: u32, out: *mut fw_spawner_status) -> c_int;

@@ -324,6 +324,11 @@ pub fn gpu_frame(
     if !gpu.check(rc, "fw_frame") {
         return;
     }
+    // what frames that have completed meanwhile flagged on the device (never waits)
+    let mut flags = 0u32;
+    if unsafe { fw_poll_device_errors(gpu.ctx, &mut flags) } == FW_OK && flags != 0 {
+        error!("firework_b200: device flags {flags:#x} (1 = a ring overflowed and spawns were dropped, 2 = look-back table too small, 4 = a nested emitter exceeded its planned per-parent bound)");
+    }
     // particles_destroyed handlers (src/core.rs:660-667): the reference runs the handler system with
     // the Vec of particles the update just destroyed. Types with a handler were reset with
     // capture_destroyed = 1, so the library kept those rows (age already bumped, old colours).

@@ -237,3 +237,14 @@ def test_dt_must_be_a_duration(engine):
     engine.frame(0.0, [])  # a paused clock is fine
     engine.frame(DT, [])
     assert engine.counts(1) == [1]
+
+
+def test_poll_device_errors_never_waits_and_reports_nothing_on_a_healthy_run(engine):
+    ps, nt, es, ne = stress_spawner(rate=5000.0).pods()
+    engine.spawner_reset(1, ps, nt, es, ne, True)
+    flags = 0
+    for _ in range(30):
+        engine.frame(DT, [frame_input(1, (0.0, 0.1, 0.0))])
+        flags |= engine.poll_device_errors()
+    engine.sync()
+    assert flags == 0 and engine.poll_device_errors() == 0
