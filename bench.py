@@ -399,8 +399,10 @@ def main():
     first_key = sc.spawners[0][0] if sc.spawners else sc.live_bursts[-1]
     lay = eng.stream_layout(first_key, 0)
     layout_bytes = int(lay.bytes_read + lay.bytes_written)
-    layout_kernel = "fw::update_kernel<%s,%d,%s>" % ("true" if lay.variant & 1 else "false", 1 if lay.variant & 2 else 0,
-                                                     "true" if lay.variant & 4 else "false")
+    # (static streams without a collision sweep run the segment-scheduled kernel, everything else the tile-scheduled one)
+    layout_kernel = ("fw::update_static_kernel<%s>" % ("true" if lay.variant & 1 else "false") if not lay.variant & 6 else
+                     "fw::update_kernel<%s,%d,%s>" % ("true" if lay.variant & 1 else "false", 1 if lay.variant & 2 else 0,
+                                                      "true" if lay.variant & 4 else "false"))
     layout_info = {"variant": int(lay.variant), "flags": int(lay.flags), "bytes_read": int(lay.bytes_read),
                    "bytes_written": int(lay.bytes_written), "bytes_count_pass": int(lay.bytes_count_pass),
                    "generic_bytes_per_particle": ALGO_BYTES_PER_PARTICLE}
