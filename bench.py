@@ -466,6 +466,52 @@ def main():
                    "ms_per_step": dt_x_all / x_steps * 1e3, "steps": x_steps,
                    "pcie_gbs": rows * 64 / (dt_x / x_steps) / 1e9,
                    "what": "fw_frame + fw_extract_instances: all live 64-byte ParticleInstance rows into pinned host memory every step"}
+        if world == 1:
+            # the same hand-off, asynchronous and double-buffered (fw_extract_begin / fw_extract_wait: the copy
+            # of frame f runs under frame f+1), and for a culled eighth of the spawners; against the plain
+            # pinned-memory D2H rate of this box for the same bytes
+            host2 = torch.empty((cap, 16), dtype=torch.float32, pin_memory=True)
+            dev = torch.empty((max(rows, 1), 16), dtype=torch.float32, device="cuda")
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 0.0
+            for _ in range(3):
+                ev0.record()
+                host[: dev.shape[0]].copy_(dev, non_blocking=True)
+                ev1.record()
+                ev1.synchronize()
+                best = max(best, dev.numel() * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9)
+            del dev
+            bufs = [host, host2]
+            barrier(eng)
+            sc.step()
+            eng.extract_begin(bufs[0].data_ptr(), cap)
+            t0 = time.perf_counter()
+            for i in range(x_steps):
+                sc.step()
+                eng.extract_begin(bufs[(i + 1) & 1].data_ptr(), cap)
+                rows_a, _ = eng.extract_wait(0)
+            dt_a = time.perf_counter() - t0
+            eng.extract_wait(0)
+            keys_all = [k for k, *_ in sc.spawners]
+            sub = keys_all[:: 8] if keys_all else None
+            culled = None
+            if sub:
+                barrier(eng)
+                t0 = time.perf_counter()
+                for i in range(x_steps):
+                    sc.step()
+                    eng.extract_begin(bufs[i & 1].data_ptr(), cap, sub)
+                    rows_c, _ = eng.extract_wait(0)
+                dt_c = time.perf_counter() - t0
+                culled = {"spawners": len(sub), "rows": rows_c, "ms_per_step": dt_c / x_steps * 1e3}
+            extract["pinned_d2h_peak_gbs"] = best
+            extract["frac_of_pinned_d2h_peak"] = extract["pcie_gbs"] / best if best else None
+            extract["async_double_buffered"] = {"ms_per_step": dt_a / x_steps * 1e3, "pcie_gbs": rows_a * 64 / (dt_a / x_steps) / 1e9,
+                                                "frac_of_pinned_d2h_peak": rows_a * 64 / (dt_a / x_steps) / 1e9 / best if best else None,
+                                                "what": "fw_extract_begin(frame f+1) issued before fw_extract_wait(frame f)"}
+            extract["culled_subset"] = culled
+            del host2
         del host
 
     live_all, launches_all = reduce_sum([live, main_t["launches"]])

@@ -215,6 +215,15 @@ struct fw_context {
     std::vector<uint32_t> fr_spawn_per_slot;
     std::vector<uint64_t> fr_add;
     std::vector<SpawnerInput> fr_inputs;
+    std::vector<Spawner *> fr_targets;
+    struct PacingUndo { // what fw_frame changed in an emitter / spawner before the frame was certain to be submitted
+        Emitter *e;
+        Spawner *sp;
+        float last_emission, time_passed_in_cycle;
+        bool enabled;
+        uint64_t serial, manual_queued_count;
+    };
+    std::vector<PacingUndo> fr_undo;
 
     // profile accumulators
     fw_frame_profile prof_last{};
@@ -283,13 +292,16 @@ inline int enter(fw_context *ctx) {
     } while (0)
 
 // ---- Rust f32 helpers used by emission pacing (core::f32::rem_euclid / div_euclid, `as usize`)
+// (fmod is exact and costs ~25 ns; the common cases need none: 0 <= a < b is its own remainder, and a
+// remainder is negative only when a is -- 512 emitters per frame pay for the difference)
 inline float rem_euclid_f32(float a, float b) {
+    if (a >= 0.0f && a < b) return a;
     const float r = std::fmod(a, b);
     return r < 0.0f ? r + std::fabs(b) : r;
 }
 inline float div_euclid_f32(float a, float b) {
     const float q = std::trunc(a / b);
-    if (std::fmod(a, b) < 0.0f) return b > 0.0f ? q - 1.0f : q + 1.0f;
+    if (a < 0.0f && std::fmod(a, b) < 0.0f) return b > 0.0f ? q - 1.0f : q + 1.0f;
     return q;
 }
 inline uint64_t f32_as_usize(float f) {
@@ -1425,12 +1437,19 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     // dt is Res<Time>::delta_secs() (src/core.rs:413,594): a Duration as f32, finite and >= 0. The
     // per-stream constants of static streams rely on that (fw_internal.h), so anything else is refused.
     if (!std::isfinite(dt) || std::signbit(dt)) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_frame: dt = %g (must be finite and >= 0)", (double)dt);
+    // resolve every key before touching any state (an unknown key fails the call and changes nothing).
+    // A shim sends its spawners in the same order every tick -- usually creation order --, so the
+    // spawner at the same position is tried before the hash map.
+    std::vector<Spawner *> &targets = ctx->fr_targets;
+    targets.resize(n_inputs);
     for (uint32_t k = 0; k < n_inputs; k++) {
-        Spawner *sp = find(ctx, inputs[k].spawner_key);
+        Spawner *sp = k < ctx->spawners.size() && ctx->spawners[k]->key == inputs[k].spawner_key ? ctx->spawners[k].get()
+                                                                                              : find(ctx, inputs[k].spawner_key);
         if (!sp) return fail(ctx, FW_ERR_UNKNOWN_SPAWNER, "fw_frame: unknown spawner %u", inputs[k].spawner_key);
+        targets[k] = sp;
     }
     for (uint32_t k = 0; k < n_inputs; k++) {
-        Spawner *sp = find(ctx, inputs[k].spawner_key);
+        Spawner *sp = targets[k];
         memcpy(sp->input.translation, inputs[k].origin_translation, sizeof(float) * 3);
         memcpy(sp->input.rotation, inputs[k].origin_rotation, sizeof(float) * 4);
         memcpy(sp->input.parent_velocity, inputs[k].parent_velocity, sizeof(float) * 3);
@@ -1451,6 +1470,25 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     // are walked in order; its k-th Nested emitter closes phase k (see PhaseInfo).
     const uint32_t n_phases = ctx->n_phases;
     const uint32_t n_slots = ctx->n_slots;
+    // Emission pacing is advanced while the frame is planned, but a later step can still fail (a
+    // ring that cannot grow, a CUDA error): the emitters' and spawners' pacing state is then put back,
+    // so that a failed fw_frame leaves everything as it was ("state untouched").
+    struct UndoGuard {
+        std::vector<fw_context::PacingUndo> &log;
+        bool committed = false;
+        ~UndoGuard() {
+            if (committed) return;
+            for (size_t k = log.size(); k-- > 0;) {
+                const fw_context::PacingUndo &u = log[k];
+                u.e->last_emission = u.last_emission;
+                u.e->time_passed_in_cycle = u.time_passed_in_cycle;
+                u.e->enabled = u.enabled;
+                u.e->serial = u.serial;
+                u.sp->manual_queued_count = u.manual_queued_count;
+            }
+        }
+    } undo{ctx->fr_undo};
+    undo.log.clear();
     // (scratch kept in the context: a steady-state frame allocates nothing)
     std::vector<SpawnCmd> *cmds = ctx->fr_cmds;
     std::vector<NestedCmd> *nested = ctx->fr_nested;
@@ -1495,6 +1533,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
                 continue;
             }
             if (!e.enabled) continue; // :388-390
+            undo.log.push_back({&e, &sp, e.last_emission, e.time_passed_in_cycle, e.enabled, e.serial, sp.manual_queued_count});
             uint64_t n = 0;
             if (e.es.pacing_kind == FW_PACING_ONE_SHOT) { // :397-400
                 e.enabled = false;
@@ -1864,6 +1903,7 @@ int fw_frame(fw_context *ctx, float dt, const fw_spawner_frame_input *inputs, ui
     fs.particles_spawned = total_spawn;
     fs.h2d_bytes = bytes;
     fs.d2h_bytes = statebuf_bytes(n_slots);
+    undo.committed = true;
     return FW_OK;
 }
 

@@ -653,6 +653,9 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
         : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef FW_STATIC_UNROLL
+#define FW_STATIC_UNROLL 1 // static update: tiles per loop trip (2: twice the loads in flight per thread)
+#endif
 #ifndef FW_PREFETCH
 #define FW_PREFETCH 0 // static update: 0 none (measured best), 1 prefetch.global.L1, 2 prefetch.global.L2
 #endif
@@ -1308,52 +1311,65 @@ __global__ void __launch_bounds__(kUpdateThreads, COMPACT ? FW_MINB_COMPACT : FW
             float mn0 = kInf, mn1 = kInf, mn2 = kInf, mx0 = -kInf, mx1 = -kInf, mx2 = -kInf; // AABB of this thread's survivors
             uint32_t n_alive = 0, n_dead = 0, hint = 0;
             uint32_t q = e.tile * (uint32_t)kTile + tid;
-            for (; tile < seg_end; tile++, q += (uint32_t)kTile) {
-                if (q - tid >= q_end) { // tiles past the stream's real count (the host's tile table holds upper bounds)
-                    tile = seg_end;
-                    break;
-                }
-                const bool valid = q >= shift && q < q_end;
-                uint32_t slot = head_aligned + q;
-                if (slot >= cap) slot -= cap;
+            struct TileIn { // one particle of one tile, as loaded
+                bool valid;
+                uint32_t slot, q, tile;
+                float4 A, V;
+                float2 K;
+                unsigned long long pre_tile, pre_warps;
+            };
+            auto load_tile = [&](uint32_t tile_i, uint32_t qi) {
+                TileIn in;
+                in.q = qi;
+                in.tile = tile_i;
+                in.valid = qi >= shift && qi < q_end;
+                in.slot = head_aligned + qi;
+                if (in.slot >= cap) in.slot -= cap;
                 // ---- loads: 32 B per particle (+ 8 B when the lifetime varies)
-                float4 A = make_float4(0.f, 0.f, 0.f, 0.f), V = A;
-                float2 K = make_float2(1.f, 0.f);
-                uint8_t *const row = base + (size_t)slot * 16u; // m0[slot]
-                if (valid) {
-                    A = ld_pack((const float4 *)row);
-                    V = ld_pack((const float4 *)(row + 2u * cap16));
-                    if (klife) K = ld_pack((const float2 *)(base + 3u * cap16 + cap16 / 2u) + slot);
+                in.A = make_float4(0.f, 0.f, 0.f, 0.f);
+                in.V = in.A;
+                in.K = make_float2(1.f, 0.f);
+                const uint8_t *const row = base + (size_t)in.slot * 16u; // m0[slot]
+                if (in.valid) {
+                    in.A = ld_pack((const float4 *)row);
+                    in.V = ld_pack((const float4 *)(row + 2u * cap16));
+                    if (klife) in.K = ld_pack((const float2 *)(base + 3u * cap16 + cap16 / 2u) + in.slot);
                 }
-                unsigned long long pre_tile = 0, pre_warps = 0;
+                in.pre_tile = 0;
+                in.pre_warps = 0;
                 if (COMPACT) {
-                    pre_tile = t.lookback[tile_base + tile];
-                    pre_warps = t.lookback[t.lookback_capacity + tile_base + tile];
+                    in.pre_tile = t.lookback[tile_base + tile_i];
+                    in.pre_warps = t.lookback[t.lookback_capacity + tile_base + tile_i];
                 }
+                return in;
+            };
+            auto process_tile = [&](const TileIn &in) {
+                const bool valid = in.valid;
+                const uint32_t slot = in.slot;
                 // ---- reference src/core.rs:591-658 for a static stream (rotation and angular velocity
                 // are per-stream constants that :645-650 map to themselves)
-                const float lifetime = klife ? K.x : ps.const_lifetime, iscale = V.w;
-                const float age = A.w + dt;                      // :594
+                const float lifetime = klife ? in.K.x : ps.const_lifetime, iscale = in.V.w;
+                const float age = in.A.w + dt;                   // :594
                 const bool alive = valid && !(age >= lifetime);  // :596-599
                 uint32_t dslot = slot;
                 if (COMPACT) {
                     const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
                     const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
-                    const uint32_t excl = (uint32_t)pre_tile + (warp ? (uint32_t)(pre_warps >> (8u * (warp - 1u))) & 255u : 0u);
+                    const uint32_t excl = (uint32_t)in.pre_tile + (warp ? (uint32_t)(in.pre_warps >> (8u * (warp - 1u))) & 255u : 0u);
                     const uint32_t dead_before = excl + __popc(valid_mask & ~alive_mask & ((1u << lane) - 1u));
-                    dslot = wrap(dst_base + ((q - shift) - dead_before), cap);
+                    dslot = wrap(dst_base + ((in.q - shift) - dead_before), cap);
                 } else {
                     n_dead += (valid && !alive) ? 1u : 0u;
                 }
                 if (alive) {
                     const float age_percent = age / lifetime;                                // :601
                     const float scale = iscale * sample_curve(ps.scale_curve, age_percent);  // :602-605
-                    const V3 vel = v3(V.x, V.y, V.z);
-                    const V3 pos = v3(A.x, A.y, A.z) + vel * dt;                             // :619-623
+                    const V3 vel = v3(in.V.x, in.V.y, in.V.z);
+                    const V3 pos = v3(in.A.x, in.A.y, in.A.z) + vel * dt;                    // :619-623
                     const V3 acc = v3(ps.acceleration[0], ps.acceleration[1], ps.acceleration[2]);
                     const V3 nvel = vel + (acc - vel * ps.linear_drag) * dt;                 // :641-643
                     // ---- stores: 28 B + the colours / scale that vary (+ 8 B when the lifetime does)
-                    uint8_t *const drow = COMPACT ? base + (size_t)dslot * 16u : row;
+                    uint8_t *const drow = base + (size_t)dslot * 16u;
                     st_pack((float4 *)drow, make_float4(pos.x, pos.y, pos.z, age));
                     st_pack((float4 *)(drow + 2u * cap16), make_float4(nvel.x, nvel.y, nvel.z, iscale));
                     if (klife) st_pack((float2 *)(base + 3u * cap16 + cap16 / 2u) + dslot, make_float2(lifetime, age)); // (lifetime, copy of age): what count_kernel reads
@@ -1371,6 +1387,27 @@ __global__ void __launch_bounds__(kUpdateThreads, COMPACT ? FW_MINB_COMPACT : FW
                     mx2 = fmaxf(mx2, pos.z + scale);
                     n_alive++;
                 }
+            };
+            while (tile < seg_end) {
+                if (q - tid >= q_end) { // tiles past the stream's real count (the host's tile table holds upper bounds)
+                    tile = seg_end;
+                    break;
+                }
+#if FW_STATIC_UNROLL == 2
+                // two tiles per trip: four LDG.128 in flight per thread before the first is used
+                const bool two = tile + 1u < seg_end && q - tid + (uint32_t)kTile < q_end;
+                const TileIn a = load_tile(tile, q);
+                TileIn b = a;
+                if (two) b = load_tile(tile + 1u, q + (uint32_t)kTile);
+                process_tile(a);
+                if (two) process_tile(b);
+                tile += two ? 2u : 1u;
+                q += two ? 2u * (uint32_t)kTile : (uint32_t)kTile;
+#else
+                process_tile(load_tile(tile, q));
+                tile++;
+                q += (uint32_t)kTile;
+#endif
             }
             // ---- end of the segment: one reduction per warp
             const uint32_t warp_alive = __reduce_add_sync(0xffffffffu, n_alive);
