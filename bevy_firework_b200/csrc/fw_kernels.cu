@@ -8,7 +8,11 @@
 //   update_kernel   reference src/core.rs:591-658 (+ :744-800 when COLLIDE), fused with death
 //                   handling (FIFO ring advance, or stable compaction out of place inside the ring
 //                   with deaths precounted by count_kernel / scan_kernel), the destroyed-
-//                   particle stream (:588,597,637) and the per-stream AABB (src/render.rs:677-703)
+//                   particle stream (:588,597,637) and the per-stream AABB (src/render.rs:677-703);
+//                   tiles dealt round robin, settings staged by bulk async copies: rotating and
+//                   colliding streams
+//   update_static_kernel  the same for static streams without a sweep (C1..C4 of BASELINE.json):
+//                   32 B in / 48 B out per particle, stream segments instead of tiles, no barrier
 //   pack kernels    assemble the 64-byte ParticleInstance rows (src/render.rs:95-115) of the
 //                   live particles into one contiguous buffer (render extract / all-gather)
 //   gather/scatter  ParticleData rows of one stream <-> the SoA packs (host mirror)
@@ -656,16 +660,6 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 #ifndef FW_STATIC_UNROLL
 #define FW_STATIC_UNROLL 1 // static update: tiles per loop trip (2: twice the loads in flight per thread)
 #endif
-#ifndef FW_PREFETCH
-#define FW_PREFETCH 0 // static update: 0 none (measured best), 1 prefetch.global.L1, 2 prefetch.global.L2
-#endif
-__device__ __forceinline__ void prefetch_pack(const void *p) {
-#if FW_PREFETCH == 2
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

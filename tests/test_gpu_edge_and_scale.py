@@ -267,3 +267,41 @@ def test_randomized_mixed_scene(engine, oracle, seed):
             assert engine.counts(key) == w.counts(key), f"frame {k} spawner {key} ({spawners[key][0]})"
     for key, (kind, _) in spawners.items():
         assert_rows_match(engine.read_particles(key, 0), w.read_particles(key, 0), what=f"spawner {key} ({kind})")
+
+
+def test_failed_frame_leaves_pacing_untouched():
+    """fw_frame advances emission clocks while it plans the frame; when a later step fails (here: a
+    OneShot that would exceed 2^32 particles in one stream) every emitter and spawner is put back, so
+    the failed call changed nothing (non-zero status, state untouched)"""
+    from bevy_firework_b200._native import Engine, FireworkError
+
+    a = stress_spawner(rate=1700.0)
+    huge = ParticleSpawner(particle_settings=[ParticleSettings(lifetime=RandF32.constant(1.0))],
+                           emission_settings=[EmissionSettings(emission_pacing=EmissionPacing.OneShot(5_000_000_000))])
+    inp = [frame_input(1, (0.0, 0.1, 0.0))]
+
+    def run(with_failure):
+        eng = Engine(device=0, seed=0x00F12E00)
+        ps, nt, es, ne = a.pods()
+        eng.spawner_reset(1, ps, nt, es, ne, True)
+        counts = []
+        for k in range(12):
+            if with_failure and k == 4:
+                hps, hnt, hes, hne = huge.pods()
+                eng.spawner_reset(2, hps, hnt, hes, hne, True)
+                for _ in range(2):  # fails the same way twice: the OneShot emitter was re-enabled too
+                    with pytest.raises(FireworkError) as e:
+                        eng.frame(DT, inp + [frame_input(2, (0.0, 0.0, 0.0))])
+                    assert e.value.code == _abi.FW_ERR_OUT_OF_MEMORY
+                assert eng.status(2).active == 1
+                eng.spawner_remove(2)
+            eng.frame(DT, inp)
+            counts.append(eng.counts(1)[0])
+        rows = eng.read_particles(1, 0)
+        eng.close()
+        return counts, rows
+
+    c0, r0 = run(False)
+    c1, r1 = run(True)
+    assert c0 == c1
+    assert r0.tobytes() == r1.tobytes()
