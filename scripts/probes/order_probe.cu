@@ -6,10 +6,12 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-__global__ void __launch_bounds__(256, 5) walk(float4 *A, float4 *V, float4 *O, size_t n_tiles, int contiguous, int rounds_per_share) {
+// team > 0: teams of `team` consecutive CTAs share one contiguous range and deal its tiles round robin
+__global__ void __launch_bounds__(256, 5) walk(float4 *A, float4 *V, float4 *O, size_t n_tiles, int contiguous, int team) {
     const size_t per = (n_tiles + gridDim.x - 1) / gridDim.x;
     for (size_t k = 0; k < per; k++) {
-        const size_t tile = contiguous ? (size_t)blockIdx.x * per + k : (size_t)blockIdx.x + k * gridDim.x;
+        size_t tile = contiguous ? (size_t)blockIdx.x * per + k : (size_t)blockIdx.x + k * gridDim.x;
+        if (team > 0) tile = (size_t)(blockIdx.x / team) * per * team + (blockIdx.x % team) + k * team;
         if (tile >= n_tiles) break;
         const size_t i = tile * 256 + threadIdx.x;
         float4 a = A[i], v = V[i];
@@ -19,7 +21,6 @@ __global__ void __launch_bounds__(256, 5) walk(float4 *A, float4 *V, float4 *O, 
         V[i] = v;
         O[i] = make_float4(a.w, a.w * 0.5f, 1.0f - a.w, 1.0f);
     }
-    (void)rounds_per_share;
 }
 
 int main() {
@@ -28,7 +29,7 @@ int main() {
     cudaMalloc(&A, n * 16); cudaMalloc(&V, n * 16); cudaMalloc(&O, n * 16);
     cudaMemset(A, 0, n * 16); cudaMemset(V, 0, n * 16);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int grid : {740, 592, 888, 1480}) {
+    for (int grid : {740, 592}) {
         for (int contiguous = 0; contiguous < 2; contiguous++) {
             for (int w = 0; w < 3; w++) walk<<<grid, 256>>>(A, V, O, n_tiles, contiguous, 0);
             cudaEventRecord(e0);
@@ -37,6 +38,16 @@ int main() {
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
             printf("grid %4d %-22s %.4f ms  %.0f GB/s\n", grid, contiguous ? "contiguous shares" : "grid-stride tiles", ms, n * 80.0 / (ms * 1e-3) / 1e9);
+        }
+        for (int team : {2, 4, 8, 16, 37, 74, 148}) {
+            if (grid % team) continue;
+            for (int w = 0; w < 3; w++) walk<<<grid, 256>>>(A, V, O, n_tiles, 1, team);
+            cudaEventRecord(e0);
+            const int reps = 20;
+            for (int r = 0; r < reps; r++) walk<<<grid, 256>>>(A, V, O, n_tiles, 1, team);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+            printf("grid %4d teams of %-13d %.4f ms  %.0f GB/s\n", grid, team, ms, n * 80.0 / (ms * 1e-3) / 1e9);
         }
     }
     return 0;
