@@ -84,6 +84,15 @@ def make_workload(name: str, rank: int):
         return ("C5 stress_test_collision.rs x8 spawners, rate 63000/s, lifetime 2 s, 256 cuboid colliders (~1 M live)",
                 [(base + i, sp, t, r) for i, (t, r) in enumerate(W.collision_ring(8))],
                 W.collision_scene_colliders(256), 124, None)
+    if name == "c5d":
+        # C5 with destroy_on_collision: a particle dies at its first hit, deaths are only known after the
+        # sweep -> the compacting update with decoupled look-back (no BASELINE config; the variant's number)
+        sp = W.collision_spawner(rate=125000.0)
+        sp.particle_settings[0].collision_settings.destroy_on_collision = True
+        return ("C5d = stress_test_collision.rs x8 spawners, rate 125000/s, destroy_on_collision, 256 cuboid colliders "
+                "(look-back compaction; ~1 M live)",
+                [(base + i, sp, t, r) for i, (t, r) in enumerate(W.collision_ring(8))],
+                W.collision_scene_colliders(256), 124, None)
     if name == "c4":
         return ("C4 one_shot.rs: one new OneShot(100000) spawner per frame, lifetime 2.5 s (~15 M live)",
                 [], None, 152, (W.one_shot_spawner(100000, 2.5), base))
@@ -237,7 +246,7 @@ def run_cpu(workload: str, steps: int, warmup: int, threads: int, budget_s: floa
         n_all = len(make_workload(workload, 0)[1])
         fill = make_workload(workload, 0)[3]
         if n_all:
-            per_spawner_frame_s = {"c5": 8.0e-3}.get(workload, 0.175 / 512.0 * (16.0 / max(threads, 1)))
+            per_spawner_frame_s = {"c5": 8.0e-3, "c5d": 8.0e-3}.get(workload, 0.175 / 512.0 * (16.0 / max(threads, 1)))
             fit = int(budget_s / ((fill + warmup + steps) * per_spawner_frame_s))
             max_spawners = max(min(n_all, threads), min(n_all, fit - fit % max(threads, 1)))
     sc = Scene(b, workload, 0, max_spawners=max_spawners)
@@ -263,7 +272,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c3g", "c3r", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c3g", "c3r", "c4", "c5", "c5d"])
     ap.add_argument("--cpu-steps", type=int, default=8, help="timed frames of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=120.0,
@@ -649,13 +658,13 @@ def parity_check(workload: str, device: int):
     class Backend(O.OracleWorld, OracleBackendTag):
         pass
 
-    n = {"c5": 2, "c4": 0}.get(workload, 4)
+    n = {"c5": 2, "c5d": 2, "c4": 0}.get(workload, 4)
     if n == 0:
         return None
     e = Engine(device=device, seed=W.SEED)
-    b = Backend(seed=W.SEED, n_threads=4, cull=workload == "c5")
+    b = Backend(seed=W.SEED, n_threads=4, cull=workload in ("c5", "c5d"))
     se, sb = Scene(e, workload, 0, max_spawners=n), Scene(b, workload, 0, max_spawners=n)
-    frames = {"c5": 130}.get(workload, 70)
+    frames = {"c5": 130, "c5d": 130}.get(workload, 70)
     for _ in range(frames):
         se.step()
         sb.step()

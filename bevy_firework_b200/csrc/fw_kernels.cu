@@ -1733,3 +1733,11 @@ cudaError_t launch_ring_copy(const StreamDesc &src, uint32_t first, uint32_t n, 
 }
 
 } // namespace fw
+
+#ifdef FW_COLLIDE_STATS
+extern "C" int fw_debug_collide_stats(unsigned long long *out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, fw::g_collide_stats, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(fw::g_collide_stats, z, sizeof z); }
+    return 0;
+}
+#endif

@@ -376,6 +376,12 @@ __device__ __noinline__ bool ray_frustum_local(float r0, float r1, float h, V3 o
 // REVOLVED: the collider set contains cylinders / cones (their exact test costs the cuboid /
 // sphere scenes registers, so it is compiled in only when the set needs it: C5 0.123 vs 0.129 ms).
 constexpr uint32_t kCandQueue = 4;
+#ifdef FW_COLLIDE_STATS
+__device__ unsigned long long g_collide_stats[16];
+#define FW_STAT(i, v) atomicAdd(&g_collide_stats[i], (unsigned long long)(v))
+#else
+#define FW_STAT(i, v)
+#endif
 __device__ __forceinline__ float grid_coord(float x, float lo, float inv_cell) { return floorf((x - lo) * inv_cell); }
 template <bool REVOLVED>
 __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ colliders, const uint8_t *__restrict__ bp,
@@ -427,6 +433,22 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
     const uint32_t n_big = h.n_big, span = base >> 24;
     uint32_t k = (act && !use_grid) ? 0u : n_nodes;
     bool more;
+#ifdef FW_COLLIDE_STATS
+    uint32_t st_total = 0, st_nonempty = 0;
+    FW_STAT(0, act ? 1 : 0);                 // rays
+    FW_STAT(1, (act && use_grid) ? 1 : 0);   // rays on the grid path
+    if ((threadIdx.x & 31u) == 0) FW_STAT(2, 1); // warp-level casts
+    if (act && use_grid && sub < 8u) {
+        for (uint32_t s2 = 0;;) {
+            const uint32_t cx = (base & 255u) + (s2 & 1u), cy = ((base >> 8) & 255u) + ((s2 >> 1) & 1u), cz = ((base >> 16) & 255u) + (s2 >> 2);
+            const uint32_t cell = (cz * h.dim[1] + cy) * h.dim[0] + cx;
+            if (cell_start[cell + 1] > cell_start[cell]) st_nonempty = 1;
+            s2 = (s2 - span) & span;
+            if (s2 == 0u) break;
+        }
+    }
+    FW_STAT(3, st_nonempty);                 // rays with a non-empty cell
+#endif
     do {
         uint32_t cnt = 0;
         if (use_grid) {
@@ -477,6 +499,11 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
             more = k < n_nodes;
         }
         const uint32_t rounds = __reduce_max_sync(0xffffffffu, cnt);
+#ifdef FW_COLLIDE_STATS
+        st_total += cnt;
+        FW_STAT(4, cnt);                              // exact tests
+        if ((threadIdx.x & 31u) == 0) { FW_STAT(5, rounds); FW_STAT(6, 1); } // warp exact rounds, warp enumeration rounds
+#endif
         for (uint32_t j = 0; j < rounds; j++) {
             if (j < cnt) {
                 const uint32_t cand = queue[j * kUpdateThreads];
@@ -505,6 +532,11 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
             __syncwarp();
         }
     } while (__any_sync(0xffffffffu, more));
+#ifdef FW_COLLIDE_STATS
+    FW_STAT(7, st_total > 0 ? 1 : 0); // rays with at least one exact test
+    FW_STAT(8, found ? 1 : 0);        // rays that hit
+    FW_STAT(9, __any_sync(0xffffffffu, st_total > 0) && (threadIdx.x & 31u) == 0 ? 1 : 0); // warp casts with any exact test
+#endif
     distance = best;
     normal = best_n;
     return found;
