@@ -445,13 +445,22 @@ template <bool STEP, int COLLIDE>
 __global__ void __launch_bounds__(256, COLLIDE ? FW_MINB_COLLIDE : 5) spawn_kernel(DeviceTables t, FrameDeviceInputs f, uint32_t phase) {
     static_assert(kUpdateThreads == 256, "the candidate queue is laid out for 256-thread CTAs");
     __shared__ uint32_t s_cmd;
+    __shared__ uint32_t s_first[256];
     __shared__ CandQueue<(STEP && COLLIDE != 0)> cq;
     const PhaseInfo ph = f.header->phase[phase];
     const float dt = f.header->dt;
     const uint32_t n_slots = f.header->n_slots;
     for (uint32_t base = blockIdx.x * blockDim.x; base < ph.total_spawn; base += gridDim.x * blockDim.x) {
-        // one binary search per CTA chunk (a chunk of 256 particles spans very few commands)
+        // one binary search per CTA chunk, then the `first` of the (at most 256: every command has
+        // count > 0) commands that begin inside the chunk go to shared memory, where every thread
+        // finds its own. (A scene of many slow emitters has one command per particle: walking the
+        // command list per thread was 90 us for 256 particles from 512 spawners.)
         if (threadIdx.x == 0) s_cmd = find_cmd(f, ph.cmd_begin, ph.cmd_end, base);
+        __syncthreads();
+        {
+            const uint32_t c = s_cmd + threadIdx.x;
+            s_first[threadIdx.x] = c < ph.cmd_end ? f.cmds[c].first : 0xFFFFFFFFu;
+        }
         __syncthreads();
         const uint32_t g = base + threadIdx.x;
         const bool in_range = g < ph.total_spawn;
@@ -460,8 +469,12 @@ __global__ void __launch_bounds__(256, COLLIDE ? FW_MINB_COLLIDE : 5) spawn_kern
         StreamDesc d{};
         ParticleRegs p{};
         if (in_range) {
-            uint32_t c = s_cmd;
-            while (c + 1u < ph.cmd_end && f.cmds[c + 1u].first <= g) c++;
+            uint32_t lo = 0, hi = 256; // last i with s_first[i] <= g (s_first[0] <= base <= g)
+            while (hi - lo > 1u) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_first[mid] <= g) lo = mid; else hi = mid;
+            }
+            const uint32_t c = s_cmd + lo;
             const SpawnCmd cmd = f.cmds[c];
             stream = cmd.stream;
             d = t.descs[stream];

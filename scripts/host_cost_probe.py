@@ -28,5 +28,16 @@ for n in (1, 64, 512, 2048):
     t1 = time.perf_counter()
     eng.sync()
     t2 = time.perf_counter()
+    # host-only cost: 3 submissions into an idle ring (4 slots: no back-pressure), GPU drained in between
+    acc = 0.0
+    R = 300
+    for _ in range(R):
+        eng.sync()
+        a = time.perf_counter()
+        for _ in range(3):
+            eng._L.fw_frame(eng._ctx, DT, arr, n)
+        acc += time.perf_counter() - a
+    host_only = 1e6 * acc / (3 * R)
+    print(f"spawners {n:5d}: host-only {host_only:6.2f} us/frame (3 frames into an idle ring)", flush=True)
     print(f"spawners {n:5d}: submit {1e6*(t1-t0)/K:7.2f} us/frame, incl. drain {1e6*(t2-t0)/K:7.2f} us/frame, live {eng.total_live()}", flush=True)
     eng.close()

@@ -305,3 +305,22 @@ def test_failed_frame_leaves_pacing_untouched():
     c1, r1 = run(True)
     assert c0 == c1
     assert r0.tobytes() == r1.tobytes()
+
+
+def test_many_slow_emitters_one_command_per_particle(engine, oracle):
+    """600 spawners at 45 particles/s: most spawn commands of a frame carry one particle, so a 256-particle
+    chunk of the spawn kernel spans hundreds of commands (each thread finds its own in shared memory);
+    two of the spawners fire fast, so chunks with one long command and many short ones exist too."""
+    w = oracle.OracleWorld(n_threads=4)
+    slow, fast = stress_spawner(rate=45.0, lifetime=0.8), stress_spawner(rate=40000.0, lifetime=0.2)
+    pos = grid_positions(600)
+    for i in range(600):
+        reset_both(engine, w, 1 + i, fast if i in (7, 311) else slow)
+    inputs = [frame_input(1 + i, p) for i, p in enumerate(pos)]
+    for k in range(75):
+        engine.frame(DT, inputs)
+        w.frame(DT, inputs)
+    for i in range(600):
+        assert engine.counts(1 + i) == w.counts(1 + i), i
+    for i in (0, 7, 8, 255, 256, 311, 599):
+        assert_rows_match(engine.read_particles(1 + i, 0), w.read_particles(1 + i, 0), f"spawner {i}")
