@@ -182,7 +182,19 @@ def test_c3_full_size_properties(oracle):
     eng.close()
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def _fuzz_seeds():
+    """seeds 1..6 always; FW_FUZZ_SEEDS=a-b adds a longer campaign (profiles/r2: 7-160 run once on the GPU box)"""
+    import os
+
+    seeds = [1, 2, 3, 4, 5, 6]
+    extra = os.environ.get("FW_FUZZ_SEEDS", "")
+    if "-" in extra:
+        a, b = extra.split("-")
+        seeds += [s for s in range(int(a), int(b) + 1) if s not in seeds]
+    return seeds
+
+
+@pytest.mark.parametrize("seed", _fuzz_seeds())
 def test_randomized_mixed_scene(engine, oracle, seed):
     """a seeded random scene replayed on both sides: spawners of every update variant in one
     context (FIFO, compacting, colliding, colliding + destroy), random shapes / curves / rates,
