@@ -336,3 +336,44 @@ def test_many_slow_emitters_one_command_per_particle(engine, oracle):
         assert engine.counts(1 + i) == w.counts(1 + i), i
     for i in (0, 7, 8, 255, 256, 311, 599):
         assert_rows_match(engine.read_particles(1 + i, 0), w.read_particles(1 + i, 0), f"spawner {i}")
+
+
+def test_long_run_ring_wraparound(engine, oracle):
+    """thousands of frames on small rings: the FIFO heads wrap their blocks hundreds of times, the
+    compacting streams flip their halves every frame, the emission clocks go through thousands of
+    cycles, the look-back epochs advance; counts every 25 frames, every row at the end.
+    FW_LONG_FRAMES overrides the length (profiles/r2: 20000 once)."""
+    import os
+
+    from bevy_firework_b200 import ParticleCollisionSettings
+    from bevy_firework_b200.workloads import cuboid
+
+    frames = int(os.environ.get("FW_LONG_FRAMES", "3000"))
+    w = oracle.OracleWorld()
+    cols = [cuboid((30, 1, 30), (0, -0.5, 0)), cuboid((30, 0.5, 30), (0, 2.5, 0.0))]  # floor, and a ceiling the sparks reach
+    engine.set_colliders(cols)
+    w.set_colliders(cols)
+    kinds = {
+        1: stress_spawner(rate=700.0, lifetime=0.25),                                   # FIFO, ~175 live, capacity_hint below
+        2: stress_spawner(rate=900.0, lifetime=0.3),
+        3: stress_spawner(rate=500.0, lifetime=0.4),
+        4: stress_spawner(rate=650.0, lifetime=0.35),
+    }
+    kinds[1].particle_settings[0].capacity_hint = 64
+    kinds[2].particle_settings[0].lifetime = RandF32(0.1, 0.5)                         # compacting
+    kinds[3].particle_settings[0].collision_settings = ParticleCollisionSettings(0.5, 0.2, False)  # FIFO + sweep
+    kinds[4].particle_settings[0].collision_settings = ParticleCollisionSettings(0.5, 0.2, True)   # look-back
+    kinds[4].particle_settings[0].lifetime = RandF32(0.2, 0.5)
+    for key, sp in kinds.items():
+        reset_both(engine, w, key, sp)
+    inputs = [frame_input(key, (0.3 * key, 1.5, 0.0)) for key in kinds]
+    for k in range(frames):
+        engine.frame(DT, inputs)
+        w.frame(DT, inputs)
+        if k % 25 == 24:
+            for key in kinds:
+                assert engine.counts(key) == w.counts(key), f"frame {k} spawner {key}"
+    for key in kinds:
+        assert_rows_match(engine.read_particles(key, 0), w.read_particles(key, 0), what=f"spawner {key}")
+    assert (w.read_particles(3, 0)["velocity"][:, 1] < 0).any()      # some bounced off the ceiling
+    assert len(w.read_particles(4, 0)) < len(w.read_particles(2, 0))  # some died on it
