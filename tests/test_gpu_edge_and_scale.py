@@ -377,3 +377,40 @@ def test_long_run_ring_wraparound(engine, oracle):
         assert_rows_match(engine.read_particles(key, 0), w.read_particles(key, 0), what=f"spawner {key}")
     assert (w.read_particles(3, 0)["velocity"][:, 1] < 0).any()      # some bounced off the ceiling
     assert len(w.read_particles(4, 0)) < len(w.read_particles(2, 0))  # some died on it
+
+
+def test_profile_counters_and_events_while_toggling_profiling(engine, oracle):
+    """fw_set_profiling / fw_profile_sum / fw_event_record: the counters are exact (particles that
+    entered the update, particles spawned), timed frames run kernel by kernel and untimed ones as
+    graphs -- switching between the two mid-run must not change a bit of the state."""
+    sp = stress_spawner(rate=9000.0, lifetime=0.5)
+    w = oracle.OracleWorld()
+    reset_both(engine, w, 1, sp)
+    inp = [frame_input(1, (0.0, 0.1, 0.0))]
+    assert engine.stream_handle != 0
+    engine.profile_reset()
+    engine.event_record(0)
+    entered = 0
+    for k in range(120):
+        if k % 20 == 0:
+            engine.set_profiling((k // 20) % 2 == 1)  # 20 frames untimed (graphs once warm), 20 timed, ...
+        engine.frame(DT, inp)
+        w.spawn_only(DT, inp)      # spawn_particles (src/core.rs:302-330) ...
+        entered += w.total_live()  # ... every particle present then enters update_particles (:577-670)
+        w.update_only(DT)
+    engine.event_record(1)
+    engine.sync()
+    assert engine.event_elapsed_ms(0, 1) > 0.0
+    p, n = engine.profile_sum()
+    assert n == 120 and p.kernel_launches >= 120
+    rows_g, rows_w = engine.read_particles(1, 0), w.read_particles(1, 0)
+    assert_rows_match(rows_g, rows_w)
+    # exact counters: spawned = what the oracle's emission arithmetic spawned over the run
+    t = last = 0.0
+    total = 0
+    for _ in range(120):
+        t = oracle.lib().fwo_rem_euclid(float(f32(t) + f32(DT)), 1.0)
+        c, last = oracle.compute_emission_count(t, last, 1.0, 0.0, 1.0, 9000.0)
+        total += c
+    assert p.particles_spawned == total and p.particles_updated == entered
+    assert p.timed_frames == 60 and p.update_ms > 0.0
