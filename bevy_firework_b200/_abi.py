@@ -28,7 +28,7 @@ FW_PACING_ONE_SHOT, FW_PACING_ON_DEMAND, FW_PACING_COUNT_OVER_DURATION = 0, 1, 2
 FW_MODE_GLOBAL, FW_MODE_NESTED = 0, 1
 FW_SHAPE_POINT, FW_SHAPE_SPHERE, FW_SHAPE_CIRCLE = 0, 1, 2
 FW_TRANSFORM_GLOBAL, FW_TRANSFORM_LOCAL = 0, 1
-FW_COLLIDER_CUBOID, FW_COLLIDER_SPHERE, FW_COLLIDER_CYLINDER, FW_COLLIDER_CONE = 0, 1, 2, 3
+FW_COLLIDER_CUBOID, FW_COLLIDER_SPHERE, FW_COLLIDER_CYLINDER, FW_COLLIDER_CONE, FW_COLLIDER_CAPSULE = 0, 1, 2, 3, 4
 FW_FLAG_PROFILE = 1
 FW_FLAG_NO_GRAPHS = 2
 FW_FLAG_NO_CONCURRENT_SPAWN = 4

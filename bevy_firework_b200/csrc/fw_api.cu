@@ -1216,11 +1216,14 @@ static void build_broadphase(const fw_collider *colliders, uint32_t n, std::vect
                                 {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
                                 {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
         for (int a = 0; a < 3; a++) {
-            // local half extents: cylinder / cone = (r, h, r)
-            const double hz = (c.kind == FW_COLLIDER_CYLINDER || c.kind == FW_COLLIDER_CONE) ? c.half_extents[0] : c.half_extents[2];
+            // local half extents: cylinder / cone = (r, h, r), capsule = (r, h + r, r)
+            const bool about_y = c.kind == FW_COLLIDER_CYLINDER || c.kind == FW_COLLIDER_CONE || c.kind == FW_COLLIDER_CAPSULE;
+            const double hz = about_y ? c.half_extents[0] : c.half_extents[2];
+            const double hy = c.kind == FW_COLLIDER_CAPSULE ? std::fabs((double)c.half_extents[1]) + std::fabs((double)c.half_extents[0])
+                                                            : (double)c.half_extents[1];
             double ext = c.kind == FW_COLLIDER_SPHERE
                              ? std::fabs((double)c.half_extents[0])
-                             : std::fabs(R[a][0] * c.half_extents[0]) + std::fabs(R[a][1] * c.half_extents[1]) + std::fabs(R[a][2] * hz);
+                             : std::fabs(R[a][0] * c.half_extents[0]) + std::fabs(R[a][1] * hy) + std::fabs(R[a][2] * hz);
             const double margin = 1e-3 + 1e-3 * (std::fabs((double)c.translation[a]) + ext);
             // a non-finite bound (NaN transform) becomes the whole line: it never culls
             lo[3 * i + a] = bvh_sane((float)(c.translation[a] - ext - margin), -FLT_MAX);
@@ -1364,7 +1367,7 @@ int fw_host_emission_count(float time_passed_in_cycle, float last_emission, floa
 int fw_host_build_broadphase(const fw_collider *colliders, uint32_t n, void *out, uint64_t cap_bytes, uint64_t *n_bytes) {
     if (n && !colliders) return FW_ERR_INVALID_ARGUMENT;
     for (uint32_t i = 0; i < n; i++)
-        if (colliders[i].kind > FW_COLLIDER_CONE) return FW_ERR_UNSUPPORTED;
+        if (colliders[i].kind > FW_COLLIDER_CAPSULE) return FW_ERR_UNSUPPORTED;
     std::vector<uint8_t> blob;
     if (n) build_broadphase(colliders, n, blob);
     if (n_bytes) *n_bytes = blob.size();
@@ -1378,7 +1381,7 @@ int fw_set_colliders(fw_context *ctx, const fw_collider *colliders, uint32_t n) 
     ENTER(ctx);
     if (n && !colliders) return fail(ctx, FW_ERR_INVALID_ARGUMENT, "fw_set_colliders: null");
     for (uint32_t i = 0; i < n; i++)
-        if (colliders[i].kind > FW_COLLIDER_CONE) return fail(ctx, FW_ERR_UNSUPPORTED, "collider %u: only cuboids, spheres, cylinders and cones are supported", i);
+        if (colliders[i].kind > FW_COLLIDER_CAPSULE) return fail(ctx, FW_ERR_UNSUPPORTED, "collider %u: only cuboids, spheres, cylinders, cones and capsules are supported", i);
     // Same collider count as before (moving colliders, re-sent every physics step): same buffers,
     // same kernel arguments, the copies below are ordered on the context's stream between the
     // frames around them -- no synchronisation, captured frame graphs stay valid. A different

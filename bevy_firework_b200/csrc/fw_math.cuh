@@ -354,6 +354,61 @@ __device__ __noinline__ bool ray_frustum_local(float r0, float r1, float h, V3 o
     normal = bn;
     return true;
 }
+// Capsule: the segment (0,-h,0)..(0,h,0) swept by a ball of radius r; the oracle's ray_capsule_local
+// operation by operation (candidates: side, bottom cap, top cap; entering roots only).
+__device__ __noinline__ bool ray_capsule_local(float r, float h, V3 o, V3 d, float max_toi, float &toi, V3 &normal) {
+    const float yc = fminf(fmaxf(o.y, -h), h);
+    const float dy0 = o.y - yc;
+    if (o.x * o.x + dy0 * dy0 + o.z * o.z <= r * r) {
+        toi = 0.0f;
+        normal = v3(0.0f, 0.0f, 0.0f);
+        return true;
+    }
+    bool found = false;
+    float best = 0.0f;
+    V3 bn = v3(0.0f, 0.0f, 0.0f);
+    const float inv_r = 1.0f / r;
+    {
+        const float A = d.x * d.x + d.z * d.z;
+        const float B = o.x * d.x + o.z * d.z;
+        const float C = o.x * o.x + o.z * o.z - r * r;
+        if (A != 0.0f) {
+            const float disc = B * B - A * C;
+            if (disc >= 0.0f) {
+                const float t = (-B - sqrtf(disc)) / A;
+                const float y = o.y + d.y * t;
+                if (t >= 0.0f && y >= -h && y <= h) {
+                    found = true;
+                    best = t;
+                    bn = v3((o.x + d.x * t) * inv_r, 0.0f, (o.z + d.z * t) * inv_r);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int cap = 0; cap < 2; cap++) {
+        const float cy = cap ? h : -h;
+        const V3 oc = v3(o.x, o.y - cy, o.z);
+        const float a = dot(d, d), b = dot(oc, d), c = dot(oc, oc) - r * r;
+        if (a != 0.0f) {
+            const float disc = b * b - a * c;
+            if (disc >= 0.0f) {
+                const float t = (-b - sqrtf(disc)) / a;
+                const V3 p = oc + d * t;
+                const bool outer = cap ? p.y >= 0.0f : p.y <= 0.0f;
+                if (t >= 0.0f && outer && (!found || t < best)) {
+                    found = true;
+                    best = t;
+                    bn = p * inv_r;
+                }
+            }
+        }
+    }
+    if (!found || !(best <= max_toi)) return false;
+    toi = best;
+    normal = bn;
+    return true;
+}
 // Broad phase (blob layout: BroadPhaseHeader in fw_internal.h). Every candidate passes a box test
 // of the ray segment's AABB against the collider's inflated world AABB; the boxes are inflated on
 // the host by far more than any fp32 rounding of the exact test, so a collider is skipped only
@@ -519,6 +574,7 @@ __device__ __forceinline__ bool cast_ray(const fw_collider *__restrict__ collide
                 if (c.kind == FW_COLLIDER_SPHERE) hit = ray_ball_local(c.half_extents[0], ol, dl, max_distance, toi, nl);
                 else if (REVOLVED && c.kind == FW_COLLIDER_CYLINDER) hit = ray_frustum_local(c.half_extents[0], c.half_extents[0], c.half_extents[1], ol, dl, max_distance, toi, nl);
                 else if (REVOLVED && c.kind == FW_COLLIDER_CONE) hit = ray_frustum_local(c.half_extents[0], 0.0f, c.half_extents[1], ol, dl, max_distance, toi, nl);
+                else if (REVOLVED && c.kind == FW_COLLIDER_CAPSULE) hit = ray_capsule_local(c.half_extents[0], c.half_extents[1], ol, dl, max_distance, toi, nl);
                 else hit = ray_cuboid_local(v3(c.half_extents[0], c.half_extents[1], c.half_extents[2]), ol, dl, max_distance, toi, nl);
                 // SpatialQueryFilter::excluded_entities (src/core.rs:247,764): a listed collider is not seen
                 for (uint32_t x = 0; x < cs.n_excluded; x++) hit = hit && cs.excluded_keys[x] != c.key;

@@ -184,6 +184,11 @@ def cone(radius, height, translation, rotation=(0.0, 0.0, 0.0, 1.0), layers: int
     return _revolved(_abi.FW_COLLIDER_CONE, radius, height, translation, rotation, layers)
 
 
+def capsule(radius, length, translation, rotation=(0.0, 0.0, 0.0, 1.0), layers: int = 1) -> _abi.fw_collider:
+    """``Collider::capsule(radius, length)``, axis +Y: a segment of ``length`` swept by a ball."""
+    return _revolved(_abi.FW_COLLIDER_CAPSULE, radius, length, translation, rotation, layers)
+
+
 def grid_positions(n: int, spacing: float = 2.0, y: float = 0.1) -> List[Tuple[float, float, float]]:
     """n spawners on a near-square grid (C2: 8x8, C3: 32x16)."""
     cols = int(math.ceil(math.sqrt(n)))

@@ -200,8 +200,10 @@ enum fw_collider_kind {
     FW_COLLIDER_CUBOID = 0,   /* Collider::cuboid(x, y, z): half_extents = (x/2, y/2, z/2) */
     FW_COLLIDER_SPHERE = 1,   /* Collider::sphere(r): half_extents[0] = r */
     FW_COLLIDER_CYLINDER = 2, /* Collider::cylinder(r, height), axis +Y: half_extents = (r, height/2, -) */
-    FW_COLLIDER_CONE = 3      /* Collider::cone(r, height), apex at +Y: half_extents = (r, height/2, -)
+    FW_COLLIDER_CONE = 3,     /* Collider::cone(r, height), apex at +Y: half_extents = (r, height/2, -)
                                  (examples/textures.rs:195,211 use both) */
+    FW_COLLIDER_CAPSULE = 4   /* Collider::capsule(r, length), axis +Y: half_extents = (r, length/2, -); the segment
+                                 from (0, -length/2, 0) to (0, length/2, 0) swept by a ball of radius r */
 };
 
 typedef struct fw_collider {

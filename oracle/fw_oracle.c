@@ -454,6 +454,63 @@ static int ray_frustum_local(float r0, float r1, float h, v3 o, v3 d, float max_
     *normal = bn;
     return 1;
 }
+/* Capsule: the segment (0,-h,0)..(0,h,0) swept by a ball of radius r (parry's Capsule; parry casts
+ * rays against it through its support map with GJK -- crate not on disk, PARITY UNPINNED -- this is
+ * the analytic solid). Solid: an origin inside gives toi 0 and a zero normal. Candidates in the
+ * order side, bottom cap, top cap; only the entering roots (the origin is outside); the first
+ * smallest one wins. */
+static int ray_capsule_local(float r, float h, v3 o, v3 d, float max_toi, float *toi, v3 *normal) {
+    const float yc = fminf(fmaxf(o.y, -h), h); /* nearest point of the segment */
+    const float dy0 = o.y - yc;
+    if (o.x * o.x + dy0 * dy0 + o.z * o.z <= r * r) {
+        *toi = 0.0f;
+        *normal = v3_make(0.0f, 0.0f, 0.0f);
+        return 1;
+    }
+    int found = 0;
+    float best = 0.0f;
+    v3 bn = v3_make(0.0f, 0.0f, 0.0f);
+    const float inv_r = 1.0f / r;
+    {
+        const float A = d.x * d.x + d.z * d.z;
+        const float B = o.x * d.x + o.z * d.z;
+        const float C = o.x * o.x + o.z * o.z - r * r;
+        if (A != 0.0f) {
+            const float disc = B * B - A * C;
+            if (disc >= 0.0f) {
+                const float t = (-B - sqrtf(disc)) / A;
+                const float y = o.y + d.y * t;
+                if (t >= 0.0f && y >= -h && y <= h) {
+                    found = 1;
+                    best = t;
+                    bn = v3_make((o.x + d.x * t) * inv_r, 0.0f, (o.z + d.z * t) * inv_r);
+                }
+            }
+        }
+    }
+    for (int cap = 0; cap < 2; cap++) {
+        const float cy = cap ? h : -h;
+        const v3 oc = v3_make(o.x, o.y - cy, o.z);
+        const float a = v3_dot(d, d), b = v3_dot(oc, d), c = v3_dot(oc, oc) - r * r;
+        if (a != 0.0f) {
+            const float disc = b * b - a * c;
+            if (disc >= 0.0f) {
+                const float t = (-b - sqrtf(disc)) / a;
+                const v3 p = v3_add(oc, v3_mul(d, t)); /* relative to the cap's centre */
+                const int outer = cap ? p.y >= 0.0f : p.y <= 0.0f;
+                if (t >= 0.0f && outer && (!found || t < best)) {
+                    found = 1;
+                    best = t;
+                    bn = v3_mul(p, inv_r);
+                }
+            }
+        }
+    }
+    if (!found || !(best <= max_toi)) return 0;
+    *toi = best;
+    *normal = bn;
+    return 1;
+}
 /* TEST HELPER (not part of the restatement): conservative boxes that let the full-size collision
  * parity tests finish in seconds. boxes[6i..6i+5] = min.xyz, max.xyz of collider i's bounding
  * sphere, inflated far beyond any fp32 rounding of the exact tests below. A collider is skipped
@@ -465,6 +522,7 @@ static void collider_cull_box(const fw_collider *c, float box[6]) {
     if (c->kind == FW_COLLIDER_SPHERE) r = fabsf(c->half_extents[0]);
     else if (c->kind == FW_COLLIDER_CUBOID)
         r = sqrtf(c->half_extents[0] * c->half_extents[0] + c->half_extents[1] * c->half_extents[1] + c->half_extents[2] * c->half_extents[2]);
+    else if (c->kind == FW_COLLIDER_CAPSULE) r = fabsf(c->half_extents[0]) + fabsf(c->half_extents[1]);
     else r = sqrtf(c->half_extents[0] * c->half_extents[0] + c->half_extents[1] * c->half_extents[1]);
     for (int a = 0; a < 3; a++) {
         const float m = 1e-3f + 1e-3f * (fabsf(c->translation[a]) + r);
@@ -515,6 +573,8 @@ static int cast_ray_impl(const fw_collider *c, uint32_t n, const float *boxes, c
             hit = ray_frustum_local(c[i].half_extents[0], c[i].half_extents[0], c[i].half_extents[1], ol, dl, max_distance, &toi, &nl);
         else if (c[i].kind == FW_COLLIDER_CONE)
             hit = ray_frustum_local(c[i].half_extents[0], 0.0f, c[i].half_extents[1], ol, dl, max_distance, &toi, &nl);
+        else if (c[i].kind == FW_COLLIDER_CAPSULE)
+            hit = ray_capsule_local(c[i].half_extents[0], c[i].half_extents[1], ol, dl, max_distance, &toi, &nl);
         else
             hit = ray_cuboid_local(v3_make(c[i].half_extents[0], c[i].half_extents[1], c[i].half_extents[2]),
                                    ol, dl, max_distance, &toi, &nl);

@@ -57,6 +57,7 @@ pub const FW_COLLIDER_CUBOID: u32 = 0;
 pub const FW_COLLIDER_SPHERE: u32 = 1;
 pub const FW_COLLIDER_CYLINDER: u32 = 2; // half_extents = (radius, height / 2, -), axis +Y
 pub const FW_COLLIDER_CONE: u32 = 3; // half_extents = (radius, height / 2, -), apex at +Y
+pub const FW_COLLIDER_CAPSULE: u32 = 4; // half_extents = (radius, length / 2, -), axis +Y
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]

@@ -26,7 +26,7 @@
 //!   curve_f32 / curve_rgba   bevy_math 0.19.0 EvenCore / UnevenCore through the crate's own
 //!                     FireworkCurve / FireworkGradient::sample_clamped (src/curve.rs:8-75,79-164)
 //!   cast_ray          parry3d 0.27.0 (through avian3d 0.7.0's Collider) cast_ray, solid = true, on
-//!                     cuboid / sphere / cylinder / cone incl. origins inside, edge and corner hits
+//!                     cuboid / sphere / cylinder / cone / capsule incl. origins inside, edge and corner hits
 //!                     (src/core.rs:756-765)
 //!   sin_cos           f32::sin_cos of the platform libm, against include/fw_sincos.h
 //!   emission_count    the crate's own compute_emission_count on random inputs (src/core.rs:553-575;
@@ -182,6 +182,7 @@ fn cast_ray_section(rng: &mut Sm, out: &mut serde_json::Map<String, Value>) {
         ("sphere", Collider::sphere(0.75), [0.75, 0.0, 0.0]),
         ("cylinder", Collider::cylinder(0.6, 2.0), [0.6, 1.0, 0.0]),
         ("cone", Collider::cone(0.5, 1.2), [0.5, 0.6, 0.0]),
+        ("capsule", Collider::capsule(0.4, 1.5), [0.4, 0.75, 0.0]),
     ];
     let mut recs = vec![];
     for (name, col, he) in &shapes {

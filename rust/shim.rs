@@ -377,7 +377,7 @@ pub fn gpu_forget_removed(gpu: ResMut<GpuParticles>, mut removed: RemovedCompone
 /// `SpatialQuery::cast_ray` (src/core.rs:756-765) sees avian's colliders as of the last physics
 /// step; the library sees what this system sends. Same count as last time = an asynchronous
 /// re-upload (moving colliders), so sending every frame is cheap. Shapes the library cannot test
-/// (anything but cuboid / ball / cylinder / cone) are skipped with a warning, once.
+/// (anything but cuboid / ball / cylinder / cone / capsule) are skipped with a warning, once.
 #[cfg(feature = "physics_avian")]
 pub fn gpu_sync_colliders(
     gpu: ResMut<GpuParticles>,
@@ -387,12 +387,23 @@ pub fn gpu_sync_colliders(
     use avian3d::parry::shape::TypedShape;
     scratch.clear();
     for (entity, collider, transform, layers) in &q {
-        let t = transform.compute_transform();
+        let mut t = transform.compute_transform();
         let (kind, half_extents) = match collider.shape_scaled().as_typed_shape() {
             TypedShape::Cuboid(c) => (FW_COLLIDER_CUBOID, [c.half_extents.x, c.half_extents.y, c.half_extents.z]),
             TypedShape::Ball(b) => (FW_COLLIDER_SPHERE, [b.radius, 0.0, 0.0]),
             TypedShape::Cylinder(c) => (FW_COLLIDER_CYLINDER, [c.radius, c.half_height, 0.0]),
             TypedShape::Cone(c) => (FW_COLLIDER_CONE, [c.radius, c.half_height, 0.0]),
+            TypedShape::Capsule(c) => {
+                // parry's capsule is any segment a..b swept by a ball; the C ABI's is about +Y through the
+                // collider's origin (what Collider::capsule(radius, length) builds): fold the rest into the pose
+                let (a, b) = (Vec3::from(c.segment.a), Vec3::from(c.segment.b));
+                let axis = b - a;
+                if let Some(dir) = axis.try_normalize() {
+                    t.translation += t.rotation * ((a + b) * 0.5);
+                    t.rotation *= Quat::from_rotation_arc(Vec3::Y, dir);
+                }
+                (FW_COLLIDER_CAPSULE, [c.radius, axis.length() * 0.5, 0.0])
+            }
             _ => {
                 bevy::log::warn_once!("firework_b200: collider shape not supported by the GPU collision sweep, ignored");
                 continue;

@@ -13,7 +13,7 @@ from bevy_firework_b200 import (EmissionMode, EmissionPacing, EmissionSettings, 
                                 FireworkGradient, LinearRgba, ParticleCollisionSettings, ParticleSettings,
                                 ParticleSpawner, RandF32, RandVec3, SpawnTransformMode)
 from bevy_firework_b200._native import frame_input
-from bevy_firework_b200.workloads import cone, cuboid, cylinder, sphere
+from bevy_firework_b200.workloads import capsule, cone, cuboid, cylinder, sphere
 from _parity import assert_rows_match, reset_both
 
 pytestmark = pytest.mark.gpu
@@ -113,8 +113,10 @@ def test_randomized_nested_scene(engine, oracle, seed):
     for i in range(30):
         p = (float(rng.uniform(-4, 4)), float(rng.uniform(0.3, 3.0)), float(rng.uniform(-4, 4)))
         layers = int(rng.choice([1, 2, 3]))
-        k = rng.integers(0, 4)
-        if k == 0:
+        k = rng.integers(0, 5)
+        if k == 4:
+            c = capsule(float(rng.uniform(0.2, 0.6)), float(rng.uniform(0.3, 1.5)), p, _quat(rng), layers=layers)
+        elif k == 0:
             c = cuboid(tuple(rng.uniform(0.3, 1.5, 3)), p, _quat(rng), layers=layers, key=101 + i)
         elif k == 1:
             c = sphere(float(rng.uniform(0.2, 0.8)), p, layers=layers, key=101 + i)

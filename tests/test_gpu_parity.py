@@ -498,10 +498,11 @@ def test_collision_moving_colliders_every_frame(engine, oracle):
     assert_rows_match(got, want, what="moving colliders")
 
 
-def test_collision_cylinder_and_cone(engine, oracle):
+@pytest.mark.parametrize("kinds", ["cylinder_cone", "with_capsules"])
+def test_collision_cylinder_and_cone(engine, oracle, kinds):
     """the colliders of examples/textures.rs:195,211 (circular base, cone) plus rotated and random
-    ones: bit-exact against the oracle on identical state, both broad-phase paths"""
-    from bevy_firework_b200.workloads import cone, cylinder
+    ones (and capsules): bit-exact against the oracle on identical state, both broad-phase paths"""
+    from bevy_firework_b200.workloads import capsule, cone, cylinder
 
     rng = np.random.default_rng(77)
     cols = [cylinder(4.0, 0.2, (0.0, 0.0, 0.0)), cone(0.5, 1.0, (0.0, 0.5, 0.0))]
@@ -510,6 +511,8 @@ def test_collision_cylinder_and_cone(engine, oracle):
         q /= np.linalg.norm(q)
         pos = (float(rng.uniform(-3.5, 3.5)), float(rng.uniform(0.3, 3.0)), float(rng.uniform(-3.5, 3.5)))
         mk = cylinder if i % 2 else cone
+        if kinds == "with_capsules" and i % 3 == 0:
+            mk = capsule
         cols.append(mk(float(rng.uniform(0.1, 0.6)), float(rng.uniform(0.2, 1.2)), pos, tuple(q)))
     sp = _idle_spawner(lifetime=RandF32.constant(100.0), linear_drag=0.15,
                        collision_settings=ParticleCollisionSettings(0.6, 0.2, False))

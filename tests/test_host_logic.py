@@ -15,7 +15,7 @@ import pytest
 
 from bevy_firework_b200 import _abi
 from bevy_firework_b200.build import build_native
-from bevy_firework_b200.workloads import collision_scene_colliders, cone, cuboid, cylinder, sphere
+from bevy_firework_b200.workloads import capsule, collision_scene_colliders, cone, cuboid, cylinder, sphere
 
 f32 = np.float32
 
@@ -153,8 +153,10 @@ def _scene(rng, n, with_big=True, with_nan=False):
         layers = 1 if len(cols) % 3 else 2
         q = rng.normal(size=4)
         q /= np.linalg.norm(q)
-        kind = len(cols) % 4
-        if kind == 1:
+        kind = len(cols) % 5
+        if kind == 4:
+            cols.append(capsule(float(rng.uniform(0.1, 0.6)), float(rng.uniform(0.2, 1.5)), pos, tuple(q), layers=layers))
+        elif kind == 1:
             cols.append(cuboid(rng.uniform(0.1, 1.6, 3), pos, tuple(q), layers=layers))
         elif kind == 2:
             cols.append(cylinder(float(rng.uniform(0.1, 0.8)), float(rng.uniform(0.2, 1.5)), pos, tuple(q), layers=layers))
@@ -180,6 +182,8 @@ def test_broadphase_boxes_contain_the_colliders(lib):
         he = np.array(c.half_extents[:], dtype=np.float64)
         if c.kind in (_abi.FW_COLLIDER_CYLINDER, _abi.FW_COLLIDER_CONE):
             he = np.array([he[0], he[1], he[0]])  # solid of revolution about +Y: (r, h, r)
+        if c.kind == _abi.FW_COLLIDER_CAPSULE:
+            he = np.array([he[0], he[1] + he[0], he[0]])  # segment half length + the ball
         ext = np.full(3, abs(he[0])) if c.kind == _abi.FW_COLLIDER_SPHERE else np.abs(R) @ np.abs(he)
         assert (bp.leaf[i, 0, :3] < t - ext).all() and (bp.leaf[i, 1, :3] > t + ext).all()
         assert int(bp.leaf_u[i, 0, 3]) == c.layers

@@ -273,16 +273,81 @@ def test_cylinder_and_cone_ray_casts_known_answers(oracle):
     assert oracle.cast_ray(pyramid, (5.0, 1.5, 0.0), (-1.0, 0.0, 0.0), 10.0) is None
 
 
+def test_capsule_ray_casts(oracle):
+    """the analytic capsule (segment swept by a ball; parry casts it with GJK): closed-form hits, and random
+    rays against a float64 sphere-tracing of the distance to the segment"""
+    from bevy_firework_b200.workloads import capsule
+
+    cap = [capsule(0.5, 2.0, (0.0, 0.0, 0.0))]                                          # segment y in [-1, 1], radius 0.5
+    hit = oracle.cast_ray(cap, (5.0, 0.3, 0.0), (-1.0, 0.0, 0.0), 10.0)                 # side
+    assert hit is not None and abs(hit[0] - 4.5) < 1e-6 and hit[1] == (1.0, 0.0, 0.0)
+    hit = oracle.cast_ray(cap, (0.0, 5.0, 0.0), (0.0, -1.0, 0.0), 10.0)                 # top of the upper ball
+    assert hit is not None and abs(hit[0] - 3.5) < 1e-6 and hit[1] == (0.0, 1.0, 0.0)
+    hit = oracle.cast_ray(cap, (0.0, -5.0, 0.0), (0.0, 1.0, 0.0), 10.0)                 # bottom of the lower ball
+    assert hit is not None and abs(hit[0] - 3.5) < 1e-6 and hit[1] == (0.0, -1.0, 0.0)
+    hit = oracle.cast_ray(cap, (5.0, 1.3, 0.0), (-1.0, 0.0, 0.0), 10.0)                 # upper ball, 0.3 above its centre
+    assert hit is not None and abs(hit[0] - (5.0 - 0.4)) < 1e-6
+    assert np.allclose(hit[1], (0.8, 0.6, 0.0), atol=1e-6)
+    assert oracle.cast_ray(cap, (5.0, 1.6, 0.0), (-1.0, 0.0, 0.0), 10.0) is None        # over the top
+    assert oracle.cast_ray(cap, (5.0, 0.3, 0.0), (-1.0, 0.0, 0.0), 4.4) is None         # max_distance
+    assert oracle.cast_ray(cap, (5.0, 0.3, 0.0), (1.0, 0.0, 0.0), 100.0) is None        # pointing away
+    hit = oracle.cast_ray(cap, (0.2, 1.2, 0.1), (0.0, 1.0, 0.0), 1.0)                   # inside the upper ball, solid
+    assert hit is not None and hit[0] == 0.0 and hit[1] == (0.0, 0.0, 0.0)
+    hit = oracle.cast_ray(cap, (0.2, 3.0, 0.0), (0.0, -1.0, 0.0), 10.0)                 # inside the cylinder's shadow, from above
+    assert hit is not None and abs(hit[0] - (3.0 - 1.0 - math.sqrt(0.25 - 0.04))) < 1e-6
+
+    def sdf(p, r, h):  # distance to the capsule surface, float64
+        q = p.copy()
+        q[1] -= np.clip(q[1], -h, h)
+        return np.linalg.norm(q) - r
+
+    rng = np.random.default_rng(11)
+    r, h = 0.4, 0.75
+    cap = [capsule(r, 2.0 * h, (0.0, 0.0, 0.0))]
+    hits = 0
+    for _ in range(1500):
+        o = rng.uniform(-2.5, 2.5, 3)
+        d = rng.uniform(-0.6, 0.6, 3) - o
+        d /= np.linalg.norm(d)
+        got = oracle.cast_ray(cap, tuple(float(np.float32(c)) for c in o), tuple(float(np.float32(c)) for c in d), 20.0)
+        o64 = np.array([np.float32(c) for c in o], dtype=np.float64)
+        d64 = np.array([np.float32(c) for c in d], dtype=np.float64)
+        if sdf(o64, r, h) <= 0.0:
+            assert got is not None and got[0] == 0.0
+            continue
+        t, want = 0.0, None
+        for _ in range(400):  # sphere tracing: never oversteps a convex solid
+            s = sdf(o64 + d64 * t, r, h)
+            if s < 1e-9:
+                want = t
+                break
+            t += s
+            if t > 20.0:
+                break
+        if want is None:
+            if got is not None:  # a grazing ray may be decided either way within rounding
+                assert sdf(o64 + d64 * got[0], r, h) < 1e-4
+            continue
+        assert got is not None and abs(got[0] - want) < 2e-5 * max(1.0, want), (o, d, got, want)
+        p = o64 + d64 * want
+        n = p.copy()
+        n[1] -= np.clip(n[1], -h, h)
+        assert np.allclose(got[1], n / np.linalg.norm(n), atol=2e-4)
+        hits += 1
+    assert hits > 300
+
+
 def test_culled_ray_cast_equals_brute_force(oracle):
     """the oracle's test helper (conservative boxes, used by the full-size collision scenes) returns
     exactly what the brute-force loop over every collider returns: hit or not, distance, normal, index"""
     import ctypes as C
 
     from bevy_firework_b200 import _abi
-    from bevy_firework_b200.workloads import collision_scene_colliders, cone, cylinder, sphere
+    from bevy_firework_b200.workloads import capsule, collision_scene_colliders, cone, cylinder, sphere
 
     cols = list(collision_scene_colliders(64)) + [sphere(0.5, (1.0, 1.0, 1.0)), cylinder(0.6, 1.0, (-2.0, 1.0, 0.5)),
-                                                  cone(0.5, 1.2, (0.5, 0.6, -2.0))]
+                                                  cone(0.5, 1.2, (0.5, 0.6, -2.0)),
+                                                  capsule(0.3, 1.4, (2.5, 1.2, -1.0), (0.0, 0.0, 0.38268343, 0.92387953))]
     arr = (_abi.fw_collider * len(cols))(*cols)
     rng = np.random.default_rng(5)
     hits = 0

@@ -162,7 +162,7 @@ def test_curves(vectors, oracle):
 
 def test_cast_ray(vectors, oracle):
     kinds = {"cuboid": _abi.FW_COLLIDER_CUBOID, "sphere": _abi.FW_COLLIDER_SPHERE, "cylinder": _abi.FW_COLLIDER_CYLINDER,
-             "cone": _abi.FW_COLLIDER_CONE}
+             "cone": _abi.FW_COLLIDER_CONE, "capsule": _abi.FW_COLLIDER_CAPSULE}
     miss = far = 0
     for r in vectors["cast_ray"]:
         i = r["in"]
