@@ -1599,16 +1599,21 @@ __global__ void __launch_bounds__(256) sincos_kernel(const float *x, uint64_t n,
 }
 __global__ void __launch_bounds__(256) ring_copy_kernel(StreamDesc src, uint32_t first, uint32_t n, StreamDesc dst) {
     const StreamArrays a = stream_arrays(src.base, src.capacity), b = stream_arrays(dst.base, dst.capacity);
+    // only the packs this stream keeps (store_particle): the others were never written
+    const bool rot = variant_rotates(src.variant);
+    const uint32_t flags = src.flags;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t s = wrap(first + i, src.capacity);
         b.m0[i] = a.m0[s];
-        b.m1[i] = a.m1[s];
         b.m2[i] = a.m2[s];
-        b.m3[i] = a.m3[s];
-        b.k[i] = a.k[s];
-        b.o0[i] = a.o0[s];
-        b.o1[i] = a.o1[s];
-        b.o2[i] = a.o2[s];
+        if (rot) {
+            b.m1[i] = a.m1[s];
+            b.m3[i] = a.m3[s];
+        }
+        if (rot || (flags & kStoreLife)) b.k[i] = a.k[s];
+        if (flags & kStoreBase) b.o0[i] = a.o0[s];
+        if (flags & kStoreEmi) b.o1[i] = a.o1[s];
+        if (flags & kStoreScale) b.o2[i] = a.o2[s];
         for (uint32_t j = 0; j < src.n_lea; j++) lea_array(dst.base, dst.capacity, j)[i] = lea_array(src.base, src.capacity, j)[s];
     }
 }
