@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 
 FW_ABI_VERSION = 2
-FW_MAX_KNOTS = 16
+FW_MAX_KNOTS = 32
 FW_MAX_EXCLUDED = 8
 FW_NO_KEY = 0xFFFFFFFF
 

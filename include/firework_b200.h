@@ -40,7 +40,7 @@ extern "C" {
 
 /* Maximum number of knots in one curve / gradient (the reference accepts any number of
  * samples, src/curve.rs:40-75; every shipped example uses <= 5). */
-#define FW_MAX_KNOTS 16u
+#define FW_MAX_KNOTS 32u
 
 enum fw_status {
     FW_OK = 0,

@@ -14,7 +14,7 @@
 use std::os::raw::{c_char, c_int, c_void};
 
 pub const FW_ABI_VERSION: u32 = 2;
-pub const FW_MAX_KNOTS: usize = 16;
+pub const FW_MAX_KNOTS: usize = 32;
 pub const FW_MAX_EXCLUDED: usize = 8;
 pub const FW_NO_KEY: u32 = 0xFFFF_FFFF;
 pub const FW_FLAG_PROFILE: u32 = 1;

@@ -360,6 +360,46 @@ def test_error_behaviour(engine):
         engine.spawner_reset(1, *sp.pods()[:1], nt, es, ne, True)
 
 
+def test_curves_at_the_knot_cap(engine, oracle):
+    """FW_MAX_KNOTS samples per curve / gradient (even and uneven), one more is refused"""
+    from bevy_firework_b200 import FireworkCurve, FireworkGradient, LinearRgba
+    from bevy_firework_b200._native import FireworkError
+
+    n = _abi.FW_MAX_KNOTS
+    assert n >= 32
+    rng = np.random.default_rng(9)
+
+    def col():
+        return LinearRgba(*[float(v) for v in rng.uniform(0.0, 3.0, 4)])
+
+    ts = np.sort(rng.uniform(0.01, 0.99, n - 2))
+    w = oracle.OracleWorld()
+    for key, lifetime in ((1, RandF32.constant(0.6)), (2, RandF32(0.3, 0.9))):  # static kernel / compacting
+        sp = stress_spawner(rate=6000.0)
+        p = sp.particle_settings[0]
+        p.lifetime = lifetime
+        p.scale_curve = FireworkCurve.even_samples([float(v) for v in rng.uniform(0.2, 2.0, n)])
+        p.base_color = FireworkGradient.uneven_samples([(0.0, col())] + [(float(t), col()) for t in ts] + [(1.0, col())])
+        p.emissive_color = FireworkGradient.even_samples([col() for _ in range(n - 7)])
+        if key == 2:
+            p.scale_curve = FireworkCurve.uneven_samples([(0.0, 1.0)] + [(float(t), float(rng.uniform(0.1, 2.0))) for t in ts] + [(1.0, 0.0)])
+            p.angular_acceleration = (0.0, 1.0, 0.0)  # the rotating (generic) kernel
+        reset_both(engine, w, key, sp)
+    inp = [frame_input(1, (0.0, 0.1, 0.0)), frame_input(2, (1.0, 0.1, 0.0))]
+    for k in range(70):
+        engine.frame(DT, inp)
+        w.frame(DT, inp)
+    for key in (1, 2):
+        assert engine.counts(key) == w.counts(key)
+        assert_rows_match(engine.read_particles(key, 0), w.read_particles(key, 0), what=f"spawner {key}")
+    ps, nt, es, ne = stress_spawner().pods()
+    ps[0].scale_curve.kind = _abi.FW_CURVE_EVEN
+    ps[0].scale_curve.n = n + 1
+    with pytest.raises(FireworkError) as e:
+        engine.spawner_reset(3, ps, nt, es, ne, True)
+    assert e.value.code == _abi.FW_ERR_INVALID_ARGUMENT
+
+
 def test_pack_instances_device(engine):
     import torch
 
