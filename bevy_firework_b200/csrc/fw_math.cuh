@@ -327,9 +327,16 @@ __device__ __noinline__ bool ray_frustum_local(float r0, float r1, float h, V3 o
     if (A != 0.0f) {
         const float disc = B * B - A * C;
         if (disc >= 0.0f) {
-            const float q = sqrtf(disc);
-            roots[0] = (-B - q) / A;
-            roots[1] = (-B + q) / A;
+            // the cancellation-free form (see the oracle): q = -(B + sign(B) sqrt(disc)), roots q / A and C / q
+            const float sq = sqrtf(disc);
+            const float q = B < 0.0f ? sq - B : -(B + sq);
+            if (q != 0.0f) {
+                roots[0] = B < 0.0f ? C / q : q / A;
+                roots[1] = B < 0.0f ? q / A : C / q;
+            } else {
+                roots[0] = 0.0f;
+                roots[1] = 0.0f;
+            }
             n_roots = 2;
         }
     } else if (B != 0.0f) {

@@ -428,9 +428,18 @@ static int ray_frustum_local(float r0, float r1, float h, v3 o, v3 d, float max_
     if (A != 0.0f) {
         const float disc = B * B - A * C;
         if (disc >= 0.0f) {
-            const float q = sqrtf(disc);
-            roots[0] = (-B - q) / A;
-            roots[1] = (-B + q) / A;
+            /* q = -(B + sign(B) sqrt(disc)); roots q / A and C / q. The textbook (-B -+ sqrt) / A cancels
+             * to 0 / A when A C is tiny against B B -- a ray almost along a cone's slant -- and reported
+             * a hit at distance (-)0 for a cone the ray never comes near. Same order: [0] = the "-" root. */
+            const float sq = sqrtf(disc);
+            const float q = B < 0.0f ? sq - B : -(B + sq);
+            if (q != 0.0f) {
+                roots[0] = B < 0.0f ? C / q : q / A;
+                roots[1] = B < 0.0f ? q / A : C / q;
+            } else { /* B = 0 and disc = 0: the double root 0 */
+                roots[0] = 0.0f;
+                roots[1] = 0.0f;
+            }
             n_roots = 2;
         }
     } else if (B != 0.0f) {

@@ -337,6 +337,63 @@ def test_capsule_ray_casts(oracle):
     assert hits > 300
 
 
+def test_exact_ray_tests_never_hit_away_from_the_solid(oracle):
+    """the broad phase of the kernels may skip a collider whose box the ray segment misses only if the exact
+    test cannot report a hit there. Found by the random campaign (seeds 66, 69): a ray almost along a cone's
+    slant made the textbook quadratic cancel to 0 / A and reported a hit at distance -0 for a cone metres
+    away. Every hit of every kind must lie on the collider's bounding ball; rays along the slant included."""
+    from bevy_firework_b200.workloads import capsule, cone, cuboid, cylinder, sphere
+
+    # the ray of seed 66, frame 80
+    c = cone(0.2573815882205963, 2 * 0.5490826368331909, (1.855310320854187, 0.6611395478248596, -2.5667452812194824),
+             (-0.6398850679397583, 0.5684993267059326, 0.5101174712181091, 0.08447343856096268))
+    assert oracle.cast_ray([c], (1.1446307, 5.8628054, -0.7957), (0.88509476, 0.12219622, -0.4490828), 0.16555828) is None
+
+    rng = np.random.default_rng(3)
+    checked = 0
+    for i in range(3000):
+        kind = i % 5
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        tr = rng.uniform(-2, 2, 3)
+        r, hh = float(rng.uniform(0.1, 0.8)), float(rng.uniform(0.2, 1.5))
+        if kind == 0:
+            he = rng.uniform(0.1, 1.0, 3)
+            col, bound = cuboid(tuple(2 * he), tr, tuple(q)), float(np.linalg.norm(he))
+        elif kind == 1:
+            col, bound = sphere(r, tr), r
+        elif kind == 2:
+            col, bound = cylinder(r, hh, tr, tuple(q)), math.hypot(r, hh / 2)
+        elif kind == 3:
+            col, bound = cone(r, hh, tr, tuple(q)), math.hypot(r, hh / 2)
+        else:
+            col, bound = capsule(r, hh, tr, tuple(q)), r + hh / 2
+        x, y, z, w = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        for j in range(6):
+            o = tr + rng.uniform(-6, 6, 3)
+            if j < 3 and kind in (2, 3):  # along the slant (cone) / the axis (cylinder), up to rounding
+                slope = (r / hh) if kind == 3 else 0.0
+                phi = rng.uniform(0, 2 * np.pi)
+                dl = np.array([slope * np.cos(phi), -1.0, slope * np.sin(phi)]) * rng.choice([-1.0, 1.0])
+                d = R @ dl
+            else:
+                d = rng.normal(size=3)
+            d = d / np.linalg.norm(d)
+            md = float(rng.choice([0.2, 3.0, 50.0]))
+            hit = oracle.cast_ray([col], tuple(float(np.float32(v)) for v in o), tuple(float(np.float32(v)) for v in d), md)
+            checked += 1
+            if hit is None:
+                continue
+            assert 0.0 <= hit[0] <= md * (1 + 1e-6)
+            p = o + d * hit[0]
+            assert np.linalg.norm(p - tr) <= bound * (1 + 1e-3) + 1e-3 or hit[0] == 0.0 and np.linalg.norm(o - tr) <= bound * (1 + 1e-3) + 1e-3, \
+                (kind, o, d, md, hit)
+    assert checked == 18000
+
+
 def test_culled_ray_cast_equals_brute_force(oracle):
     """the oracle's test helper (conservative boxes, used by the full-size collision scenes) returns
     exactly what the brute-force loop over every collider returns: hit or not, distance, normal, index"""
