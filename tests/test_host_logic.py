@@ -229,3 +229,47 @@ def test_bvh_walk_is_short_for_short_segments(lib):
         e = (o + rng.uniform(-0.08, 0.08, 3).astype(f32)).astype(f32)
         steps.append(bp.walk_bvh(np.minimum(o, e), np.maximum(o, e))[1])
     assert np.mean(steps) < 80 and bp.n_nodes == 511
+
+
+def test_broadphase_never_drops_the_hit_the_exact_test_reports(lib):
+    """what the kernels rely on (fw_math.cuh, cast_ray): whatever collider the brute-force loop over every
+    collider reports as the closest hit is among the candidates of the grid walk, or of the BVH walk when the
+    segment is long. Rays of a particle step, long rays, rays along cone slants and capsule / cylinder axes.
+    (The random campaign found the one case where this failed: a false hit of the analytic cone at distance 0.)"""
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(21)
+    cols = _scene(rng, 120)
+    arr = (_abi.fw_collider * len(cols))(*cols)
+    bp = BroadPhase(lib, cols)
+    n = int(__import__("os").environ.get("FW_BROADPHASE_RAYS", "4000"))
+    hits = 0
+    for i in range(n):
+        c = cols[int(rng.integers(1, len(cols)))]
+        tr = np.array(c.translation[:], dtype=np.float64)
+        o = (tr + rng.uniform(-3, 3, 3)) if i % 3 else rng.uniform(-9, 9, 3) * (1.0, 0.4, 1.0) + (0.0, 1.0, 0.0)
+        if i % 4 == 0 and c.kind in (_abi.FW_COLLIDER_CYLINDER, _abi.FW_COLLIDER_CONE, _abi.FW_COLLIDER_CAPSULE):
+            x, y, z, w = [float(v) for v in c.rotation[:]]
+            R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                          [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+            slope = float(c.half_extents[0]) / (2.0 * float(c.half_extents[1])) if c.kind == _abi.FW_COLLIDER_CONE else 0.0
+            phi = rng.uniform(0, 2 * np.pi)
+            d = R @ (np.array([slope * np.cos(phi), -1.0, slope * np.sin(phi)]) * rng.choice([-1.0, 1.0]))
+        else:
+            d = rng.normal(size=3)
+        d = (d / np.linalg.norm(d)).astype(f32)
+        o = o.astype(f32)
+        md = f32(rng.choice([0.03, 0.15, 0.6, 25.0]))
+        mask = int(rng.choice([0xFFFFFFFF, 1, 2]))
+        hit = O.cast_ray(arr, tuple(float(v) for v in o), tuple(float(v) for v in d), float(md), filter_mask=mask)
+        if hit is None:
+            continue
+        hits += 1
+        e = (o + d * md).astype(f32)
+        slo, shi = np.minimum(o, e), np.maximum(o, e)
+        cand = bp.enumerate_grid(slo, shi, mask)
+        if cand is None:
+            cand = bp.walk_bvh(slo, shi, mask)[0]
+        assert hit[2] in cand, (i, cols[hit[2]].kind, o, d, md, hit, cand)
+    assert hits > n // 20
