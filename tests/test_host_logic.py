@@ -273,3 +273,25 @@ def test_broadphase_never_drops_the_hit_the_exact_test_reports(lib):
             cand = bp.walk_bvh(slo, shi, mask)[0]
         assert hit[2] in cand, (i, cols[hit[2]].kind, o, d, md, hit, cand)
     assert hits > n // 20
+
+
+def test_fuzz_cast_ray_harness(lib, tmp_path):
+    """scripts/probes/fuzz_cast_ray.c (the 1e9-ray campaign of profiles/r2/x_fuzz_cast_ray_1e9_rays.txt) on a
+    few million rays: compiled from the oracle's source, boxes from the library's own broad-phase builder"""
+    import os
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "fuzz_cast_ray")
+    subprocess.check_call([gcc, "-O2", "-std=gnu11", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-w",
+                           "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "oracle"),
+                           os.path.join(root, "scripts", "probes", "fuzz_cast_ray.c"), "-o", exe, "-lm", "-ldl"])
+    from bevy_firework_b200._native import LIB_PATH
+
+    out = subprocess.run([exe, LIB_PATH, "8", "400000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "broad-phase box: 0 |" in out.stdout and "culled helper: 0 |" in out.stdout
