@@ -295,3 +295,33 @@ def test_fuzz_cast_ray_harness(lib, tmp_path):
     out = subprocess.run([exe, LIB_PATH, "8", "400000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "broad-phase box: 0 |" in out.stdout and "culled helper: 0 |" in out.stdout
+
+
+def test_kernel_cast_ray_source_on_the_host_equals_the_oracle(lib, tmp_path):
+    """scripts/probes/host_cast_ray.cu compiles the KERNELS' cast_ray (fw_math.cuh: grid / BVH enumeration,
+    candidate queue, exact tests, masks, exclusions, tie-break) for the host as a one-lane warp and compares
+    it with the oracle's brute-force loop bit for bit (6.6e8 rays once: profiles/r2/x_host_cast_ray_6e8_rays.txt;
+    here ~1.6 M). No GPU involved: it checks the source the GPU runs, not the GPU."""
+    import os
+    import shutil
+    import subprocess
+
+    from bevy_firework_b200._native import LIB_PATH
+    from bevy_firework_b200.build import nvcc_path
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        nvcc = nvcc_path()
+    except RuntimeError:
+        pytest.skip("no nvcc")
+    from oracle import oracle as O
+
+    O.lib()  # builds oracle/libfw_oracle.so if needed
+    exe = str(tmp_path / "host_cast_ray")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-w", "-Xcompiler", "-ffp-contract=off,-fno-fast-math,-fopenmp",
+                           "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "bevy_firework_b200", "csrc"),
+                           os.path.join(root, "scripts", "probes", "host_cast_ray.cu"), "-o", exe, "-ldl", "-lgomp"])
+    out = subprocess.run([exe, LIB_PATH, os.path.join(root, "oracle", "libfw_oracle.so"), "16", "100000"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "!= oracle brute force: 0" in out.stdout
