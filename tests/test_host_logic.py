@@ -325,3 +325,13 @@ def test_kernel_cast_ray_source_on_the_host_equals_the_oracle(lib, tmp_path):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "!= oracle brute force: 0" in out.stdout
+    # the rest of the header the same way: particle_collision, curves, gradients, Philox, quaternions
+    # (5.1e8 collisions once: profiles/r2/x_host_math_5e8_collisions.txt)
+    exe2 = str(tmp_path / "host_math")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-w", "-Xcompiler", "-ffp-contract=off,-fno-fast-math,-fopenmp",
+                           "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "bevy_firework_b200", "csrc"),
+                           os.path.join(root, "scripts", "probes", "host_math.cu"), "-o", exe2, "-ldl", "-lgomp"])
+    out = subprocess.run([exe2, LIB_PATH, os.path.join(root, "oracle", "libfw_oracle.so"), "16", "50000"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("mismatches 0") == 4
