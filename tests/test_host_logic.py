@@ -335,3 +335,48 @@ def test_kernel_cast_ray_source_on_the_host_equals_the_oracle(lib, tmp_path):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("mismatches 0") == 4
+
+
+def test_warp_searches_restated():
+    """the two 32-ary warp searches of the kernels (fw_kernels.cu: find_cmd_warp, find_tile_warp), restated lane
+    by lane: every size from 1 to 130, around the powers of 32, past 32^3; streams without tiles share a prefix
+    value with their successor and the LAST of them owns the tile"""
+    def find_cmd_warp(first, begin, end, g):
+        lo, n = begin, end - begin
+        while n > 1:
+            step = (n + 31) >> 5
+            ok = [lane == 0 or (lo + lane * step < lo + n and first[lo + lane * step] <= g) for lane in range(32)]
+            assert all(ok[i] or not ok[i + 1] for i in range(31))  # monotone: the ballot is a prefix of the lanes
+            k = max(i for i in range(32) if ok[i])
+            hi = lo + n
+            lo += k * step
+            n = min(step, hi - lo)
+        return lo
+
+    def find_tile_warp(prefix, n_slots, tile):
+        lo, n = 0, n_slots
+        while n > 1:
+            step = (n + 31) // 32
+            le = [lane * step < n and prefix[lo + lane * step] <= tile for lane in range(32)]
+            k = max([i for i in range(32) if le[i]], default=0)
+            lo += k * step
+            n = min(step, n - k * step)
+        return lo
+
+    rng = np.random.default_rng(0)
+    for n in list(range(1, 131)) + [255, 256, 257, 1023, 1024, 1025, 2048, 4097, 32768, 32769, 40000]:
+        counts = rng.integers(1, 5, n)                      # every command has count > 0
+        first = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        begin = int(rng.integers(0, 3))
+        arr = np.concatenate([np.zeros(begin, dtype=np.int64), first])
+        total = int(counts.sum())
+        for g in (range(total) if total < 1500 else rng.integers(0, total, 1500)):
+            assert find_cmd_warp(arr, begin, begin + n, int(g)) == begin + int(np.searchsorted(first, g, side="right") - 1)
+        tiles = rng.integers(0, 4, n) * (rng.random(n) < 0.5)  # half the streams have no tile
+        if tiles.sum() == 0:
+            tiles[int(rng.integers(0, n))] = 2
+        prefix = np.concatenate([[0], np.cumsum(tiles)]).astype(np.int64)
+        total = int(prefix[-1])
+        for t in (range(total) if total < 1500 else rng.integers(0, total, 1500)):
+            s = find_tile_warp(prefix, n, int(t))
+            assert prefix[s] <= t < prefix[s + 1]
