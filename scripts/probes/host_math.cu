@@ -23,6 +23,13 @@ static inline __host__ uint32_t emul_f2u(float f) { uint32_t u; memcpy(&u, &f, 4
 #define __syncwarp() ((void)0)
 #define __umulhi(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
 #include "fw_math.cuh"
+#ifdef FW_HAVE_SGH
+// the static update kernel's gradient sampler with a carried knot interval: its text, cut out of fw_kernels.cu by the
+// caller (from its signature to the next template) into sgh.inc
+namespace fw {
+#include "sgh.inc"
+}
+#endif
 
 typedef int (*build_fn)(const fw_collider *, uint32_t, void *, uint64_t, uint64_t *);
 typedef void (*pc_fn)(const fw_collider *, uint32_t, const fw_collision_settings *, float *, float *, float, uint32_t *);
@@ -161,6 +168,28 @@ int main(int argc, char **argv) {
                 n_grad++;
                 if (!same(ga, gb4, 4)) { bad_grad++; if (bad_grad < 4) fprintf(stderr, "GRADIENT kind %u n %u t %.9g\n", g.kind, n, t); }
             }
+#ifdef FW_HAVE_SGH
+            {   // a run of ages as a warp lane sees them along a ring (slowly varying, with jumps, knots, tails, NaN),
+                // the knot interval carried from call to call
+                uint32_t hint = 0;
+                float t = uni(&s, 0, 1);
+                for (int q = 0; q < 48; q++) {
+                    const int m = (int)(rnd(&s) % 10);
+                    if (m == 0) t = g.times[rnd(&s) % n];
+                    else if (m == 1) t = uni(&s, -0.5f, 1.5f);
+                    else if (m == 2) t = NAN;
+                    else if (m == 3) t = uni(&s, 0, 1);
+                    else t = t + uni(&s, -0.02f, 0.03f);
+                    float ga[4];
+                    o_grad(&g, t, ga);
+                    const float4 gb = fw::sample_gradient_hint(dg, t, hint);
+                    const float gb4[4] = {gb.x, gb.y, gb.z, gb.w};
+                    n_grad++;
+                    if (!same(ga, gb4, 4)) { bad_grad++; if (bad_grad < 4) fprintf(stderr, "GRADIENT (hint) kind %u n %u t %.9g hint %u\n", g.kind, n, t, hint); }
+                    if (t != t) t = uni(&s, 0, 1);
+                }
+            }
+#endif
         }
         // ---- Philox, quaternions
         for (long r = 0; r < cases / 4 + 1; r++) {

@@ -328,8 +328,15 @@ def test_kernel_cast_ray_source_on_the_host_equals_the_oracle(lib, tmp_path):
     # the rest of the header the same way: particle_collision, curves, gradients, Philox, quaternions
     # (5.1e8 collisions once: profiles/r2/x_host_math_5e8_collisions.txt)
     exe2 = str(tmp_path / "host_math")
-    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-w", "-Xcompiler", "-ffp-contract=off,-fno-fast-math,-fopenmp",
+    # the static update kernel's own gradient sampler (knot interval carried from call to call) lives in
+    # fw_kernels.cu: cut its text out, from its signature to the next template
+    src = open(os.path.join(root, "bevy_firework_b200", "csrc", "fw_kernels.cu")).read()
+    i = src.index("__device__ __forceinline__ float4 sample_gradient_hint")
+    j = src.index("template <bool COMPACT>", i)
+    (tmp_path / "sgh.inc").write_text(src[i:j])
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-w", "-DFW_HAVE_SGH", "-Xcompiler", "-ffp-contract=off,-fno-fast-math,-fopenmp",
                            "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "bevy_firework_b200", "csrc"),
+                           "-I" + str(tmp_path),
                            os.path.join(root, "scripts", "probes", "host_math.cu"), "-o", exe2, "-ldl", "-lgomp"])
     out = subprocess.run([exe2, LIB_PATH, os.path.join(root, "oracle", "libfw_oracle.so"), "16", "50000"],
                          capture_output=True, text=True, timeout=600)
