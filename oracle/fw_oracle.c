@@ -128,6 +128,37 @@ void fwo_quat_mul(const float a[4], const float b[4], float out[4]) {
     out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
 }
 
+/* the glam / bevy_utilitarian restatements one by one, for tests/test_reference_vectors.py (known answers of the
+ * crates themselves, rust/gen_golden.rs) and the host-compiled kernel harness (scripts/probes/host_math.cu) */
+void fwo_quat_from_rotation_arc(const float from[3], const float to[3], float out[4]) {
+    q4 q = q_from_rotation_arc(v3_make(from[0], from[1], from[2]), v3_make(to[0], to[1], to[2]));
+    out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+}
+void fwo_quat_mul_vec3(const float q[4], const float v[3], float out[3]) {
+    q4 qq = {q[0], q[1], q[2], q[3]};
+    v3 r = q_mul_v3(qq, v3_make(v[0], v[1], v[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+void fwo_vec3_normalize_or_zero(const float v[3], float out[3]) {
+    v3 r = v3_normalize_or_zero(v3_make(v[0], v[1], v[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+void fwo_vec3_project_onto(const float a[3], const float b[3], float out[3]) {
+    v3 r = v3_project_onto(v3_make(a[0], a[1], a[2]), v3_make(b[0], b[1], b[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+void fwo_vec3_reject_from(const float a[3], const float b[3], float out[3]) {
+    v3 r = v3_reject_from(v3_make(a[0], a[1], a[2]), v3_make(b[0], b[1], b[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+/* PitchYaw(u, v).to_unit_vec() as fwo_generate_point uses it: (sin v cos u, cos v, sin v sin u) */
+void fwo_pitch_yaw_to_unit_vec(float u, float v, float out[3]) {
+    float su, cu, sv, cv;
+    fw_sincosf(u, &su, &cu);
+    fw_sincosf(v, &sv, &cv);
+    out[0] = sv * cu; out[1] = cv; out[2] = sv * su;
+}
+
 /* ------------------------------------------------------------------ Rust f32 helpers */
 /* core::f32::rem_euclid */
 float fwo_rem_euclid(float a, float b) {

@@ -87,6 +87,12 @@ void fwo_particle_collision(const fw_collider *c, uint32_t n, const fw_collision
                             float pos[3], float vel[3], float delta, uint32_t *should_destroy);
 void fwo_quat_from_scaled_axis(const float v[3], float out[4]);
 void fwo_quat_mul(const float a[4], const float b[4], float out[4]);
+void fwo_quat_from_rotation_arc(const float from[3], const float to[3], float out[4]);
+void fwo_quat_mul_vec3(const float q[4], const float v[3], float out[3]);
+void fwo_vec3_normalize_or_zero(const float v[3], float out[3]);
+void fwo_vec3_project_onto(const float a[3], const float b[3], float out[3]);
+void fwo_vec3_reject_from(const float a[3], const float b[3], float out[3]);
+void fwo_pitch_yaw_to_unit_vec(float u, float v, float out[3]);
 float fwo_rem_euclid(float a, float b);
 float fwo_div_euclid(float a, float b);
 

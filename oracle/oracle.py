@@ -73,6 +73,12 @@ def lib():
                                           P(f32 * 3), P(f32 * 3), f32, P(u32)]),
         "fwo_quat_from_scaled_axis": (None, [P(f32 * 3), P(f32 * 4)]),
         "fwo_quat_mul": (None, [P(f32 * 4), P(f32 * 4), P(f32 * 4)]),
+        "fwo_quat_from_rotation_arc": (None, [P(f32 * 3), P(f32 * 3), P(f32 * 4)]),
+        "fwo_quat_mul_vec3": (None, [P(f32 * 4), P(f32 * 3), P(f32 * 3)]),
+        "fwo_vec3_normalize_or_zero": (None, [P(f32 * 3), P(f32 * 3)]),
+        "fwo_vec3_project_onto": (None, [P(f32 * 3), P(f32 * 3), P(f32 * 3)]),
+        "fwo_vec3_reject_from": (None, [P(f32 * 3), P(f32 * 3), P(f32 * 3)]),
+        "fwo_pitch_yaw_to_unit_vec": (None, [f32, f32, P(f32 * 3)]),
         "fwo_sincosf": (None, [f32, P(f32), P(f32)]),
         "fwo_sincosf_array": (None, [vp, u64, vp, vp]),
         "fwo_rem_euclid": (f32, [f32, f32]),

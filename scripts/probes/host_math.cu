@@ -1,7 +1,8 @@
 // One-off campaign (CPU): the rest of the kernels' math header (fw_math.cuh) compiled for the host as a one-lane
 // warp against the oracle's exports, bit for bit: particle_collision (up to 4 bounces: restitution, friction,
 // destroy, the distance-0 push-out), sample_curve / sample_gradient (constant / even / uneven up to FW_MAX_KNOTS
-// knots; t below 0, above 1, NaN, exactly on knots), Philox4x32-10, quaternion from_scaled_axis / mul.
+// knots; t below 0, above 1, NaN, exactly on knots), Philox4x32-10, the glam helpers (quaternion from_scaled_axis / mul / from_rotation_arc / rotate, normalize_or_zero,
+// project_onto, reject_from; parallel, antiparallel, tiny, zero and huge vectors).
 //   nvcc -O2 -std=c++17 -Xcompiler -ffp-contract=off,-fno-fast-math,-fopenmp -Iinclude -Ibevy_firework_b200/csrc -Ioracle \
 //        scripts/probes/host_math.cu -o scripts/probes/host_math -ldl -lgomp
 //   scripts/probes/host_math bevy_firework_b200/libfirework_b200.so oracle/libfw_oracle.so <scenes> <cases per scene>
@@ -38,6 +39,8 @@ typedef void (*grad_fn)(const fw_gradient *, float, float *);
 typedef void (*philox_fn)(const uint32_t *, const uint32_t *, uint32_t *);
 typedef void (*qsa_fn)(const float *, float *);
 typedef void (*qmul_fn)(const float *, const float *, float *);
+typedef void (*v3v3_fn)(const float *, const float *, float *);
+typedef void (*v3_fn)(const float *, float *);
 static inline uint64_t rnd(uint64_t *s) { uint64_t x = *s; x ^= x << 13; x ^= x >> 7; x ^= x << 17; return *s = x; }
 static inline float uni(uint64_t *s, float a, float b) { return a + (b - a) * (float)((rnd(s) >> 40) * (1.0 / 16777216.0)); }
 static inline bool same(const float *a, const float *b, int n) {
@@ -57,6 +60,9 @@ int main(int argc, char **argv) {
     philox_fn o_philox = (philox_fn)dlsym(ho, "fwo_philox4x32_10");
     qsa_fn o_qsa = (qsa_fn)dlsym(ho, "fwo_quat_from_scaled_axis");
     qmul_fn o_qmul = (qmul_fn)dlsym(ho, "fwo_quat_mul");
+    v3v3_fn o_arc = (v3v3_fn)dlsym(ho, "fwo_quat_from_rotation_arc"), o_qrot = (v3v3_fn)dlsym(ho, "fwo_quat_mul_vec3");
+    v3v3_fn o_proj = (v3v3_fn)dlsym(ho, "fwo_vec3_project_onto"), o_rej = (v3v3_fn)dlsym(ho, "fwo_vec3_reject_from");
+    v3_fn o_norm = (v3_fn)dlsym(ho, "fwo_vec3_normalize_or_zero");
     const int scenes = atoi(argv[3]);
     const long cases = atol(argv[4]);
     unsigned long long n_pc = 0, n_hit = 0, bad_pc = 0, n_curve = 0, bad_curve = 0, n_grad = 0, bad_grad = 0, n_misc = 0, bad_misc = 0;
@@ -214,6 +220,48 @@ int main(int argc, char **argv) {
             const float qm4[4] = {qm.x, qm.y, qm.z, qm.w};
             n_misc++;
             if (!same(qo, qm4, 4)) bad_misc++;
+            // from_rotation_arc: random, parallel, antiparallel (the any_orthonormal branch) and almost so
+            float fa[3] = {uni(&s, -1, 1), uni(&s, -1, 1), uni(&s, -1, 1)}, fb[3] = {uni(&s, -1, 1), uni(&s, -1, 1), uni(&s, -1, 1)};
+            float la = sqrtf(fa[0] * fa[0] + fa[1] * fa[1] + fa[2] * fa[2]), lb = sqrtf(fb[0] * fb[0] + fb[1] * fb[1] + fb[2] * fb[2]);
+            if (la > 1e-3f && lb > 1e-3f) {
+                for (int k = 0; k < 3; k++) { fa[k] /= la; fb[k] /= lb; }
+                const int m = (int)(rnd(&s) % 8);
+                if (m == 0) { fa[0] = 0; fa[1] = 1; fa[2] = 0; }                                       // from = Y, as the spawn code calls it
+                if (m == 1) for (int k = 0; k < 3; k++) fb[k] = fa[k];                                 // parallel
+                if (m == 2) for (int k = 0; k < 3; k++) fb[k] = -fa[k];                                // antiparallel
+                if (m == 3) for (int k = 0; k < 3; k++) fb[k] = -fa[k] + uni(&s, -3e-4f, 3e-4f);       // almost antiparallel
+                if (m == 4) for (int k = 0; k < 3; k++) fb[k] = fa[k] + uni(&s, -3e-4f, 3e-4f);        // almost parallel
+                float ao[4];
+                o_arc(fa, fb, ao);
+                const fw::Q4 ak = fw::q_from_rotation_arc(fw::v3(fa[0], fa[1], fa[2]), fw::v3(fb[0], fb[1], fb[2]));
+                const float ak4[4] = {ak.x, ak.y, ak.z, ak.w};
+                n_misc++;
+                if (!same(ao, ak4, 4)) { bad_misc++; if (bad_misc < 4) fprintf(stderr, "ARC %.9g %.9g %.9g -> %.9g %.9g %.9g\n", fa[0], fa[1], fa[2], fb[0], fb[1], fb[2]); }
+                float ro[3];
+                o_qrot(ao, v, ro);
+                const fw::V3 rk = fw::qrot(ak, fw::v3(v[0], v[1], v[2]));
+                const float rk3[3] = {rk.x, rk.y, rk.z};
+                n_misc++;
+                if (!same(ro, rk3, 3)) bad_misc++;
+            }
+            // normalize_or_zero / project_onto / reject_from, tiny and zero vectors included
+            float w[3] = {uni(&s, -3, 3), uni(&s, -3, 3), uni(&s, -3, 3)};
+            const int mw = (int)(rnd(&s) % 6);
+            if (mw == 0) { w[0] *= 1e-20f; w[1] *= 1e-20f; w[2] *= 1e-20f; }
+            if (mw == 1) { w[0] = w[1] = w[2] = 0; }
+            if (mw == 2) { w[0] *= 1e18f; w[1] *= 1e18f; w[2] *= 1e18f; }
+            float no[3], po[3], jo[3];
+            o_norm(w, no);
+            o_proj(v, w, po);
+            o_rej(v, w, jo);
+            const fw::V3 nk = fw::normalize_or_zero(fw::v3(w[0], w[1], w[2]));
+            const fw::V3 pjk = fw::project_onto(fw::v3(v[0], v[1], v[2]), fw::v3(w[0], w[1], w[2]));
+            const fw::V3 jk = fw::reject_from(fw::v3(v[0], v[1], v[2]), fw::v3(w[0], w[1], w[2]));
+            const float nk3[3] = {nk.x, nk.y, nk.z}, pk3[3] = {pjk.x, pjk.y, pjk.z}, jk3[3] = {jk.x, jk.y, jk.z};
+            n_misc += 3;
+            if (!same(no, nk3, 3)) { bad_misc++; if (bad_misc < 4) fprintf(stderr, "NORMALIZE %.9g %.9g %.9g\n", w[0], w[1], w[2]); }
+            if (!same(po, pk3, 3)) { bad_misc++; if (bad_misc < 4) fprintf(stderr, "PROJECT onto %.9g %.9g %.9g\n", w[0], w[1], w[2]); }
+            if (!same(jo, jk3, 3)) bad_misc++;
         }
     }
     printf("particle_collision %llu (changed or destroyed: %llu) mismatches %llu | sample_curve %llu mismatches %llu | sample_gradient %llu mismatches %llu | philox / quaternions %llu mismatches %llu\n",

@@ -193,3 +193,117 @@ def test_platform_sin_cos_against_fw_sincos(vectors, oracle):
     want = np.array([_f(r["out"]) for r in vectors["sin_cos"]])
     s, c = oracle.sincosf(x)
     assert _ulps(s, want[:, 0]).max() <= 1 and _ulps(c, want[:, 1]).max() <= 1
+
+
+# ------------------------------------------------------------------------------------------------
+def _bits(x):
+    return [int(v) for v in np.atleast_1d(np.asarray(x, dtype=np.float32)).view(np.uint32)]
+
+
+def _synthetic_vectors(oracle):
+    """a reference_vectors.json in the generator's format whose answers come from the ORACLE itself: it pins
+    nothing, it only proves that every consumer above runs (names of the oracle exports, record formats,
+    argument order) -- so that the day a real file arrives the tests compare instead of crashing"""
+    import ctypes as C
+
+    rng = np.random.default_rng(4)
+    L = oracle.lib()
+
+    def call(name, *arrs, n_out):
+        out = (C.c_float * n_out)()
+        getattr(L, name)(*[(C.c_float * len(a))(*[float(x) for x in a]) for a in arrs], out)
+        return np.array(list(out), dtype=np.float32)
+
+    def unit():
+        v = rng.normal(size=3)
+        return (v / np.linalg.norm(v)).astype(np.float32)
+
+    v = {k: [] for k in ("glam_from_scaled_axis", "glam_from_rotation_arc", "glam_mul_quat", "glam_mul_vec3", "glam_normalize_or_zero",
+                         "glam_project_onto", "glam_reject_from", "glam_from_rotation_y", "pitch_yaw", "rand_vec3", "rand_f32",
+                         "curve_f32", "curve_rgba", "cast_ray", "sin_cos")}
+    for _ in range(40):
+        a, b, x = unit(), unit(), rng.uniform(-2, 2, 3).astype(np.float32)
+        qa = call("fwo_quat_from_scaled_axis", x, n_out=4)
+        qb = call("fwo_quat_from_rotation_arc", a, b, n_out=4)
+        v["glam_from_scaled_axis"].append({"in": _bits(x), "out": _bits(qa)})
+        v["glam_from_rotation_arc"].append({"in": [_bits(a), _bits(b)], "out": _bits(qb)})
+        v["glam_mul_quat"].append({"in": [_bits(qa), _bits(qb)], "out": _bits(call("fwo_quat_mul", qa, qb, n_out=4))})
+        v["glam_mul_vec3"].append({"in": [_bits(qa), _bits(x)], "out": _bits(call("fwo_quat_mul_vec3", qa, x, n_out=3))})
+        v["glam_normalize_or_zero"].append({"in": _bits(x), "out": _bits(call("fwo_vec3_normalize_or_zero", x, n_out=3))})
+        v["glam_project_onto"].append({"in": [_bits(x), _bits(a)], "out": _bits(call("fwo_vec3_project_onto", x, a, n_out=3))})
+        v["glam_reject_from"].append({"in": [_bits(x), _bits(a)], "out": _bits(call("fwo_vec3_reject_from", x, a, n_out=3))})
+        uv = rng.uniform(0, 3, 2).astype(np.float32)
+        out = (C.c_float * 3)()
+        L.fwo_pitch_yaw_to_unit_vec(C.c_float(float(uv[0])), C.c_float(float(uv[1])), out)
+        v["pitch_yaw"].append({"in": _bits(uv), "out": _bits(list(out))})
+        x1 = np.float32(rng.uniform(-50, 50))
+        s, c = oracle.sincosf(np.array([x1], dtype=np.float32))
+        v["sin_cos"].append({"in": _bits(x1)[0], "out": _bits([s[0], c[0]])})
+    # the sampler families the build assumed (statistical sections)
+    d = unit()
+    spread, lo, hi = 0.6, 1.0, 3.0
+    ang = rng.uniform(0, spread, 4000)
+    az = rng.uniform(0, 2 * np.pi, 4000)
+    e1 = np.cross(d, [1.0, 0.0, 0.0])
+    e1 /= np.linalg.norm(e1)
+    e2 = np.cross(d, e1)
+    m = rng.uniform(lo, hi, 4000)
+    samples = (np.cos(ang)[:, None] * d + np.sin(ang)[:, None] * (np.cos(az)[:, None] * e1 + np.sin(az)[:, None] * e2)) * m[:, None]
+    v["rand_vec3"].append({"in": {"direction": _bits(d), "spread": _bits(spread)[0], "min": _bits(lo)[0], "max": _bits(hi)[0]},
+                           "out": [_bits(s_) for s_ in samples.astype(np.float32)]})
+    v["rand_f32"].append({"in": _bits([0.5, 2.5]), "out": _bits(rng.uniform(0.5, 2.5, 4000))})
+    # curves
+    from bevy_firework_b200 import FireworkCurve, FireworkGradient, LinearRgba
+
+    vals = rng.uniform(0, 2, 5).astype(np.float32)
+    knots = [(0.0, 1.0), (0.25, 0.5), (0.8, 2.0), (1.0, 0.0)]
+    cols = rng.uniform(0, 3, (4, 4)).astype(np.float32)
+    for t in (0.0, 0.25, 0.3, 0.5, 0.99, 1.0, 1.5, -0.5):
+        t32 = np.float32(t)
+        v["curve_f32"].append({"in": {"kind": "even", "values": _bits(vals), "t": _bits(t32)[0]},
+                               "out": _bits(oracle.sample_curve(FireworkCurve.even_samples([float(x) for x in vals]).to_pod(), float(t32)))})
+        v["curve_f32"].append({"in": {"kind": "uneven", "knots": [[_bits(a)[0], _bits(b)[0]] for a, b in knots], "t": _bits(t32)[0]},
+                               "out": _bits(oracle.sample_curve(FireworkCurve.uneven_samples(knots).to_pod(), float(t32)))})
+        v["curve_f32"].append({"in": {"kind": "constant", "value": _bits(0.7)[0], "t": _bits(t32)[0]},
+                               "out": _bits(oracle.sample_curve(FireworkCurve.constant(float(np.float32(0.7))).to_pod(), float(t32)))})
+        g_even = FireworkGradient.even_samples([LinearRgba(*[float(x) for x in c]) for c in cols])
+        g_un = FireworkGradient.uneven_samples([(float(np.float32(a)), LinearRgba(*[float(x) for x in c])) for (a, _), c in zip(knots, cols)])
+        v["curve_rgba"].append({"in": {"kind": "even", "values": [_bits(c) for c in cols], "t": _bits(t32)[0]},
+                                "out": _bits(oracle.sample_gradient(g_even.to_pod(), float(t32)))})
+        v["curve_rgba"].append({"in": {"kind": "uneven", "knots": [[_bits(a)[0], _bits(c)] for (a, _), c in zip(knots, cols)], "t": _bits(t32)[0]},
+                                "out": _bits(oracle.sample_gradient(g_un.to_pod(), float(t32)))})
+    # ray casts
+    shapes = {"cuboid": (_abi.FW_COLLIDER_CUBOID, [0.5, 1.0, 1.5]), "sphere": (_abi.FW_COLLIDER_SPHERE, [0.75, 0.0, 0.0]),
+              "cylinder": (_abi.FW_COLLIDER_CYLINDER, [0.6, 1.0, 0.0]), "cone": (_abi.FW_COLLIDER_CONE, [0.5, 0.6, 0.0]),
+              "capsule": (_abi.FW_COLLIDER_CAPSULE, [0.4, 0.75, 0.0])}
+    for name, (kind, he) in shapes.items():
+        for _ in range(60):
+            c = _abi.fw_collider()
+            c.kind, c.layers = kind, 1
+            c.half_extents[:] = he
+            tr = rng.uniform(-1, 1, 3).astype(np.float32)
+            q = rng.normal(size=4)
+            q = (q / np.linalg.norm(q)).astype(np.float32)
+            c.translation[:] = [float(x) for x in tr]
+            c.rotation[:] = [float(x) for x in q]
+            o = (tr + rng.uniform(-4, 4, 3)).astype(np.float32)
+            dd = (tr + rng.uniform(-0.5, 0.5, 3) - o)
+            dd = (dd / np.linalg.norm(dd)).astype(np.float32)
+            hit = oracle.cast_ray([c], [float(x) for x in o], [float(x) for x in dd], 10.0)
+            v["cast_ray"].append({"in": {"shape": name, "half_extents": _bits(he), "translation": _bits(tr), "rotation": _bits(q),
+                                         "origin": _bits(o), "direction": _bits(dd), "max_distance": _bits(10.0)[0]},
+                                  "out": None if hit is None else {"distance": _bits(hit[0])[0], "normal": _bits(hit[1])}})
+    return v
+
+
+def test_consumers_run_on_synthetic_vectors(oracle):
+    """every section of the (absent) reference_vectors.json is consumed without error when the file has the
+    generator's format; the answers here are the oracle's own, so this pins nothing (see _synthetic_vectors)"""
+    v = _synthetic_vectors(oracle)
+    test_glam(v, oracle)
+    test_pitch_yaw_and_rotation_y(v, oracle)
+    test_rand_vec3_family(v)
+    test_rand_f32_family(v)
+    test_curves(v, oracle)
+    test_cast_ray(v, oracle)
+    test_platform_sin_cos_against_fw_sincos(v, oracle)
