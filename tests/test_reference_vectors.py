@@ -261,11 +261,11 @@ def _synthetic_vectors(oracle):
     for t in (0.0, 0.25, 0.3, 0.5, 0.99, 1.0, 1.5, -0.5):
         t32 = np.float32(t)
         v["curve_f32"].append({"in": {"kind": "even", "values": _bits(vals), "t": _bits(t32)[0]},
-                               "out": _bits(oracle.sample_curve(FireworkCurve.even_samples([float(x) for x in vals]).to_pod(), float(t32)))})
+                               "out": _bits(oracle.sample_curve(FireworkCurve.even_samples([float(x) for x in vals]).to_pod(), float(t32)))[0]})
         v["curve_f32"].append({"in": {"kind": "uneven", "knots": [[_bits(a)[0], _bits(b)[0]] for a, b in knots], "t": _bits(t32)[0]},
-                               "out": _bits(oracle.sample_curve(FireworkCurve.uneven_samples(knots).to_pod(), float(t32)))})
+                               "out": _bits(oracle.sample_curve(FireworkCurve.uneven_samples(knots).to_pod(), float(t32)))[0]})
         v["curve_f32"].append({"in": {"kind": "constant", "value": _bits(0.7)[0], "t": _bits(t32)[0]},
-                               "out": _bits(oracle.sample_curve(FireworkCurve.constant(float(np.float32(0.7))).to_pod(), float(t32)))})
+                               "out": _bits(oracle.sample_curve(FireworkCurve.constant(float(np.float32(0.7))).to_pod(), float(t32)))[0]})
         g_even = FireworkGradient.even_samples([LinearRgba(*[float(x) for x in c]) for c in cols])
         g_un = FireworkGradient.uneven_samples([(float(np.float32(a)), LinearRgba(*[float(x) for x in c])) for (a, _), c in zip(knots, cols)])
         v["curve_rgba"].append({"in": {"kind": "even", "values": [_bits(c) for c in cols], "t": _bits(t32)[0]},
